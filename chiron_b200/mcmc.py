@@ -1,0 +1,417 @@
+"""MCMC moves, schedule and sampler with chiron's interface (`chiron/mcmc.py`).
+
+The control flow (two PRNG splits per Monte Carlo step, statistics, autotune and report cadence,
+accept-returns-new-state / reject-returns-same-state-with-advanced-key) follows the reference;
+proposals and energies run in libchiron_b200 kernels and the state copies the reference makes
+with `copy.deepcopy` are replaced by tensor clones of what actually changes.
+"""
+import copy
+import math
+from abc import abstractmethod
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, random, unit
+from .states import SamplerState, ThermodynamicState
+
+
+class MCMCMove:
+    """`mcmc.py:11-89`."""
+
+    def __init__(self, number_of_moves: int, reporter=None, report_interval: Optional[int] = 100):
+        self.number_of_moves = number_of_moves
+        self.reporter = reporter
+        self.report_interval = report_interval
+        self._move_iteration = 0
+        self._number_of_attempts_made = 0
+        if self.reporter is not None:
+            assert self.report_interval is not None
+
+    @abstractmethod
+    def update(self, sampler_state, thermodynamic_state, nbr_list=None):
+        pass
+
+    @property
+    def number_of_attemps_made(self):
+        return self._number_of_attempts_made
+
+
+class LangevinDynamicsMove(MCMCMove):
+    """`mcmc.py:91-199`."""
+
+    def __init__(self, timestep=1.0 * unit.femtoseconds, collision_rate=1.0 / unit.picoseconds,
+                 refresh_velocities: bool = False, reporter=None, report_interval: int = 100,
+                 number_of_steps: int = 1_000, save_traj_in_memory: bool = False):
+        super().__init__(number_of_moves=number_of_steps, reporter=reporter, report_interval=report_interval)
+        self.timestep = timestep
+        self.collision_rate = collision_rate
+        self.save_traj_in_memory = save_traj_in_memory
+        self.traj = []
+        from .integrators import LangevinIntegrator
+        self.integrator = LangevinIntegrator(
+            timestep=self.timestep, collision_rate=self.collision_rate,
+            refresh_velocities=refresh_velocities, report_interval=report_interval, reporter=reporter,
+            save_traj_in_memory=save_traj_in_memory)
+
+    def update(self, sampler_state, thermodynamic_state, nbr_list=None):
+        assert isinstance(sampler_state, SamplerState), \
+            f"Sampler state must be SamplerState, not {type(sampler_state)}"
+        assert isinstance(thermodynamic_state, ThermodynamicState), \
+            f"Thermodynamic state must be ThermodynamicState, not {type(thermodynamic_state)}"
+        updated_sampler_state, updated_nbr_list = self.integrator.run(
+            thermodynamic_state=thermodynamic_state, sampler_state=sampler_state,
+            number_of_steps=self.number_of_moves, nbr_list=nbr_list)
+        self._number_of_attempts_made += self.number_of_moves
+        if self.save_traj_in_memory:
+            self.traj.append(self.integrator.traj)
+            self.integrator.traj = []
+        self._move_iteration += 1
+        return updated_sampler_state, thermodynamic_state, updated_nbr_list
+
+
+def _shallow_state_copy(state: SamplerState) -> SamplerState:
+    """New SamplerState object sharing the (immutable-by-convention) array Quantities."""
+    new = copy.copy(state)
+    new._cache = dict(state._cache)
+    new._current_PRNG_key = np.array(state._current_PRNG_key, dtype=np.uint32)
+    return new
+
+
+def _copy_nbr_list(nbr_list):
+    """Equivalent of the reference's deepcopy of a list before rebuilding it: build() replaces the
+    arrays wholesale, so a shallow copy is enough."""
+    return copy.copy(nbr_list)
+
+
+class MCMove(MCMCMove):
+    """Metropolis loop shared by all Monte Carlo moves (`mcmc.py:202-548`)."""
+
+    def __init__(self, number_of_moves: int, reporter, report_interval: int = 1, autotune: bool = False,
+                 autotune_interval: int = 100, acceptance_method: str = "Metropolis-Hastings") -> None:
+        super().__init__(number_of_moves=number_of_moves, reporter=reporter, report_interval=report_interval)
+        self.acceptance_method = acceptance_method
+        self.reset_statistics()
+        self.autotune = autotune
+        self.autotune_interval = autotune_interval
+
+    def update(self, sampler_state, thermodynamic_state, nbr_list=None):
+        self._current_reduced_potential = None
+        for i in range(self.number_of_moves):
+            sampler_state, thermodynamic_state, nbr_list = self._step(sampler_state, thermodynamic_state, nbr_list)
+            self._number_of_attempts_made += 1
+            if getattr(self, "reporter", None) is not None:
+                if self._number_of_attempts_made % self.report_interval == 0:
+                    self._report(i, self._move_iteration, self._number_of_attempts_made,
+                                 self.n_accepted / self.n_proposed, sampler_state, thermodynamic_state, nbr_list)
+            if self.autotune:
+                if self._number_of_attempts_made % self.autotune_interval == 0 and self._number_of_attempts_made > 0:
+                    self._autotune()
+        self._move_iteration += 1
+        return sampler_state, thermodynamic_state, nbr_list
+
+    @abstractmethod
+    def _report(self, step, iteration, number_of_attempts_made, acceptance_probability, sampler_state,
+                thermodynamic_state, nbr_list=None):
+        pass
+
+    @abstractmethod
+    def _autotune(self):
+        pass
+
+    def _step(self, current_sampler_state, current_thermodynamic_state, current_nbr_list=None):
+        """`mcmc.py:357-463`."""
+        if self._current_reduced_potential is None:
+            current_reduced_potential = current_thermodynamic_state.get_reduced_potential(
+                current_sampler_state, current_nbr_list)
+            self._current_reduced_potential = current_reduced_potential
+        else:
+            current_reduced_potential = self._current_reduced_potential
+
+        (proposed_sampler_state, proposed_thermodynamic_state, proposed_reduced_potential,
+         log_proposal_ratio, proposed_nbr_list) = self._propose(
+            current_sampler_state, current_thermodynamic_state, current_reduced_potential, current_nbr_list)
+
+        # one host read per Monte Carlo step: the decision is made on the host like in the reference
+        log_ratio_host = float(log_proposal_ratio)
+        proposed_host = float(proposed_reduced_potential)
+        if math.isnan(proposed_host):
+            decision = False
+        else:
+            decision = self._accept_or_reject(log_ratio_host, proposed_sampler_state.new_PRNG_key,
+                                              acceptance_method=self.acceptance_method)
+        self._update_statistics(decision)
+        if decision:
+            self._current_reduced_potential = proposed_reduced_potential
+            return proposed_sampler_state, proposed_thermodynamic_state, proposed_nbr_list
+        current_sampler_state._current_PRNG_key = proposed_sampler_state._current_PRNG_key
+        return current_sampler_state, current_thermodynamic_state, current_nbr_list
+
+    def _update_statistics(self, decision):
+        if decision:
+            self.n_accepted += 1
+        self.n_proposed += 1
+
+    @property
+    def statistics(self):
+        return dict(n_accepted=self.n_accepted, n_proposed=self.n_proposed)
+
+    @statistics.setter
+    def statistics(self, value):
+        self.n_accepted = value["n_accepted"]
+        self.n_proposed = value["n_proposed"]
+
+    def reset_statistics(self):
+        self.n_accepted = 0
+        self.n_proposed = 0
+
+    @abstractmethod
+    def _propose(self, current_sampler_state, current_thermodynamic_state, current_reduced_potential,
+                 current_nbr_list=None):
+        pass
+
+    def _accept_or_reject(self, log_proposal_ratio, key, acceptance_method):
+        """`mcmc.py:531-548`: accept iff log_ratio >= 0 or uniform(key) < exp(log_ratio) (fp32)."""
+        if acceptance_method == "Metropolis-Hastings":
+            compare_to = random.uniform_host(key)
+            lr = np.float32(log_proposal_ratio)
+            with np.errstate(over="ignore"):
+                return bool(-lr <= 0.0 or compare_to < np.exp(lr, dtype=np.float32))
+
+
+class MonteCarloDisplacementMove(MCMove):
+    """Gaussian displacement of all particles (or `atom_subset`) (`mcmc.py:551-787`).
+
+    With `atom_subset` set, an `LJPotential` and a periodic list, the proposed energy is obtained
+    from the single-pass delta-energy kernel (only the moved particles' rows are evaluated);
+    `use_delta_energy=False` forces the reference's full re-evaluation.
+    """
+
+    def __init__(self, displacement_sigma=1.0 * unit.nanometer, number_of_moves: int = 100,
+                 atom_subset: Optional[List[int]] = None, report_interval: int = 1, reporter=None,
+                 autotune: bool = False, autotune_interval: int = 100,
+                 acceptance_method="Metropolis-Hastings", use_delta_energy: bool = True):
+        super().__init__(number_of_moves=number_of_moves, reporter=reporter, report_interval=report_interval,
+                         autotune=autotune, autotune_interval=autotune_interval,
+                         acceptance_method=acceptance_method)
+        self.displacement_sigma = displacement_sigma
+        self.atom_subset = atom_subset
+        self.atom_subset_mask = None
+        self.use_delta_energy = use_delta_energy
+        self._subset_ids = None
+
+    def _report(self, step, iteration, number_of_attempts_made, acceptance_probability, sampler_state,
+                thermodynamic_state, nbr_list=None):
+        potential = thermodynamic_state.potential.compute_energy(sampler_state.positions, nbr_list)
+        self.reporter.report({
+            "step": step,
+            "iteration": iteration,
+            "number_of_attempts_made": number_of_attempts_made,
+            "potential_energy": potential,
+            "displacement_sigma": self.displacement_sigma.value_in_unit_system(unit.md_unit_system),
+            "acceptance_probability": acceptance_probability,
+        })
+
+    def _autotune(self):
+        acceptance_ratio = self.n_accepted / self.n_proposed
+        if acceptance_ratio > 0.6:
+            self.displacement_sigma *= 1.1
+        elif acceptance_ratio < 0.4:
+            self.displacement_sigma /= 1.1
+
+    def _propose(self, current_sampler_state, current_thermodynamic_state, current_reduced_potential,
+                 current_nbr_list=None):
+        x = current_sampler_state.positions
+        n, dev = x.shape[0], x.device
+        if self.atom_subset is not None and self.atom_subset_mask is None:
+            m = torch.zeros(n, dtype=torch.float32, device=dev)
+            ids = torch.as_tensor(list(self.atom_subset), dtype=torch.long, device=dev)
+            m[ids] = 1.0
+            self.atom_subset_mask = m
+            self._subset_ids = ids.to(torch.int32).contiguous()
+
+        key = current_sampler_state.new_PRNG_key
+        sigma = float(self.displacement_sigma.value_in_unit_system(unit.md_unit_system))
+        proposed_sampler_state = _shallow_state_copy(current_sampler_state)
+        wrap = current_nbr_list is not None and current_nbr_list.space.periodic
+        if wrap:
+            lx, ly, lz = current_sampler_state.box_lengths_host()
+        else:
+            lx = ly = lz = 1.0
+        xp = torch.empty_like(x)
+        _lib.get_context(dev).call(
+            "chx_mc_displace", _lib.ptr(x), n, int(key[0]), int(key[1]), sigma,
+            _lib.ptr(self.atom_subset_mask), lx, ly, lz, int(wrap), _lib.ptr(xp))
+        proposed_sampler_state.positions = xp
+
+        if current_nbr_list is not None:
+            if current_nbr_list.check(xp):
+                proposed_nbr_list = _copy_nbr_list(current_nbr_list)
+                proposed_nbr_list.build(xp, proposed_sampler_state.box_vectors)
+            else:
+                proposed_nbr_list = current_nbr_list
+        else:
+            proposed_nbr_list = None
+
+        delta = self._delta_reduced_potential(x, xp, current_sampler_state, current_thermodynamic_state,
+                                              current_nbr_list)
+        if delta is not None:
+            proposed_reduced_potential = current_reduced_potential + delta
+        else:
+            proposed_reduced_potential = current_thermodynamic_state.get_reduced_potential(
+                proposed_sampler_state, proposed_nbr_list)
+        log_proposal_ratio = -proposed_reduced_potential + current_reduced_potential
+        return (proposed_sampler_state, current_thermodynamic_state, proposed_reduced_potential,
+                log_proposal_ratio, proposed_nbr_list)
+
+    def _delta_reduced_potential(self, x, xp, sampler_state, thermodynamic_state, nbr_list):
+        """beta * (U(new) - U(old)) from the subset delta-energy kernel, or None if not applicable."""
+        from .potential import LJPotential
+        pot = thermodynamic_state.potential
+        if not (self.use_delta_energy and self.atom_subset is not None and isinstance(pot, LJPotential)
+                and nbr_list is not None and nbr_list.space.periodic
+                and thermodynamic_state.temperature is not None):
+            return None
+        n, dev = x.shape[0], x.device
+        if len(self.atom_subset) * 8 > n:
+            return None
+        lx, ly, lz = sampler_state.box_lengths_host()
+        delta = torch.zeros((), dtype=torch.float64, device=dev)
+        _lib.get_context(dev).call(
+            "chx_lj_subset_delta_energy", _lib.ptr(x), _lib.ptr(xp), n, _lib.ptr(self._subset_ids),
+            int(self._subset_ids.shape[0]), lx, ly, lz, 1, pot.sigma, pot.epsilon, pot.cutoff, _lib.ptr(delta))
+        from .utils import kT_md
+        return (delta / kT_md(thermodynamic_state.temperature)).float()
+
+
+class MonteCarloBarostatMove(MCMove):
+    """Isotropic volume move (`mcmc.py:790-1009`)."""
+
+    def __init__(self, volume_max_scale=0.01, number_of_moves: int = 100, report_interval: int = 1,
+                 reporter=None, autotune: bool = False, autotune_interval: int = 100,
+                 acceptance_method="Metropolis-Hastings"):
+        super().__init__(number_of_moves=number_of_moves, reporter=reporter, report_interval=report_interval,
+                         autotune=autotune, autotune_interval=autotune_interval,
+                         acceptance_method=acceptance_method)
+        self.volume_max_scale = volume_max_scale
+
+    def _report(self, step, iteration, number_of_attempts_made, acceptance_probability, sampler_state,
+                thermodynamic_state, nbr_list=None):
+        potential = thermodynamic_state.potential.compute_energy(sampler_state.positions, nbr_list)
+        box = sampler_state.box_vectors
+        volume = box[0][0] * box[1][1] * box[2][2]
+        self.reporter.report({
+            "step": step,
+            "iteration": iteration,
+            "number_of_attempts_made": number_of_attempts_made,
+            "potential_energy": potential,
+            "volume": volume,
+            "box_vectors": box,
+            "max_volume_scale": self.volume_max_scale,
+            "acceptance_probability": acceptance_probability,
+        })
+
+    def _autotune(self):
+        acceptance_ratio = self.n_accepted / self.n_proposed
+        if acceptance_ratio < 0.25:
+            self.volume_max_scale /= 1.1
+        elif acceptance_ratio > 0.75:
+            self.volume_max_scale = min(self.volume_max_scale * 1.1, 0.3)
+
+    def _propose(self, current_sampler_state, current_thermodynamic_state, current_reduced_potential,
+                 current_nbr_list=None):
+        key = current_sampler_state.new_PRNG_key
+        nr_of_atoms = current_sampler_state.number_of_particles
+        x = current_sampler_state.positions
+        dev = x.device
+        f32 = np.float32
+        lx, ly, lz = (f32(t) for t in current_sampler_state.box_lengths_host())
+        # scalar arithmetic in fp32 on the host, mirroring mcmc.py:956-974
+        initial_volume = f32(f32(lx * ly) * lz)
+        delta_volume_max = f32(f32(self.volume_max_scale) * initial_volume)
+        delta_volume = f32(random.uniform_host(key, minval=-1, maxval=1) * delta_volume_max)
+        proposed_volume = f32(initial_volume + delta_volume)
+        length_scaling_factor = np.power(f32(proposed_volume / initial_volume), f32(1.0 / 3.0), dtype=f32)
+
+        proposed_sampler_state = _shallow_state_copy(current_sampler_state)
+        ctx = _lib.get_context(dev)
+        xp = torch.empty_like(x)
+        ctx.call("chx_scale", _lib.ptr(x), x.numel(), float(length_scaling_factor), _lib.ptr(xp))
+        box = current_sampler_state.box_vectors
+        boxp = torch.empty_like(box)
+        ctx.call("chx_scale", _lib.ptr(box.contiguous()), box.numel(), float(length_scaling_factor), _lib.ptr(boxp))
+        proposed_sampler_state.positions = xp
+        proposed_sampler_state.box_vectors = boxp
+
+        proposed_nbr_list = None
+        if current_nbr_list is not None:
+            proposed_nbr_list = _copy_nbr_list(current_nbr_list)
+            proposed_nbr_list.build(xp, boxp)
+
+        proposed_reduced_potential = current_thermodynamic_state.get_reduced_potential(
+            proposed_sampler_state, proposed_nbr_list)
+        log_volume = f32(f32(nr_of_atoms) * np.log(f32(proposed_volume / initial_volume), dtype=f32))
+        log_proposal_ratio = -(proposed_reduced_potential - current_reduced_potential) + float(log_volume)
+        return (proposed_sampler_state, current_thermodynamic_state, proposed_reduced_potential,
+                log_proposal_ratio, proposed_nbr_list)
+
+
+class RotamerMove(MCMove):
+    def _propose(self):
+        pass
+
+
+class ProtonationStateMove(MCMove):
+    def _propose(self):
+        pass
+
+
+class TautomericStateMove(MCMove):
+    def _propose(self):
+        pass
+
+
+# the names BASELINE.json uses (they survive in the reference's test function names only)
+MetropolisDisplacementMove = MonteCarloDisplacementMove
+MCBarostatMove = MonteCarloBarostatMove
+
+
+class MoveSchedule:
+    """`mcmc.py:1036-1071`."""
+
+    def __init__(self, move_schedule: List[Tuple[str, MCMCMove]]) -> None:
+        self.move_schedule = move_schedule
+        self._validate_sequence()
+
+    def _validate_sequence(self):
+        for move_name, move_class in self.move_schedule:
+            if not isinstance(move_class, MCMCMove):
+                raise ValueError(f"Move {move_name} in the sequence is not available.")
+
+
+class MCMCSampler:
+    """`mcmc.py:1074-1155`."""
+
+    def __init__(self, move_set: MoveSchedule):
+        from loguru import logger as log
+        log.info("Initializing MCMC sampler")
+        self.move = move_set
+
+    def run(self, sampler_state, thermodynamic_state, n_iterations: int = 1, nbr_list=None):
+        from loguru import logger as log
+        sampler_state = copy.deepcopy(sampler_state)
+        thermodynamic_state = copy.deepcopy(thermodynamic_state)
+        nbr_list = copy.deepcopy(nbr_list)
+        log.info("Running MCMC sampler")
+        for iteration in range(n_iterations):
+            log.info(f"Iteration {iteration + 1}/{n_iterations}")
+            for move_name, move in self.move.move_schedule:
+                log.debug(f"Performing: {move_name}")
+                sampler_state, thermodynamic_state, nbr_list = move.update(
+                    sampler_state, thermodynamic_state, nbr_list)
+        log.info("Finished running MCMC sampler")
+        for _, move in self.move.move_schedule:
+            if move.reporter is not None:
+                move.reporter.flush_buffer()
+        return sampler_state, thermodynamic_state, nbr_list

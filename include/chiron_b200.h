@@ -1,0 +1,208 @@
+/*
+ * chiron_b200.h -- C ABI of libchiron_b200.so, the sm_100a implementation of chiron's particle
+ * hot path (pair finding, LJ energy/force, BAOAB Langevin update, Metropolis move energies).
+ *
+ * chiron (choderalab/chiron) is pure Python on JAX and has no FFI of its own; the boundary this
+ * library replaces is the set of jitted methods of its duck-typed classes.  Every entry point
+ * below names the reference method it stands in for (file:line relative to the chiron repo).
+ * The Python classes in chiron_b200/ (same names/signatures as chiron's) are the only callers;
+ * INTEGRATION.md shows the ctypes stub a chiron maintainer would add.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes.  All array arguments are DEVICE pointers unless the
+ *    name ends in _host.  Positions / velocities / forces are float32 (N,3) row-major.
+ *    Particle ids are uint32 like the reference (neighbors.py:619,681).
+ *  - Orthorhombic boxes only, like the reference (neighbors.py:74-76 uses the diagonal):
+ *    box is passed as three floats lx, ly, lz; `periodic` = 0 selects
+ *    OrthogonalNonPeriodicSpace semantics (neighbors.py:115-175).
+ *  - A chx_ctx binds one device and one CUDA stream.  Every call enqueues work on that stream
+ *    and returns without synchronising, except where a host scalar is returned (documented
+ *    per function).  A context is not thread-safe; distinct contexts are independent.
+ *  - Return value: 0 = CHX_OK, negative = error (see enum); chx_last_error_string() has detail.
+ *    No C++ exception crosses the boundary.
+ *  - Predicates (d < cutoff, d < cutoff+skin, d >= skin/2) are evaluated with the reference's
+ *    exact fp32 operation order, so pair sets are bit-identical.
+ */
+#ifndef CHIRON_B200_H
+#define CHIRON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct chx_ctx chx_ctx;
+typedef struct chx_ljmd chx_ljmd;   /* fused LJ Langevin engine, see below */
+
+enum {
+    CHX_OK = 0,
+    CHX_BAD_ARG = -1,
+    CHX_NEIGHBOR_OVERFLOW = -2,
+    CHX_CELL_OVERFLOW = -3,
+    CHX_NAN_ENERGY = -4,
+    CHX_CUDA_ERROR = -5
+};
+
+int chx_version(void);
+const char* chx_last_error_string(void);
+
+/* One context per (device, stream).  `cuda_stream` is a cudaStream_t (NULL = legacy default). */
+int chx_context_create(int device, void* cuda_stream, chx_ctx** out);
+int chx_context_set_stream(chx_ctx* ctx, void* cuda_stream);
+int chx_context_destroy(chx_ctx* ctx);
+int chx_synchronize(chx_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long chx_launch_count(chx_ctx* ctx);
+
+/* ---- Space (chiron/neighbors.py:45-112 periodic, :116-175 non-periodic) ------------------------ */
+/* Space.displacement for n independent point pairs: r_out (n,3), d_out (n). */
+int chx_displacement(chx_ctx* ctx, const float* x1, const float* x2, long long n,
+                     float lx, float ly, float lz, int periodic, float* r_out, float* d_out);
+/* Space.wrap: out = x - floor(x/L)*L (identity when periodic == 0); out may alias x. */
+int chx_wrap(chx_ctx* ctx, const float* x, long long n, float lx, float ly, float lz,
+             int periodic, float* out);
+
+/* ---- NeighborListNsqrd (chiron/neighbors.py:446-907) -------------------------------------------- */
+/* build (neighbors.py:548-729): half Verlet list i<j, d < cutoff_plus_skin, ascending ids, first M
+ * entries, padded with the first neighbour (0 if none, +1 if that equals i); mask[k] = k < n_i.
+ * n_neighbors holds the UNTRUNCATED counts.  Synchronises: *max_count_host = max_i n_i and
+ * *count_eq_M_host = number of rows with n_i == M (the reference's growth trigger, :709).
+ * _nsq is the O(N^2) restatement; _cell is the O(N) counting-sort cell list producing the
+ * identical arrays (periodic only; falls back to _nsq when the box has < 3 cells per edge). */
+int chx_nlist_build_nsq(chx_ctx* ctx, const float* x, int n, float lx, float ly, float lz,
+                        int periodic, float cutoff_plus_skin, int M, uint32_t* neighbor_list,
+                        int32_t* neighbor_mask, int32_t* n_neighbors, int* max_count_host,
+                        int* count_eq_M_host);
+int chx_nlist_build_cell(chx_ctx* ctx, const float* x, int n, float lx, float ly, float lz,
+                         int periodic, float cutoff_plus_skin, int M, uint32_t* neighbor_list,
+                         int32_t* neighbor_mask, int32_t* n_neighbors, int* max_count_host,
+                         int* count_eq_M_host);
+/* calculate (neighbors.py:731-826): n_out (N), mask_out (N,M) = (d<cutoff)&pad, dist (N,M), r_ij (N,M,3). */
+int chx_nlist_calculate(chx_ctx* ctx, const float* x, int n, float lx, float ly, float lz,
+                        int periodic, float cutoff, int M, const uint32_t* neighbor_list,
+                        const int32_t* neighbor_mask, int32_t* n_out, int32_t* mask_out,
+                        float* dist_out, float* rij_out);
+/* check (neighbors.py:828-907): *flag_dev = any_i ||minimg(x_i - ref_i)|| >= skin/2.  Asynchronous;
+ * flag_dev is a device int the caller reads (or hands to the next kernel). */
+int chx_nlist_check(chx_ctx* ctx, const float* x, const float* ref_x, int n, float lx, float ly,
+                    float lz, int periodic, float half_skin, int32_t* flag_dev);
+
+/* ---- PairListNsqrd (chiron/neighbors.py:1018-1289) ---------------------------------------------- */
+/* build: all_pairs (N,N-1) = ids j != i ascending; reduction_mask (N,N-1) uint8 = i < j. */
+int chx_pairlist_build(chx_ctx* ctx, int n, uint32_t* all_pairs, uint8_t* reduction_mask);
+/* calculate: cutoff < 0 means "no cutoff" (_calc_distance_per_particle_no_cutoff, :1163-1216). */
+int chx_pairlist_calculate(chx_ctx* ctx, const float* x, int n, float lx, float ly, float lz,
+                           int periodic, float cutoff, int32_t* n_out, int32_t* mask_out,
+                           float* dist_out, float* rij_out);
+
+/* ---- Potentials (chiron/potential.py) ------------------------------------------------------------- */
+/* LJPotential.compute_energy / compute_force over a built NeighborListNsqrd
+ * (potential.py:193-213,263-300; force = -grad = potential.py:322-326 scattered to i and j).
+ * energy_dev (double, device, nullable) receives sum over listed pairs with d < cutoff of
+ * 4 eps ((s/d)^12 - (s/d)^6); force (N,3, nullable) is overwritten. */
+int chx_lj_nlist_energy_force(chx_ctx* ctx, const float* x, int n, float lx, float ly, float lz,
+                              int periodic, const uint32_t* neighbor_list,
+                              const int32_t* n_neighbors, int M, float sigma, float epsilon,
+                              float cutoff, double* energy_dev, float* force);
+/* All pairs i<j (PairListNsqrd path neighbors.py:1106-1216 + potential.py:272-279, and the
+ * nbr_list=None non-periodic path potential.py:26-63,235-258).  cutoff < 0 = no cutoff. */
+int chx_lj_allpairs_energy_force(chx_ctx* ctx, const float* x, int n, float lx, float ly, float lz,
+                                 int periodic, float sigma, float epsilon, float cutoff,
+                                 double* energy_dev, float* force);
+/* HarmonicOscillatorPotential (potential.py:413-418): 0.5 k sum (x - x0)^2 + U0; x0 is (n0,3) with
+ * n0 == n or n0 == 1 (broadcast); force = -k (x - x0). */
+int chx_ho_energy_force(chx_ctx* ctx, const float* x, int n, const float* x0, int n0, float k,
+                        float U0, double* energy_dev, float* force);
+/* Single-pass Metropolis delta energy for a displaced subset (new fast path; semantics of
+ * mcmc.py:733-777 restricted to atom_subset): for each moved particle m in `moved` (n_moved ids),
+ * sum over all j of u(x_new_m, x_j') - u(x_old_m, x_j), pairs inside the subset counted once.
+ * delta_dev (double) receives U(new) - U(old). */
+int chx_lj_subset_delta_energy(chx_ctx* ctx, const float* x_old, const float* x_new, int n,
+                               const uint32_t* moved, int n_moved, float lx, float ly, float lz,
+                               int periodic, float sigma, float epsilon, float cutoff,
+                               double* delta_dev);
+
+/* ---- jax.random, legacy threefry stream -------------------------------------- */
+/* random.split(key, 2) on the host: out_host[0..1] = carried key, out_host[2..3] = subkey. */
+int chx_threefry_split_host(const uint32_t key_host[2], uint32_t out_host[4]);
+/* random_bits(key, n) on the host (small n: scalar uniforms for the Metropolis test, mcmc.py:544). */
+int chx_random_bits_host(const uint32_t key_host[2], long long n, uint32_t* out_host);
+/* random.normal(key, (n,)) / random.uniform(key, (n,), lo, hi), bit-compatible layout. */
+int chx_random_normal(chx_ctx* ctx, uint32_t key0, uint32_t key1, long long n, float* out);
+int chx_random_uniform(chx_ctx* ctx, uint32_t key0, uint32_t key1, long long n, float lo,
+                       float hi, float* out);
+
+/* ---- BAOAB building blocks (chiron/integrators.py:174-195) for arbitrary potentials --------------- */
+/* One fused kernel for everything between two force evaluations of step t:
+ *   v += h F/m ; x += h v ; v = a v + b sqrt(kT/m) xi ; x += h v ; [wrap] ; [check vs ref_x]
+ * with h = dt/2 and xi = random.normal(subkey,(n,3)) generated in-kernel on the reference's
+ * stream.  `first_half_kick` = 0 skips the leading B (used to fuse the trailing B of step t-1:
+ * pass `trailing_kick` = 1 to apply v += h F/m before anything else).  flag_dev (nullable) is
+ * OR-ed with the rebuild condition of neighbors.py:864-868. */
+int chx_baoab_update(chx_ctx* ctx, float* x, float* v, const float* force, const float* mass,
+                     int n, float half_dt, float a, float b, float kT, uint32_t subkey0,
+                     uint32_t subkey1, int trailing_kick, float lx, float ly, float lz,
+                     int wrap_periodic, const float* ref_x, float half_skin, int32_t* flag_dev);
+/* v += h F/m (the trailing B of the last step). */
+int chx_kick(chx_ctx* ctx, float* v, const float* force, const float* mass, int n, float half_dt);
+/* Maxwell-Boltzmann velocities (utils.py:116-144): v = sqrt(kT/m) * normal(key,(n,3)). */
+int chx_init_velocities(chx_ctx* ctx, float* v, const float* mass, int n, float kT, uint32_t key0,
+                        uint32_t key1);
+
+/* ---- Monte Carlo proposals (chiron/mcmc.py:733-752, 956-983) -------------------------------------- */
+/* x_out = wrap(x + sigma * normal(key,(n,3)) * subset_mask[:,None]) ; subset_mask nullable (all). */
+int chx_mc_displace(chx_ctx* ctx, const float* x, int n, uint32_t key0, uint32_t key1,
+                    float sigma, const float* subset_mask, float lx, float ly, float lz,
+                    int wrap_periodic, float* x_out);
+/* x_out = x * s (barostat coordinate scaling). */
+int chx_scale(chx_ctx* ctx, const float* x, long long n_elems, float s, float* x_out);
+
+/* ---- Fused LJ Langevin engine (integrators.py:110-218 + neighbors.py + potential.py) -------------- */
+/* Runs whole trajectories on the device: cell-sorted particles, counting-sort cell list,
+ * tiled neighbour structure, fused BAOAB(+wrap+check) kernel, device-side rebuild decision.
+ * Produces the same positions / velocities / energies as the building blocks above. */
+typedef struct {
+    int n;                 /* particles */
+    float lx, ly, lz;      /* box */
+    float sigma, epsilon;  /* LJ parameters, md units */
+    float cutoff, skin;    /* nm; rebuild when any displacement >= skin/2 (neighbors.py:864) */
+    float dt, gamma, kT;   /* ps, 1/ps, kJ/mol */
+    int n_replicas;        /* >= 1: independent replicas batched in one launch (blockIdx.y) */
+    float internal_skin;   /* 0 = use `skin`; otherwise the (smaller) skin of the engine's own
+                              neighbour tables -- a tuning knob, results do not depend on it */
+} chx_ljmd_params;
+
+int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out);
+int chx_ljmd_destroy(chx_ljmd* md);
+/* Upload state (device pointers, original particle order): x (R,N,3); v (R,N,3); mass (N);
+ * kT_per_replica_host (R) nullable = params.kT for all.  Sorts, builds the neighbour tables
+ * (reference positions := x, like nbr_list.build_from_state, integrators.py:169) and evaluates
+ * the forces (integrators.py:171).  Synchronises. */
+int chx_ljmd_set_state(chx_ljmd* md, const float* x, const float* v, const float* mass,
+                       const float* kT_per_replica_host);
+/* Download state into original particle order; any pointer may be NULL. */
+int chx_ljmd_get_state(chx_ljmd* md, float* x, float* v, float* force, float* ref_x);
+/* Advance all replicas by nsteps BAOAB steps.  keys_host: (R,2) uint32 loop keys, updated in place
+ * to the keys after the loop (integrators.py:179).  energies_dev (double, (R, n_reports)) nullable:
+ * potential energy after every step with step % report_interval == 0 (integrators.py:197-205).
+ * Synchronises at the end. */
+int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_interval,
+                 double* energies_dev, int n_reports_capacity);
+/* Potential energy of the current positions per replica (double, device, (R)). Asynchronous. */
+int chx_ljmd_energy(chx_ljmd* md, double* energy_dev);
+/* Measurement hooks (bench.py roofline): launch the force kernel `repeats` times on the current
+ * positions (asynchronous); run an FFMA-chain microbenchmark and return the fp32 FLOP count it
+ * executed in *flops_host (asynchronous, time it with events on the context's stream). */
+int chx_ljmd_force_only(chx_ljmd* md, int repeats);
+int chx_fma_peak(chx_ctx* ctx, int iters, double* flops_host);
+/* Host statistics (8 values): [0]=table rebuilds, [1]=candidate pairs i<j (d<cutoff+internal skin)
+ * at the last build, [2]=interacting pairs i<j (d<cutoff) at the last energy evaluation,
+ * [3]=steps run, [4]=kernel launches, [5]=reference rebuild events (neighbors.py:903-905) summed
+ * over replicas, [6]=table capacity (tiles per block), [7]=blocks per replica.  Synchronises. */
+int chx_ljmd_stats(chx_ljmd* md, long long* stats_host8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHIRON_B200_H */

@@ -1,0 +1,583 @@
+"""GPU parity tests: every CUDA entry point (called through the C ABI via the Python mirror of
+chiron's classes) against the CPU oracle on identical seeded inputs, and against the reference's
+golden vectors.  Bar: bit-exact for lists / masks / counts / PRNG bits; energies, forces and
+trajectories within rel 1e-5 (the tolerance BASELINE.json states for fp32), written in each test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dynamics as dyn
+from oracle import jax_random as jr
+from oracle import pairs, potentials as pot
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+BOX10 = np.eye(3, dtype=f32) * 10
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _lj_system(n_side, rho_star, seed, sigma=0.34):
+    from chiron_b200 import unit
+    from chiron_b200.testsystems import LennardJonesFluid
+    lj = LennardJonesFluid(nparticles=n_side ** 3, reduced_density=rho_star, sigma=sigma * unit.nanometer, seed=seed)
+    x = np.asarray(lj.positions.value_in_unit(unit.nanometer), dtype=f32)
+    box = np.asarray(lj.box_vectors.value_in_unit(unit.nanometer), dtype=f32)
+    return lj, x, box
+
+
+# ---------------------------------------------------------------------------------------------------
+# Space, PRNG
+# ---------------------------------------------------------------------------------------------------
+def test_space_goldens_and_random_points(cuda_device, goldens):
+    from chiron_b200.neighbors import OrthogonalNonPeriodicSpace, OrthogonalPeriodicSpace
+    g = goldens["space_periodic"]
+    sp, sn = OrthogonalPeriodicSpace(), OrthogonalNonPeriodicSpace()
+    r, d = sp.displacement(np.array(g["p1"], f32), np.array(g["p2"], f32), BOX10)
+    assert np.array_equal(_np(r), np.array(g["r_ij"], f32)) and np.array_equal(_np(d), np.array(g["dist"], f32))
+    for a, b in zip(g["wrap_in"], g["wrap_out"]):
+        assert np.array_equal(_np(sp.wrap(np.array(a, f32), BOX10)), np.array(b, f32))
+    r, d = sn.displacement(np.array(g["p1"], f32), np.array(g["p2"], f32), BOX10)
+    assert np.array_equal(_np(r), np.array([[-1, 0, 0], [-6, 0, 0]], f32))
+    assert np.array_equal(_np(sn.wrap(np.array([11, -1, 2], f32), BOX10)), np.array([11, -1, 2], f32))
+    with pytest.raises(ValueError):
+        sp.displacement(np.zeros((1, 3), f32), np.zeros((1, 3), f32), None)
+    # random points, including far outside the box: bit-exact vs the oracle
+    rng = np.random.default_rng(3)
+    box = np.diag([3.1, 4.7, 2.9]).astype(f32)
+    a = (rng.normal(size=(5000, 3)) * 6).astype(f32)
+    b = (rng.normal(size=(5000, 3)) * 6).astype(f32)
+    r, d = sp.displacement(a, b, box)
+    ro, do = pairs.displacement(a, b, box)
+    assert np.array_equal(_np(r), ro) and np.array_equal(_np(d), do)
+    assert np.array_equal(_np(sp.wrap(a, box)), pairs.wrap(a, box))
+
+
+def test_threefry_stream_bit_exact(cuda_device):
+    from chiron_b200 import random as crandom
+    for seed, n in ((0, 1), (1234, 3), (7, 6), (99, 3001), (5, 30000)):
+        key = jr.PRNGKey(seed)
+        u = crandom.uniform(key, (n,), -1.0, 1.0)
+        assert np.array_equal(_np(u), jr.uniform(key, (n,), -1.0, 1.0))
+        z = _np(crandom.normal(key, (n,)))
+        zo = jr.normal(key, (n,))
+        # erfinv goes through log1p whose last bit differs between libm and CUDA: 2 ulp
+        assert np.allclose(z, zo, rtol=3e-7, atol=1e-7)
+    assert np.isclose(float(crandom.normal(jr.PRNGKey(0), (1,))[0]), -0.20584226, atol=1e-7)
+    assert np.isclose(float(crandom.normal(jr.PRNGKey(42), (1,))[0]), -0.18471177, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------
+# NeighborListNsqrd / PairListNsqrd
+# ---------------------------------------------------------------------------------------------------
+def _state(x, box, seed=1234):
+    from chiron_b200 import unit
+    from chiron_b200.states import SamplerState
+    from chiron_b200.utils import PRNG
+    PRNG.set_seed(seed)
+    return SamplerState(positions=unit.Quantity(x, unit.nanometer), current_PRNG_key=PRNG.get_random_key(),
+                        box_vectors=None if box is None else unit.Quantity(box, unit.nanometer))
+
+
+@pytest.mark.parametrize("builder", ["nsq", "cell"])
+def test_neighborlist_goldens(cuda_device, goldens, builder):
+    from chiron_b200 import unit
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    g = goldens["nlist_pair2"]
+    x = np.array([[0, 0, 0], [1, 0, 0]], f32)
+    state = _state(x, BOX10)
+    nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.1 * unit.nanometer, skin=0.1 * unit.nanometer,
+                           n_max_neighbors=5, builder=builder)
+    nl.build_from_state(state)
+    assert nl.is_built and np.array_equal(_np(nl.ref_positions), x) and np.array_equal(_np(nl.box_vectors), BOX10)
+    nl.build(state.positions, state.box_vectors)
+    assert _np(nl.neighbor_list).tolist() == g["neighbor_list"]
+    assert _np(nl.n_neighbors).tolist() == g["n_neighbors"]
+    assert _np(nl.neighbor_mask).tolist() == g["neighbor_mask"]
+    n, lst, mask, dist, rij = nl.calculate(x)
+    assert _np(n).tolist() == [1, 0] and tuple(lst.shape) == (2, 5)
+    assert _np(mask).tolist() == g["neighbor_mask"] and np.all(_np(dist) == 1.0)
+    assert np.all(_np(rij)[0] == np.array([-1, 0, 0], f32)) and np.all(_np(rij)[1] == np.array([1, 0, 0], f32))
+    assert nl.check(torch.as_tensor(x)) is False
+    assert nl.check(torch.as_tensor(x + f32(0.1))) is True
+    assert nl.check(torch.zeros(3, 3)) is True
+
+    c = goldens["nlist_cube8"]
+    grid = np.mgrid[0:2, 0:2, 0:2].astype(f32)
+    x8 = np.stack(grid.reshape(3, -1), axis=1).astype(f32)
+    state = _state(x8, BOX10)
+    nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=2.1 * unit.nanometer, skin=0.1 * unit.nanometer,
+                           n_max_neighbors=5, builder=builder)
+    nl.build_from_state(state)
+    assert _np(nl.n_neighbors).tolist() == c["n_neighbors"]
+    assert _np(nl.calculate(x8)[0]).tolist() == c["n_neighbors"]
+    nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.1 * unit.nanometer, skin=1.1 * unit.nanometer,
+                           n_max_neighbors=5, builder=builder)
+    nl.build_from_state(state)
+    n, lst, mask, dist, rij = nl.calculate(x8)
+    assert _np(n).tolist() == c["n_interacting_cutoff_1p1"]
+    assert tuple(lst.shape) == (8, 17) and _np(lst).tolist() == c["neighbor_list_8x17"]
+    # error contract (chiron/tests/test_pairs.py:163-237)
+    with pytest.raises(ValueError):
+        nl.build_from_state(_state(x8, None))
+    with pytest.raises(ValueError):
+        nl.build(x8, np.zeros((4, 3), f32))
+    with pytest.raises(ValueError):
+        nl.build(unit.Quantity(x8, unit.radian), BOX10)
+    with pytest.raises(ValueError):
+        nl.build(unit.Quantity(x8, unit.nanometer), unit.Quantity(BOX10, unit.radian))
+
+
+def _build_ref(x, box, cutoff, skin, M):
+    return pairs.build_neighborlist(x, box, cutoff, skin, M)
+
+
+@pytest.mark.parametrize("n_side,rho", [(6, 0.8), (10, 0.8), (10, 0.1)])
+def test_neighborlist_bit_exact_vs_oracle(cuda_device, n_side, rho):
+    """Lists, masks, counts and n_max growth identical to the oracle; cell builder == N^2 builder."""
+    from chiron_b200 import unit
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    _, x, box = _lj_system(n_side, rho, seed=11)
+    x = x + np.random.default_rng(5).normal(0, 0.05, x.shape).astype(f32)   # some outside the box
+    ref = _build_ref(x, box, 1.02, 0.5, 30)
+    out = {}
+    for builder in ("nsq", "cell"):
+        nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.02 * unit.nanometer, skin=0.5 * unit.nanometer,
+                               n_max_neighbors=30, builder=builder)
+        nl.build(x, box)
+        assert nl.n_max_neighbors == ref["n_max_neighbors"]
+        assert np.array_equal(_np(nl.n_neighbors), ref["n_neighbors"])
+        assert np.array_equal(_np(nl.neighbor_list).astype(np.uint32), ref["neighbor_list"])
+        assert np.array_equal(_np(nl.neighbor_mask), ref["neighbor_mask"])
+        out[builder] = nl
+    # calculate at displaced positions: bit-exact masks, distances and displacement vectors
+    x2 = pairs.wrap(x + np.random.default_rng(6).normal(0, 0.03, x.shape).astype(f32), box)
+    n, lst, mask, dist, rij = out["cell"].calculate(x2)
+    no, _, mo, do, ro = pairs.calculate_neighborlist(x2, box, 1.02, ref["neighbor_list"], ref["neighbor_mask"])
+    assert np.array_equal(_np(n), no) and np.array_equal(_np(mask), mo)
+    assert np.array_equal(_np(dist), do) and np.array_equal(_np(rij), ro)
+    assert out["cell"].check(torch.as_tensor(x2)) == pairs.check_neighborlist(x2, x, box, 0.5)
+    x3 = x.copy()
+    x3[7, 0] += f32(0.25)
+    assert out["cell"].check(torch.as_tensor(x3)) == pairs.check_neighborlist(x3, x, box, 0.5) is True
+
+
+def test_neighborlist_nonperiodic_and_empty_rows(cuda_device):
+    from chiron_b200 import unit
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalNonPeriodicSpace
+    rng = np.random.default_rng(2)
+    x = (rng.random((300, 3)) * 4).astype(f32)
+    x[0] = [50, 50, 50]          # particle 0 isolated: fill value rule (fill == i -> +1)
+    ref = pairs.build_neighborlist(x, None, 0.9, 0.3, 12, periodic=False)
+    nl = NeighborListNsqrd(OrthogonalNonPeriodicSpace(), cutoff=0.9 * unit.nanometer, skin=0.3 * unit.nanometer,
+                           n_max_neighbors=12)
+    nl.build(x, None)
+    assert np.array_equal(_np(nl.neighbor_list).astype(np.uint32), ref["neighbor_list"])
+    assert np.array_equal(_np(nl.n_neighbors), ref["n_neighbors"])
+    assert _np(nl.neighbor_list)[0, 0] == 1 and _np(nl.n_neighbors)[0] == 0
+
+
+def test_pairlist_goldens_and_oracle(cuda_device, goldens):
+    from chiron_b200 import unit
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace, PairListNsqrd
+    g = goldens["pairlist_cube8"]
+    grid = np.mgrid[0:2, 0:2, 0:2].astype(f32)
+    x8 = np.stack(grid.reshape(3, -1), axis=1).astype(f32)
+    pl = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=2.1 * unit.nanometer)
+    pl.build_from_state(_state(x8, BOX10))
+    assert pl.is_built and _np(pl.all_pairs).tolist() == g["all_pairs"]
+    n, ap, mask, dist, rij = pl.calculate(x8)
+    assert _np(n).tolist() == [7, 6, 5, 4, 3, 2, 1, 0] and tuple(mask.shape) == (8, 7)
+    assert np.allclose(_np(dist), np.array(g["distances"], f32), rtol=0, atol=1e-7)
+    nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=2.1 * unit.nanometer, skin=0.1 * unit.nanometer,
+                           n_max_neighbors=20)
+    nl.build_from_state(_state(x8, BOX10))
+    n1, _, m1, d1, _ = nl.calculate(x8)
+    assert float(torch.where(mask != 0, dist, 0 * dist).sum()) == float(torch.where(m1 != 0, d1, 0 * d1).sum())
+    x2 = np.array([[0, 0, 0], [1, 0, 0]], f32)
+    pl = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.1 * unit.nanometer)
+    pl.build_from_state(_state(x2, BOX10))
+    assert _np(pl.all_pairs).tolist() == [[1], [0]] and _np(pl.reduction_mask).tolist() == [[True], [False]]
+    n, ap, mask, dist, rij = pl.calculate(x2)
+    assert _np(n).tolist() == [1, 0] and _np(mask).tolist() == [[1], [0]] and _np(dist).tolist() == [[1.0], [1.0]]
+    assert _np(rij).tolist() == [[[-1.0, 0.0, 0.0]], [[1.0, 0.0, 0.0]]]
+    assert pl.check(torch.as_tensor(x2)) is False and pl.check(torch.zeros(3, 3)) is True
+    pl.cutoff = 0.5 * unit.nanometer
+    assert _np(pl.calculate(x2)[2]).tolist() == [[0], [0]]
+    pl.cutoff = None
+    assert _np(pl.calculate(x2)[2]).tolist() == [[1], [0]]
+    with pytest.raises(ValueError):
+        pl.calculate(np.zeros((3, 3), f32))
+    # random system vs oracle, bit exact
+    rng = np.random.default_rng(4)
+    x = (rng.random((97, 3)) * 3).astype(f32)
+    box = np.eye(3, dtype=f32) * 3
+    pl = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.0 * unit.nanometer)
+    pl.build(x, box)
+    apo, redo = pairs.build_pairlist(97)
+    no, _, mo, do, ro = pairs.calculate_pairlist(x, box, 1.0, apo, redo)
+    n, ap, mask, dist, rij = pl.calculate(x)
+    assert np.array_equal(_np(ap).astype(np.uint32), apo) and np.array_equal(_np(pl.reduction_mask), redo)
+    assert np.array_equal(_np(n), no) and np.array_equal(_np(mask), mo)
+    assert np.array_equal(_np(dist), do) and np.array_equal(_np(rij), ro)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Potentials
+# ---------------------------------------------------------------------------------------------------
+def test_lj_two_particles_like_reference_test(cuda_device):
+    """chiron/tests/test_potential.py:155-230."""
+    from chiron_b200 import unit
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    from chiron_b200.potential import LJPotential
+    sigma, epsilon, cutoff, skin = 1.0, 1.0, 3.0, 0.5
+    lj = LJPotential(None, unit.Quantity(sigma, unit.nanometer), unit.Quantity(epsilon, unit.kilojoules_per_mole),
+                     unit.Quantity(cutoff, unit.nanometer))
+    for i in range(1, 11):
+        x = np.array([[0, 0, 0], [i * 0.25 * 2 ** (1 / 6), 0, 0]], f32)
+        nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=unit.Quantity(cutoff, unit.nanometer),
+                               skin=unit.Quantity(skin, unit.nanometer), n_max_neighbors=5)
+        nl.build_from_state(_state(x, BOX10))
+        d = float(np.linalg.norm(x[0] - x[1]))
+        e_ref = 4.0 * epsilon * ((sigma / d) ** 12 - (sigma / d) ** 6) if d < cutoff else 0.0
+        f_ref = (24 * (epsilon / (d * d)) * (2 * (sigma / d) ** 12 - (sigma / d) ** 6)) * (x[0] - x[1]) if d < cutoff else 0 * x[0]
+        F_ref = np.array([f_ref, -f_ref])
+        assert np.isclose(float(lj.compute_energy(x)), e_ref, rtol=1e-5, atol=1e-8)
+        assert np.isclose(float(lj.compute_energy(x, nl)), e_ref, rtol=1e-5, atol=1e-8)
+        atol = 1e-5 * max(1.0, float(np.abs(F_ref).max()))
+        for F in (lj.compute_force(x), lj.compute_force(x, nl), lj.compute_force_analytical(x)):
+            assert np.allclose(_np(F), F_ref, rtol=1e-5, atol=atol)
+    with pytest.raises(ValueError):
+        nl2 = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=unit.Quantity(cutoff, unit.nanometer),
+                                skin=unit.Quantity(skin, unit.nanometer), n_max_neighbors=5)
+        lj.compute_energy(x, nl2)                       # not built
+    with pytest.raises(ValueError):
+        nl3 = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=unit.Quantity(2.0, unit.nanometer),
+                                skin=unit.Quantity(skin, unit.nanometer), n_max_neighbors=5)
+        nl3.build_from_state(_state(x, BOX10))
+        lj.compute_energy(x, nl3)                       # cutoff mismatch
+
+
+@pytest.mark.parametrize("n_side,rho", [(10, 0.8), (10, 0.1), (16, 0.8)])
+def test_lj_fluid_energy_force_vs_oracle(cuda_device, n_side, rho):
+    """Energy rel 1e-5; forces within 1e-5 of the force scale (max |F|), both list kinds."""
+    from chiron_b200 import unit
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace, PairListNsqrd
+    from chiron_b200.potential import LJPotential
+    lj_sys, x, box = _lj_system(n_side, rho, seed=21)
+    sigma, eps, rc = 0.34, 0.238 * 4.184, 1.02
+    lj = LJPotential(lj_sys.topology, lj_sys.sigma, lj_sys.epsilon, 1.02 * unit.nanometer)
+    nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.02 * unit.nanometer, skin=0.5 * unit.nanometer,
+                           n_max_neighbors=180, builder="cell")
+    nl.build(x, box)
+    x2 = pairs.wrap(x + np.random.default_rng(8).normal(0, 0.02, x.shape).astype(f32), box)
+    assert not nl.check(torch.as_tensor(x2))
+    e_ref, F_ref, n_int = pot.lj_energy_force_bruteforce(x2, box, sigma, eps, rc)
+    scale = float(np.abs(F_ref).max())
+    for lst in (nl, ):
+        e, F = lj.compute_energy_and_force(x2, lst)
+        assert np.isclose(float(e), e_ref, rtol=1e-5)
+        assert np.allclose(_np(F), F_ref, rtol=1e-5, atol=1e-5 * scale)
+        assert np.isclose(float(lj.compute_energy(x2, lst)), e_ref, rtol=1e-5)
+        assert np.allclose(_np(lj.compute_force(x2, lst)), F_ref, rtol=1e-5, atol=1e-5 * scale)
+    if n_side <= 10:
+        pl = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.02 * unit.nanometer)
+        pl.build(x, box)
+        e, F = lj.compute_energy_and_force(x2, pl)
+        assert np.isclose(float(e), e_ref, rtol=1e-5)
+        assert np.allclose(_np(F), F_ref, rtol=1e-5, atol=1e-5 * scale)
+        # oracle over the reference-shaped list gives the same numbers
+        ref = pairs.build_neighborlist(x, box, 1.02, 0.5, 180)
+        assert np.isclose(pot.lj_energy_nlist(x2, box, sigma, eps, rc, ref["neighbor_list"], ref["neighbor_mask"]),
+                          e_ref, rtol=1e-6)
+
+
+def test_harmonic_oscillator_goldens(cuda_device, goldens):
+    from chiron_b200 import unit
+    from chiron_b200.potential import HarmonicOscillatorPotential, IdealGasPotential
+    from chiron_b200.testsystems import HarmonicOscillator
+    g = goldens["ho_energies"]
+    ho = HarmonicOscillator()
+    p = HarmonicOscillatorPotential(ho.topology, g["k_kcal_per_mol_A2"] * unit.kilocalories_per_mole / unit.angstroms ** 2,
+                                    unit.Quantity(np.array([[0.0, 0.0, 0.0]]), unit.angstrom), 0.0 * unit.kilocalories_per_mole)
+    for pos, e in zip(g["positions_A"], g["energies"]):
+        x = (np.array([pos]) * 0.1).astype(f32)
+        assert np.isclose(float(p.compute_energy(x)), e, rtol=1e-5, atol=1e-8)
+    F = p.compute_force(x)
+    assert tuple(F.shape) == x.shape and np.allclose(_np(F), pot.ho_force(x, np.zeros((1, 3), f32), p.k), rtol=1e-6)
+    ig = IdealGasPotential(ho.topology)
+    assert ig.compute_energy(x) == 0.0 and float(ig.compute_force(x).abs().sum()) == 0.0
+
+
+def test_subset_delta_energy_matches_full_difference(cuda_device):
+    from chiron_b200 import _lib
+    _, x, box = _lj_system(10, 0.8, seed=31)
+    sigma, eps, rc = 0.34, 0.238 * 4.184, 1.02
+    rng = np.random.default_rng(1)
+    for moved in ([17], [3, 500, 999], list(range(40, 60))):
+        xn = x.copy()
+        xn[moved] += rng.normal(0, 0.01, (len(moved), 3)).astype(f32)
+        xn = pairs.wrap(xn, box)
+        e0, _, _ = pot.lj_energy_force_bruteforce(x, box, sigma, eps, rc, want_force=False)
+        e1, _, _ = pot.lj_energy_force_bruteforce(xn, box, sigma, eps, rc, want_force=False)
+        ctx = _lib.get_context()
+        xo_t, xn_t = _lib.as_device_f32(x), _lib.as_device_f32(xn)
+        ids = torch.as_tensor(moved, dtype=torch.int32, device=xo_t.device)
+        delta = torch.zeros((), dtype=torch.float64, device=xo_t.device)
+        ctx.call("chx_lj_subset_delta_energy", _lib.ptr(xo_t), _lib.ptr(xn_t), x.shape[0], _lib.ptr(ids), len(moved),
+                 float(box[0, 0]), float(box[1, 1]), float(box[2, 2]), 1, sigma, eps, rc, _lib.ptr(delta))
+        assert np.isclose(float(delta), e1 - e0, rtol=1e-5, atol=1e-5 * abs(e0) * 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Langevin: golden traces through the GPU path, single step, engine vs building blocks vs oracle
+# ---------------------------------------------------------------------------------------------------
+def _ho_run(k, dt_fs, nsteps, refresh):
+    from chiron_b200 import unit
+    from chiron_b200.integrators import LangevinIntegrator
+    from chiron_b200.potential import HarmonicOscillatorPotential
+    from chiron_b200.reporters import LangevinDynamicsReporter
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import HarmonicOscillator
+    from chiron_b200.utils import PRNG
+    ho = HarmonicOscillator()
+    potential = HarmonicOscillatorPotential(ho.topology, k, U0=ho.U0)
+    ts = ThermodynamicState(potential=potential, temperature=300 * unit.kelvin)
+    PRNG.set_seed(1234)
+    state = SamplerState(positions=ho.positions, current_PRNG_key=PRNG.get_random_key())
+    reporter = LangevinDynamicsReporter(f"ho_{nsteps}")
+    reporter.reset_reporter_file()
+    integ = LangevinIntegrator(timestep=dt_fs * unit.femtosecond, reporter=reporter, report_interval=1,
+                               refresh_velocities=refresh)
+    integ.run(state, ts, number_of_steps=nsteps)
+    return np.asarray(reporter.get_property("potential_energy"), dtype=np.float64).reshape(-1)
+
+
+def test_langevin_golden_traces_on_gpu(cuda_device, goldens, tmp_path):
+    """chiron/tests/test_mcmc.py:12-84 and chiron/tests/test_utils.py:53-113 through the CUDA path."""
+    from chiron_b200 import unit
+    from chiron_b200.reporters import BaseReporter
+    BaseReporter.set_directory(tmp_path)
+    e = _ho_run(100.0 * unit.kilocalories_per_mole / unit.angstrom ** 2, 2, 5, True)
+    assert np.allclose(e, np.array(goldens["langevin_ho_energy_trace"]["values"]), rtol=1e-5, atol=1e-8)
+    e = _ho_run(1.0 * unit.kilocalories_per_mole / unit.angstrom ** 2, 1, 20, False)
+    assert np.allclose(e, np.array(goldens["langevin_ho_energy_trace_20"]["values"]), rtol=1e-5, atol=1e-8)
+
+
+def _lj_langevin_setup(n_side, rho, seed, skin=0.5, builder="cell"):
+    from chiron_b200 import unit
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.utils import PRNG
+    lj_sys, x, box = _lj_system(n_side, rho, seed=seed)
+    potential = LJPotential(lj_sys.topology, lj_sys.sigma, lj_sys.epsilon, 1.02 * unit.nanometer)
+    PRNG.set_seed(1234)
+    state = SamplerState(positions=lj_sys.positions, current_PRNG_key=PRNG.get_random_key(),
+                         box_vectors=lj_sys.box_vectors)
+    ts = ThermodynamicState(potential=potential, temperature=300 * unit.kelvin)
+    nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.02 * unit.nanometer, skin=skin * unit.nanometer,
+                           n_max_neighbors=180, builder=builder)
+    return lj_sys, x, box, potential, state, ts, nl
+
+
+def _oracle_langevin(x, box, nsteps, skin=0.5, trace=None):
+    sigma, eps, rc = 0.34, 0.238 * 4.184, 1.02
+    nbr = dyn.OracleNeighborList(box, rc, skin, 180)
+    st = dyn.KeyedState(next(dyn.prng_stream(1234)))
+
+    def force(xx):
+        return pot.lj_force_nlist(xx, box, sigma, eps, rc, nbr.neighbor_list, nbr.neighbor_mask)
+
+    def energy(xx):
+        return pot.lj_energy_nlist(xx, box, sigma, eps, rc, nbr.neighbor_list, nbr.neighbor_mask)
+    xo, vo, key, en = dyn.langevin_run(x, None, np.full(x.shape[0], 39.948), 300.0, 0.001, 1.0, st, nsteps,
+                                       force, energy, report_interval=1, nbr=nbr, trace=trace)
+    return xo, vo, key, np.array(en), nbr, st
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_lj_langevin_single_and_few_steps_vs_oracle(cuda_device, fused, tmp_path):
+    """With the reference's jax.random stream a BAOAB step agrees within 1e-5 (BASELINE.json); after
+    10 steps positions / velocities / reported energies still agree to 1e-5 of their scale."""
+    from chiron_b200 import unit
+    from chiron_b200.integrators import LangevinIntegrator
+    from chiron_b200.reporters import BaseReporter, LangevinDynamicsReporter
+    BaseReporter.set_directory(tmp_path)
+    for nsteps in (1, 10):
+        lj_sys, x, box, potential, state, ts, nl = _lj_langevin_setup(8, 0.8, seed=41)
+        reporter = LangevinDynamicsReporter(f"lj_{fused}_{nsteps}")
+        reporter.reset_reporter_file()
+        integ = LangevinIntegrator(timestep=1.0 * unit.femtosecond, reporter=reporter, report_interval=1)
+        integ.use_fused_engine = fused
+        out, nl_out = integ.run(state, ts, number_of_steps=nsteps, nbr_list=nl)
+        assert integ.last_run_stats["path"] == ("fused" if fused else "blocks")
+        xo, vo, key, en, _, st = _oracle_langevin(x, box, nsteps)
+        xg, vg = _np(out.positions), _np(out.velocities)
+        dx = xg - xo
+        dx -= np.diag(box) * np.round(dx / np.diag(box))
+        assert np.abs(dx).max() < 1e-5 * float(np.diag(box).max())
+        assert np.allclose(vg, vo, rtol=1e-5, atol=1e-5 * float(np.abs(vo).max()))
+        assert np.array_equal(np.asarray(out.current_PRNG_key), key)
+        assert np.array_equal(np.asarray(out._current_PRNG_key), st.key)
+        eg = np.asarray(reporter.get_property("potential_energy"), dtype=np.float64).reshape(-1)
+        assert eg.shape == en.shape and np.allclose(eg, en, rtol=1e-5)
+
+
+def test_fused_engine_rebuild_events_match_oracle(cuda_device):
+    """Small skin so several rebuilds happen: the engine's reference-rebuild bookkeeping (count and
+    final ref_positions), the lazily materialised list, and the trajectory all follow the oracle."""
+    from chiron_b200 import unit
+    from chiron_b200.integrators import LangevinIntegrator
+    nsteps, skin = 60, 0.02
+    lj_sys, x, box, potential, state, ts, nl = _lj_langevin_setup(8, 0.8, seed=43, skin=skin)
+    integ = LangevinIntegrator(timestep=2.0 * unit.femtosecond)
+    out, nl_out = integ.run(state, ts, number_of_steps=nsteps, nbr_list=nl)
+    sigma, eps, rc = 0.34, 0.238 * 4.184, 1.02
+    nbr = dyn.OracleNeighborList(box, rc, skin, 180)
+    st = dyn.KeyedState(next(dyn.prng_stream(1234)))
+    force = lambda xx: pot.lj_force_nlist(xx, box, sigma, eps, rc, nbr.neighbor_list, nbr.neighbor_mask)  # noqa: E731
+    xo, vo, key, _ = dyn.langevin_run(x, None, np.full(x.shape[0], 39.948), 300.0, 0.002, 1.0, st, nsteps, force, nbr=nbr)
+    assert nbr.n_builds >= 3
+    assert integ.last_run_stats["reference_rebuilds"] == nbr.n_builds - 1
+    assert nl_out.n_builds == nbr.n_builds
+    dref = _np(nl_out.ref_positions) - nbr.ref
+    assert np.abs(dref).max() < 2e-4        # same rebuild step, positions equal to trajectory tolerance
+    dx = _np(out.positions) - xo
+    dx -= np.diag(box) * np.round(dx / np.diag(box))
+    assert np.abs(dx).max() < 5e-5 * float(np.diag(box).max())
+    # the list handed back is the list of its reference positions
+    ref = pairs.build_neighborlist(_np(nl_out.ref_positions), box, rc, skin, 180)
+    assert np.array_equal(_np(nl_out.n_neighbors), ref["n_neighbors"])
+    assert np.array_equal(_np(nl_out.neighbor_list).astype(np.uint32), ref["neighbor_list"])
+
+
+def test_fused_engine_force_and_energy_vs_bruteforce(cuda_device):
+    """Engine tables (Morton sort + tiles + bitmasks): forces/energy of the uploaded state equal the
+    all-pairs oracle; candidate-pair count equals the reference list size."""
+    from chiron_b200._engine import LJLangevinEngine
+    sigma, eps, rc = 0.34, 0.238 * 4.184, 1.02
+    for n_side, rho in ((8, 0.8), (12, 0.8), (10, 0.1), (16, 0.8)):
+        _, x, box = _lj_system(n_side, rho, seed=51)
+        n = x.shape[0]
+        eng = LJLangevinEngine(n, np.diag(box), sigma, eps, rc, 0.5, 0.001, 1.0, 2.494)
+        eng.set_state(x, np.zeros_like(x), np.full(n, 39.948, f32))
+        xs, vs, F, ref = eng.get_state(want_force=True, want_ref=True)
+        assert np.array_equal(_np(xs), x) and np.array_equal(_np(ref), x)
+        e_ref, F_ref, n_int = pot.lj_energy_force_bruteforce(x, box, sigma, eps, rc)
+        e = float(eng.energy()[0])
+        st = eng.stats()
+        assert np.isclose(e, e_ref, rtol=1e-5)
+        assert np.allclose(_np(F), F_ref, rtol=1e-5, atol=1e-5 * float(np.abs(F_ref).max()))
+        assert st["interacting_pairs"] == n_int
+        rows = pairs.neighbor_rows(x, box, rc + 0.5)
+        assert st["candidate_pairs"] == sum(r.size for r in rows)
+        eng.close()
+
+
+def test_fused_engine_batched_replicas(cuda_device):
+    """R replicas in one launch == R independent single-replica runs (bitwise)."""
+    from chiron_b200._engine import LJLangevinEngine
+    sigma, eps, rc = 0.34, 0.238 * 4.184, 1.02
+    R = 3
+    xs, keys, kts = [], [], [2.0, 2.494, 3.1]
+    for r in range(R):
+        _, x, box = _lj_system(8, 0.8, seed=60 + r)
+        xs.append(x)
+        keys.append(jr.PRNGKey(100 + r))
+    n = xs[0].shape[0]
+    mass = np.full(n, 39.948, f32)
+    v0 = [dyn.maxwell_boltzmann(jr.PRNGKey(7 + r), mass, 300.0) for r in range(R)]
+    eng = LJLangevinEngine(n, np.diag(box), sigma, eps, rc, 0.05, 0.002, 1.0, 2.494, n_replicas=R)
+    eng.set_state(np.stack(xs), np.stack(v0), mass, kts)
+    kout, en = eng.run(40, np.stack(keys), report_interval=10)
+    xb, vb, _, _ = eng.get_state()
+    eng.close()
+    for r in range(R):
+        e1 = LJLangevinEngine(n, np.diag(box), sigma, eps, rc, 0.05, 0.002, 1.0, kts[r])
+        e1.set_state(xs[r], v0[r], mass, [kts[r]])
+        k1, en1 = e1.run(40, keys[r], report_interval=10)
+        x1, v1, _, _ = e1.get_state()
+        assert np.array_equal(_np(xb)[r], _np(x1)) and np.array_equal(_np(vb)[r], _np(v1))
+        assert np.array_equal(kout[r], k1[0]) and np.array_equal(_np(en)[:, r], _np(en1)[:, 0])
+        e1.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Monte Carlo moves
+# ---------------------------------------------------------------------------------------------------
+def test_mc_barostat_golden(cuda_device, goldens, tmp_path):
+    """chiron/tests/test_mcmc.py:340-452: PE == 0, beta P V identity, n_accepted == 8 of 10."""
+    from chiron_b200 import unit
+    from chiron_b200.mcmc import MonteCarloBarostatMove
+    from chiron_b200.neighbors import OrthogonalPeriodicSpace, PairListNsqrd
+    from chiron_b200.potential import IdealGasPotential
+    from chiron_b200.reporters import BaseReporter, MCReporter
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import _topology
+    from chiron_b200.utils import PRNG
+    BaseReporter.set_directory(tmp_path)
+    reporter = MCReporter(1)
+    move = MonteCarloBarostatMove(volume_max_scale=0.1, number_of_moves=10, reporter=reporter, report_interval=1)
+    x = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [1, 0, 1], [0, 1, 1], [1, 1, 1]], f32)
+    PRNG.set_seed(1234)
+    state = SamplerState(positions=x * unit.nanometer, box_vectors=BOX10 * unit.nanometer,
+                         current_PRNG_key=PRNG.get_random_key())
+    ts = ThermodynamicState(potential=IdealGasPotential(_topology(8)), temperature=300 * unit.kelvin,
+                            pressure=1.0 * unit.atmosphere)
+    nl = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=0 * unit.nanometer)
+    state, ts, nl = move.update(state, ts, nl)
+    pe = reporter.get_property("potential_energy")
+    vol = reporter.get_property("volume")
+    assert pe[0] == 0 and pe[-1] == 0
+    assert np.isclose(float(ts.get_reduced_potential(state)),
+                      float(ts.pressure * ts.beta * (float(vol[-1]) * unit.nanometer ** 3)), rtol=1e-3)
+    g = goldens["mc_barostat_counts"]
+    assert move.statistics["n_proposed"] == g["n_proposed"]
+    assert move.statistics["n_accepted"] == g["n_accepted"]
+
+
+def test_mc_displacement_lj_vs_oracle(cuda_device):
+    """MonteCarloDisplacementMove on an LJ fluid: the accept/reject sequence, final positions and key
+    follow the oracle (decisions are identical unless a uniform lands within fp32 noise of the
+    threshold, which this seed does not hit)."""
+    from chiron_b200 import unit
+    from chiron_b200.mcmc import MonteCarloDisplacementMove
+    lj_sys, x, box, potential, state, ts, nl = _lj_langevin_setup(6, 0.8, seed=71, builder="nsq")
+    nl.build_from_state(state)
+    move = MonteCarloDisplacementMove(displacement_sigma=0.0005 * unit.nanometer, number_of_moves=12)
+    out, _, nl_out = move.update(state, ts, nl)
+    sigma, eps, rc = 0.34, 0.238 * 4.184, 1.02
+    nbr = dyn.OracleNeighborList(box, rc, 0.5, 180)
+    nbr.build(x)
+    st = dyn.KeyedState(next(dyn.prng_stream(1234)))
+    red = lambda xx, b: dyn.reduced_potential(  # noqa: E731
+        pot.lj_energy_nlist(xx, box, sigma, eps, rc, nbr.neighbor_list, nbr.neighbor_mask), 300.0)
+    xo, u, acc = x, red(x, box), 0
+    for _ in range(12):
+        xo, u, a = dyn.mc_displacement_step(xo, box, st, 0.0005, u, red, nbr=nbr)
+        acc += a
+    assert 0 < acc < 12
+    assert move.statistics == dict(n_accepted=acc, n_proposed=12)
+    assert np.allclose(_np(out.positions), xo, rtol=0, atol=2e-6)
+    assert np.array_equal(np.asarray(out._current_PRNG_key), st.key)
+
+
+def test_mc_displacement_subset_delta_path(cuda_device):
+    """atom_subset moves through the single-pass delta-energy kernel == full re-evaluation path."""
+    from chiron_b200 import unit
+    from chiron_b200.mcmc import MonteCarloDisplacementMove
+    res = []
+    for use_delta in (True, False):
+        lj_sys, x, box, potential, state, ts, nl = _lj_langevin_setup(8, 0.8, seed=73, builder="cell")
+        nl.build_from_state(state)
+        move = MonteCarloDisplacementMove(displacement_sigma=0.01 * unit.nanometer, number_of_moves=30,
+                                          atom_subset=[5], use_delta_energy=use_delta)
+        out, _, _ = move.update(state, ts, nl)
+        res.append((move.statistics["n_accepted"], _np(out.positions)))
+    assert res[0][0] == res[1][0] and 0 < res[0][0] < 30
+    assert np.array_equal(res[0][1], res[1][1])
+    moved = np.nonzero(np.any(res[0][1] != x, axis=1))[0]
+    assert moved.tolist() == [5]
