@@ -24,10 +24,12 @@
 
 #define FULL 0xffffffffu
 #define IMG_NONE 13u  // image code of "no shift": (1,1,1) in base 3
+#define HALT_NONE 0x7f7f7f7f  // cudaMemset-able "no halt" value of MdCtrl::halt_step
 
 struct MdCtrl {
-    int halt;            // set by the BAOAB kernel when the internal list must be rebuilt
-    int halt_step;       // step at which it was raised
+    int halt_step;       // first step whose BAOAB update invalidated the internal tables
+                         // (HALT_NONE = none); kernels of later steps turn into no-ops
+    int pad1;
     int overflow;        // table capacity exceeded during a build
     int pad0;
     unsigned long long cand_pairs2;  // sum of mask popcounts at the last build (= 2 * P_cand)
@@ -63,6 +65,7 @@ struct chx_ljmd {
     uint32_t* tiles;
     int* ntiles;
     uint8_t* generic;
+    float4* bcenter;          // per block: centre of its bounding box at the last build
     int tcap;
     MdCtrl* ctrl;
     MdRep* rep;
@@ -261,7 +264,8 @@ __device__ __forceinline__ float axis_gap(float v, float lo, float hi) {
 __global__ void __launch_bounds__(BW * 32)
 k_md_build(const float4* __restrict__ xs_all, const int* __restrict__ start_all, MdGeom g, float R,
            int tcap, uint32_t* __restrict__ tiles_all, int* __restrict__ ntiles_all,
-           uint8_t* __restrict__ generic_all, MdCtrl* __restrict__ ctrl) {
+           uint8_t* __restrict__ generic_all, float4* __restrict__ bcenter_all, float drift,
+           MdCtrl* __restrict__ ctrl) {
     __shared__ uint32_t queue[BW][QCAP];
     __shared__ uint32_t idxbuf[BW][32];
     const int r = blockIdx.y;
@@ -287,8 +291,10 @@ k_md_build(const float4* __restrict__ xs_all, const int* __restrict__ start_all,
     if (nx >= g.ncx) { nx = g.ncx; c0x = 0; gen = true; }
     if (ny >= g.ncy) { ny = g.ncy; c0y = 0; gen = true; }
     if (nz >= g.ncz) { nz = g.ncz; c0z = 0; gen = true; }
-    if (0.5f * (hix - lox) + Rm >= g.box.hx || 0.5f * (hiy - loy) + Rm >= g.box.hy ||
-        0.5f * (hiz - loz) + Rm >= g.box.hz)
+    // non-generic blocks resolve periodic images per TILE (force kernel): everything the block can
+    // interact with until the next rebuild must stay within half a box of the block centre
+    if (0.5f * (hix - lox) + Rm + drift >= g.box.hx || 0.5f * (hiy - loy) + Rm + drift >= g.box.hy ||
+        0.5f * (hiz - loz) + Rm + drift >= g.box.hz)
         gen = true;
     const int total = nx * ny * nz;
     const float Rm2 = Rm * Rm;
@@ -399,6 +405,7 @@ k_md_build(const float4* __restrict__ xs_all, const int* __restrict__ start_all,
     if (lane == 0) {
         ntiles_all[(size_t)r * g.nblk + b] = min((nslots + 31) >> 5, tcap);
         generic_all[(size_t)r * g.nblk + b] = gen ? 1 : 0;
+        bcenter_all[(size_t)r * g.nblk + b] = make_float4(0.5f * (lox + hix), 0.5f * (loy + hiy), 0.5f * (loz + hiz), 0.f);
         if (ovf) atomicExch(&ctrl->overflow, 1);
     }
 #pragma unroll
@@ -423,13 +430,14 @@ template <bool ENERGY>
 __global__ void __launch_bounds__(FW * 32)
 k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
            float4* __restrict__ refu_all, const uint32_t* __restrict__ tiles_all,
-           const int* __restrict__ ntiles_all, const uint8_t* __restrict__ generic_all, MdGeom g,
-           LjConst lj, int tcap, MdCtrl* __restrict__ ctrl, MdRep* __restrict__ rep, int step,
+           const int* __restrict__ ntiles_all, const uint8_t* __restrict__ generic_all,
+           const float4* __restrict__ bcenter_all, MdGeom g, LjConst lj, int tcap, MdCtrl* __restrict__ ctrl, MdRep* __restrict__ rep, int step,
            int honor_halt, double* __restrict__ energy_out) {
     __shared__ uint32_t sj[FW][32];
     __shared__ double red[FW];
     __shared__ unsigned long long redn[FW];
-    if (honor_halt && *((volatile int*)&ctrl->halt)) return;
+    // the tables are stale from step halt_step on: that step's forces are evaluated after the rebuild
+    if (honor_halt && *((volatile int*)&ctrl->halt_step) <= step) return;
     const int r = blockIdx.y;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * FW + w;
@@ -438,14 +446,24 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
     if (b < g.nblk) {
         const float4* xs = xs_all + (size_t)r * g.np;
         const int i = b * 32 + lane;
-        const float4 xi = xs[i];
+        const float4 xi0 = xs[i];
+        float4 xi = xi0;
         if (rep[r].user_step == step) {  // reference rebuild (neighbors.py:903-905 -> build)
-            refu_all[(size_t)r * g.np + i] = xi;
+            refu_all[(size_t)r * g.np + i] = xi0;
             if (b == 0 && lane == 0) rep[r].user_rebuilds++;
         }
         const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * tcap * 64;
         const int nt = ntiles_all[(size_t)r * g.nblk + b];
         const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
+        // positions are wrapped every step (integrators.py:239), so a particle may have jumped by a
+        // box length since the build: images are resolved against the block centre, once per
+        // particle per tile instead of once per pair
+        const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
+        if (!gen) {
+            xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
+            xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
+            xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
+        }
         float fx = 0.f, fy = 0.f, fz = 0.f;
         for (int t = 0; t < nt; ++t, tp += 64) {
             const uint32_t code = tp[lane];
@@ -455,10 +473,9 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
             __syncwarp();
             sj[w][lane] = (uint32_t)j;
             if (!gen) {
-                const int ic = (int)(code >> 24);
-                xj.x += (float)(ic / 9 - 1) * g.box.lx;
-                xj.y += (float)((ic / 3) % 3 - 1) * g.box.ly;
-                xj.z += (float)(ic % 3 - 1) * g.box.lz;
+                xj.x -= g.box.lx * rintf((xj.x - bc.x) * g.inv_lx);
+                xj.y -= g.box.ly * rintf((xj.y - bc.y) * g.inv_ly);
+                xj.z -= g.box.lz * rintf((xj.z - bc.z) * g.inv_lz);
             }
             __syncwarp();
             while (__any_sync(FULL, m != 0u)) {
@@ -480,7 +497,7 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
                     // within a few ulps of the cutoff: decide with the reference's exact predicate
                     const float4 xo = xs[sj[w][bit]];
                     float rx, ry, rz, d;
-                    ref_displacement<true>(xi.x, xi.y, xi.z, xo.x, xo.y, xo.z, g.box, rx, ry, rz, d);
+                    ref_displacement<true>(xi0.x, xi0.y, xi0.z, xo.x, xo.y, xo.z, g.box, rx, ry, rz, d);
                     in = d < lj.rc;
                 }
                 if (in) {
@@ -519,7 +536,8 @@ k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float
            float h, float a, float b, float half_skin_user, float half_skin_int2, int step,
            int trailing, MdCtrl* __restrict__ ctrl, MdRep* __restrict__ rep) {
     __shared__ uint32_t sk[2];
-    if (*((volatile int*)&ctrl->halt)) return;
+    // a halt raised by ANOTHER block of this same launch (halt_step == step) must not stop us
+    if (*((volatile int*)&ctrl->halt_step) < step) return;
     const int r = blockIdx.y;
     if (threadIdx.x == 0) {
         uint32_t c0, c1, s0, s1;
@@ -575,7 +593,7 @@ k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float
     const int any_int = __syncthreads_or(moved_int);
     const int any_user = __syncthreads_or(moved_user);
     if (threadIdx.x == 0) {
-        if (any_int) { ctrl->halt_step = step; ctrl->halt = 1; }
+        if (any_int) atomicMin(&ctrl->halt_step, step);
         if (any_user) rep[r].user_step = step;
     }
 }
@@ -613,6 +631,7 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->tiles, nb * md->tcap * 64 * sizeof(uint32_t)));
     CHX_CUDA(cudaMalloc(&md->ntiles, nb * sizeof(int)));
     CHX_CUDA(cudaMalloc(&md->generic, nb));
+    CHX_CUDA(cudaMalloc(&md->bcenter, nb * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->ctrl, sizeof(MdCtrl)));
     CHX_CUDA(cudaMalloc(&md->rep, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMalloc(&md->e_scratch, md->R * sizeof(double)));
@@ -662,7 +681,8 @@ static int md_rebuild(chx_ljmd* md) {
         CHX_CUDA(cudaMemsetAsync(&md->ctrl->overflow, 0, sizeof(int), st));
         CHX_CUDA(cudaMemsetAsync(&md->ctrl->cand_pairs2, 0, sizeof(unsigned long long), st));
         k_md_build<<<dim3(chx_div_up(g.nblk, BW), R), BW * 32, 0, st>>>(
-            md->xs[b], md->cell_start, g, R_list, md->tcap, md->tiles, md->ntiles, md->generic, md->ctrl);
+            md->xs[b], md->cell_start, g, R_list, md->tcap, md->tiles, md->ntiles, md->generic, md->bcenter,
+            md->internal_skin, md->ctrl);
         CHX_LAUNCHED(ctx);
         CHX_CUDA(cudaMemcpyAsync(md->ctrl_host, md->ctrl, sizeof(MdCtrl), cudaMemcpyDeviceToHost, st));
         CHX_CUDA(cudaStreamSynchronize(st));
@@ -684,11 +704,11 @@ static int md_force(chx_ljmd* md, int step, bool energy, int honor_halt, double*
     const int c = md->cur;
     if (energy)
         k_md_force<true><<<gf, FW * 32, 0, md->ctx->stream>>>(
-            md->xs[c], md->fs, md->refu[c], md->tiles, md->ntiles, md->generic, g, md_lj(md), md->tcap,
+            md->xs[c], md->fs, md->refu[c], md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md), md->tcap,
             md->ctrl, md->rep, step, honor_halt, e_dev);
     else
         k_md_force<false><<<gf, FW * 32, 0, md->ctx->stream>>>(
-            md->xs[c], md->fs, md->refu[c], md->tiles, md->ntiles, md->generic, g, md_lj(md), md->tcap,
+            md->xs[c], md->fs, md->refu[c], md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md), md->tcap,
             md->ctrl, md->rep, step, honor_halt, e_dev);
     CHX_LAUNCHED(md->ctx);
     return CHX_OK;
@@ -747,7 +767,7 @@ int chx_ljmd_destroy(chx_ljmd* md) {
     for (int k = 0; k < 2; ++k) { cudaFree(md->xs[k]); cudaFree(md->vs[k]); cudaFree(md->refu[k]); }
     cudaFree(md->fs); cudaFree(md->refi); cudaFree(md->cell_count); cudaFree(md->cell_start);
     cudaFree(md->cell_of); cudaFree(md->order); cudaFree(md->tiles); cudaFree(md->ntiles);
-    cudaFree(md->generic); cudaFree(md->ctrl); cudaFree(md->rep); cudaFree(md->e_scratch);
+    cudaFree(md->generic); cudaFree(md->bcenter); cudaFree(md->ctrl); cudaFree(md->rep); cudaFree(md->e_scratch);
     cudaFreeHost(md->ctrl_host); cudaFreeHost(md->rep_host);
     delete md;
     return CHX_OK;
@@ -811,7 +831,7 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
         md->rep_host[r].user_step = -1;
     }
     CHX_CUDA(cudaMemcpyAsync(md->rep, md->rep_host, R * sizeof(MdRep), cudaMemcpyHostToDevice, st));
-    CHX_CUDA(cudaMemsetAsync(&md->ctrl->halt, 0, 2 * sizeof(int), st));
+    CHX_CUDA(cudaMemsetAsync(&md->ctrl->halt_step, 0x7f, sizeof(int), st));
     if (report) CHX_CUDA(cudaMemsetAsync(energies_dev, 0, sizeof(double) * R * n_reports, st));
 
     const float dt = md->p.dt, gamma = md->p.gamma;
@@ -845,11 +865,11 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
         }
         CHX_CUDA(cudaMemcpyAsync(md->ctrl_host, md->ctrl, sizeof(MdCtrl), cudaMemcpyDeviceToHost, st));
         CHX_CUDA(cudaStreamSynchronize(st));
-        if (!md->ctrl_host->halt) { t += chunk; continue; }
         const int hs = md->ctrl_host->halt_step;
+        if (hs == HALT_NONE) { t += chunk; continue; }
         int rc = md_rebuild(md);
         if (rc != CHX_OK) return rc;
-        CHX_CUDA(cudaMemsetAsync(&md->ctrl->halt, 0, 2 * sizeof(int), st));
+        CHX_CUDA(cudaMemsetAsync(&md->ctrl->halt_step, 0x7f, sizeof(int), st));
         rc = force_at(hs, 0);
         if (rc != CHX_OK) return rc;
         t = hs + 1;
