@@ -244,7 +244,16 @@ def run_ours(args):
     st1 = eng.stats()
     e_now = float(eng.energy()[0])
     st_e = eng.stats()
-    p_cand, p_int = st_e["candidate_pairs"], st_e["interacting_pairs"]
+    p_int, p_cand_internal = st_e["interacting_pairs"], st_e["candidate_pairs"]
+    # P_cand of SURVEY.md section 8d: size of the REFERENCE Verlet list (i<j, d < rc+skin, exact
+    # predicate) for the current positions, from the reference-shaped cell-list builder
+    ref_list = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=RC * unit.nanometer, skin=SKIN * unit.nanometer,
+                                 n_max_neighbors=400, builder="cell")
+    x_now = eng.get_state()[0]
+    ref_list.build(x_now, box)
+    p_cand = int(ref_list.n_neighbors.sum().item())
+    del ref_list
+    torch.cuda.empty_cache()
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -336,10 +345,10 @@ def run_ours(args):
                        "parallelism": "1 independent system per GPU (replicas only)",
                        "l2": "working set (tiles %.0f MB + state) exceeds nothing to flush: inputs are produced by the previous step"
                              % (st_e["blocks"] * st_e["tile_capacity"] * 256 / 1e6),
-                       "internal_skin_nm": args.internal_skin or SKIN},
+                       "internal_skin_nm": args.internal_skin or round(0.35 * SIGMA, 4)},
             "pair_interactions_per_s": p_int * steps_per_s / world * world,
             "pair_tests_per_s": p_cand * steps_per_s,
-            "p_cand": p_cand, "p_int": p_int, "potential_energy_kj_mol": e_now,
+            "p_cand": p_cand, "p_int": p_int, "p_cand_internal_tables": p_cand_internal, "potential_energy_kj_mol": e_now,
             "table_rebuilds_in_timed_region": rebuilds,
             "ms_per_baoab_step": ms_max / (K * S),
             "clocks": clocks.summary(),

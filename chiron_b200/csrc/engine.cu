@@ -8,49 +8,53 @@
 //   fs   float4  force,    w = per-particle potential energy (half of each pair)
 //   refi float4  positions at the last internal rebuild     (drives the engine's own rebuild)
 //   refu float4  positions at the last REFERENCE rebuild    (what nbr_list.ref_positions holds)
-// Particles are kept sorted by the Morton code of a fine cell grid (~4 particles per cell), so a
-// "block" of 32 consecutive particles is a compact blob handled by one warp.
+// Particles are kept sorted along a Hilbert curve through a 2^b x 2^b x 2^b cell grid (~8 particles
+// per cell), so a "block" of 32 consecutive particles is a compact blob handled by one warp.
 //
 // Neighbour structure ("tiles"): for every block a table of candidate j particles (all particles
-// within cutoff+skin of any particle of the block), grouped 32 to a tile.  A tile is 256 bytes:
-// 32 x {j id | periodic image code << 24} followed by 32 x 32-bit masks, one mask per i lane, bit k
-// set iff pair (i, j_k) was within cutoff+skin at build time with the reference's exact fp32
-// predicate.  The force kernel loads a tile with two coalesced 128 B reads, gathers the 32 j
-// positions once, and every lane walks only ITS set bits, fetching j coordinates with warp shuffles
-// -- no per-pair memory traffic, no atomics, no padding work.  Both (i,j) and (j,i) are listed, so
-// f_i is complete in registers and is written with one coalesced store.
+// within cutoff + internal skin of any particle of the block), grouped 32 to a tile.  A tile is
+// 256 bytes: 32 x j index (bits 0..23; lane 0 carries the tile's trip count in bits 24..31)
+// followed by 32 x 32-bit masks, one mask per i lane, bit k set iff pair (i, j_k) was within
+// cutoff + internal skin at build time.  Candidates are dealt to tiles round-robin (candidate k of
+// K goes to tile k mod T), so every tile samples the whole neighbourhood and all 32 lanes find
+// about the same number of set bits in it -- the per-tile trip count (max over lanes) stays close
+// to the mean.  The force kernel loads a tile with two coalesced 128 B reads, gathers the 32 j
+// positions once, and every lane walks only ITS set bits, fetching j coordinates with warp
+// shuffles -- no per-pair memory traffic, no atomics, no padding work.  Both (i,j) and (j,i) are
+// listed, so f_i is complete in registers and is written with one coalesced store.
+//
+// The internal tables are an implementation detail: they are rebuilt on the engine's own
+// (smaller) skin, per replica, while the REFERENCE rebuild events (neighbors.py:864-907) are
+// tracked exactly and independently (refu / user_step), so the nbr_list object handed back to
+// the caller is what the reference would hold.  The cutoff predicate d < rc uses the reference's
+// exact fp32 operation order whenever a pair is within a few ulps of the cutoff.
 #include <vector>
 #include "common.cuh"
 
 #define FULL 0xffffffffu
-#define IMG_NONE 13u  // image code of "no shift": (1,1,1) in base 3
-#define HALT_NONE 0x7f7f7f7f  // cudaMemset-able "no halt" value of MdCtrl::halt_step
-
-struct MdCtrl {
-    int halt_step;       // first step whose BAOAB update invalidated the internal tables
-                         // (HALT_NONE = none); kernels of later steps turn into no-ops
-    int pad1;
-    int overflow;        // table capacity exceeded during a build
-    int pad0;
-    unsigned long long cand_pairs2;  // sum of mask popcounts at the last build (= 2 * P_cand)
-    unsigned long long int_pairs2;   // directed interacting pairs seen by the last energy kernel
-};
+#define HALT_NONE 0x7f7f7f7f  // "no halt" value of MdRep::halt
 
 struct MdRep {            // per replica control block
     uint32_t key[2][2];   // loop key, double buffered by step parity
     int user_step;        // last step at which the reference rebuild condition fired
     int user_rebuilds;
     float kT;
-    int pad;
+    int lo;               // first step this replica executes in the current pass
+    int halt;             // first step whose BAOAB update invalidated the tables (HALT_NONE = none)
+    int flag;             // 1 = takes part in the current rebuild / force-redo pass
+    int redo_step;        // step whose forces the redo pass evaluates
+    int overflow;         // table or queue capacity exceeded during the last build
+    unsigned long long cand_pairs2;  // mask bits set by the last build (= 2 * candidate pairs)
+    unsigned long long int_pairs2;   // directed interacting pairs seen by the last energy kernel
 };
 
 struct MdGeom {
     Box box;
     float inv_lx, inv_ly, inv_lz;
-    int ncx, ncy, ncz, bits;      // fine cell grid, Morton bits per dimension
+    int nb, bits;                 // cells per dimension (2^bits)
     float inv_cx, inv_cy, inv_cz; // 1 / cell edge
     float cx, cy, cz;             // cell edge
-    int n, np, nblk, ncm;         // particles, padded, blocks, Morton cells
+    int n, np, nblk, ncell;       // particles, padded, blocks, cells
 };
 
 struct chx_ljmd {
@@ -58,20 +62,18 @@ struct chx_ljmd {
     chx_ljmd_params p;
     MdGeom g;
     int R;
-    int cur;                 // which half of the double buffers is live
-    float4 *xs[2], *vs[2], *refu[2];
-    float4 *fs, *refi;
+    float4 *xs, *vs, *refu, *fs, *refi;
+    float4 *xs_t, *vs_t, *ru_t;      // gather targets of the sort
+    int *lin2h, *h2lin;              // Hilbert rank of a cell / its inverse
     int *cell_count, *cell_start, *cell_of, *order;
+    int2* cell_range;                // per (x,y,z)-linear cell: [begin, end) in sorted order
     uint32_t* tiles;
     int* ntiles;
     uint8_t* generic;
-    float4* bcenter;          // per block: centre of its bounding box at the last build
-    int tcap;
-    MdCtrl* ctrl;
+    float4* bcenter;                 // per block: centre of its bounding box at the last build
+    int tcap, qcap;
     MdRep* rep;
-    MdCtrl* ctrl_host;       // pinned
-    MdRep* rep_host;         // pinned (R entries)
-    double* e_scratch;       // R doubles
+    MdRep* rep_host;                 // pinned (R entries)
     float internal_skin;
     long long rebuilds, steps, launches0;
     bool have_state;
@@ -80,19 +82,7 @@ struct chx_ljmd {
 // ---------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t spread3(uint32_t v) {
-    v &= 0x3ffu;
-    v = (v | (v << 16)) & 0x030000ffu;
-    v = (v | (v << 8)) & 0x0300f00fu;
-    v = (v | (v << 4)) & 0x030c30c3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-__host__ __device__ __forceinline__ uint32_t morton3(int x, int y, int z) {
-    return spread3((uint32_t)x) | (spread3((uint32_t)y) << 1) | (spread3((uint32_t)z) << 2);
-}
-
-__device__ __forceinline__ int fine_cell(float x, float inv_c, int nc) {
+__device__ __forceinline__ int cell_coord_clamped(float x, float inv_c, int nc) {
     int c = (int)floorf(x * inv_c);
     c = c < 0 ? 0 : c;
     return c >= nc ? nc - 1 : c;
@@ -114,6 +104,38 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// Hilbert rank of cell (x,y,z) on a 2^bits cube (Skilling's transpose algorithm), host side
+static uint32_t hilbert_rank(uint32_t x, uint32_t y, uint32_t z, int bits) {
+    if (bits <= 0) return 0u;
+    uint32_t X[3] = {x, y, z};
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) {
+                X[0] ^= P;
+            } else {
+                const uint32_t t = (X[0] ^ X[i]) & P;
+                X[0] ^= t; X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0]; X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    for (int i = 0; i < 3; ++i) X[i] ^= t;
+    uint32_t h = 0;
+    for (int b = bits - 1; b >= 0; --b)
+        for (int i = 0; i < 3; ++i) h = (h << 1) | ((X[i] >> b) & 1u);
+    return h;
+}
 
 // ---------------------------------------------------------------------------------------------
 // import / export between the caller's (N,3) arrays and the sorted float4 state
@@ -134,7 +156,7 @@ __global__ void k_md_import(const float* __restrict__ x, const float* __restrict
     const size_t s = ((size_t)r * g.n + i) * 3;
     float px = x[s], py = x[s + 1], pz = x[s + 2];
     refu[o] = make_float4(px, py, pz, __int_as_float(i));
-    // positions outside [0, L) are wrapped on import (the sort and the image codes assume it)
+    // positions outside [0, L) are wrapped on import (the cell grid assumes it)
     if (px < 0.f || px >= g.box.lx) px = ref_wrap(px, g.box.lx);
     if (py < 0.f || py >= g.box.ly) py = ref_wrap(py, g.box.ly);
     if (pz < 0.f || pz >= g.box.lz) pz = ref_wrap(pz, g.box.lz);
@@ -156,70 +178,99 @@ __global__ void k_md_export_ids(const float4* __restrict__ src, const float4* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// sort: Morton cell id -> counting sort -> per-cell order by original id (deterministic)
+// sort: Hilbert cell rank -> counting sort -> per-cell order by original id (deterministic).
+// Every kernel of the rebuild is a no-op for replicas whose `flag` is clear.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_md_cellcount(const float4* __restrict__ xs, MdGeom g, int* __restrict__ cell_of,
+__global__ void k_md_cellcount(const float4* __restrict__ xs, MdGeom g, const int* __restrict__ lin2h,
+                               const MdRep* __restrict__ rep, int* __restrict__ cell_of,
                                int* __restrict__ count) {
     const int r = blockIdx.y;
+    if (!rep[r].flag) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.np) return;
     const size_t o = (size_t)r * g.np + i;
     const float4 p = xs[o];
     if (__float_as_int(p.w) < 0) { cell_of[o] = -1; return; }
-    const int m = (int)morton3(fine_cell(p.x, g.inv_cx, g.ncx), fine_cell(p.y, g.inv_cy, g.ncy),
-                               fine_cell(p.z, g.inv_cz, g.ncz));
-    cell_of[o] = m;
-    atomicAdd(&count[(size_t)r * (g.ncm + 1) + m], 1);
+    const int cx = cell_coord_clamped(p.x, g.inv_cx, g.nb);
+    const int cy = cell_coord_clamped(p.y, g.inv_cy, g.nb);
+    const int cz = cell_coord_clamped(p.z, g.inv_cz, g.nb);
+    const int h = lin2h[(cx * g.nb + cy) * g.nb + cz];
+    cell_of[o] = h;
+    atomicAdd(&count[(size_t)r * (g.ncell + 1) + h], 1);
 }
 
+// one CTA per replica: exclusive scan over the cells in Hilbert order, 1024 cells per pass
 __global__ void __launch_bounds__(1024)
-k_md_scan(int* __restrict__ count, int* __restrict__ start, int ncm) {
-    __shared__ int part[1024];
+k_md_scan(int* __restrict__ count, int* __restrict__ start, int2* __restrict__ range,
+          const int* __restrict__ h2lin, int ncell, const MdRep* __restrict__ rep) {
+    __shared__ int wsum[32];
+    __shared__ int total;
     const int r = blockIdx.x;
-    count += (size_t)r * (ncm + 1);
-    start += (size_t)r * (ncm + 1);
-    const int t = threadIdx.x;
-    const int per = (ncm + 1023) / 1024;
-    const int lo = t * per, hi = min(ncm, lo + per);
-    int s = 0;
-    for (int c = lo; c < hi; ++c) s += count[c];
-    part[t] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        int v = t >= o ? part[t - o] : 0;
+    if (!rep[r].flag) return;
+    count += (size_t)r * (ncell + 1);
+    start += (size_t)r * (ncell + 1);
+    range += (size_t)r * ncell;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    int base = 0;
+    for (int c0 = 0; c0 < ncell; c0 += 1024) {
+        const int c = c0 + t;
+        const int v = c < ncell ? count[c] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) wsum[w] = inc;
         __syncthreads();
-        part[t] += v;
+        if (w == 0) {
+            int s = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(FULL, s, o);
+                if (lane >= o) s += u;
+            }
+            wsum[lane] = s;
+            if (lane == 31) total = s;
+        }
+        __syncthreads();
+        const int excl = base + inc - v + (w > 0 ? wsum[w - 1] : 0);
+        if (c < ncell) {
+            start[c] = excl;
+            count[c] = 0;
+            range[h2lin[c]] = make_int2(excl, excl + v);
+        }
+        base += total;
         __syncthreads();
     }
-    int run = part[t] - s;
-    for (int c = lo; c < hi; ++c) {
-        const int k = count[c];
-        start[c] = run;
-        count[c] = 0;
-        run += k;
-    }
-    if (t == 1023) start[ncm] = part[t];
+    if (t == 0) start[ncell] = base;
 }
 
 __global__ void k_md_place(const int* __restrict__ cell_of, MdGeom g, const int* __restrict__ start,
-                           int* __restrict__ cursor, int* __restrict__ order) {
+                           const MdRep* __restrict__ rep, int* __restrict__ cursor,
+                           int* __restrict__ order) {
     const int r = blockIdx.y;
+    if (!rep[r].flag) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.np) return;
     const size_t o = (size_t)r * g.np + i;
     const int m = cell_of[o];
     if (m < 0) return;
-    const size_t cb = (size_t)r * (g.ncm + 1);
+    const size_t cb = (size_t)r * (g.ncell + 1);
     order[(size_t)r * g.np + start[cb + m] + atomicAdd(&cursor[cb + m], 1)] = i;
 }
 
-// one thread per Morton cell: insertion sort of the cell's slots by original particle id
+// one thread per cell: insertion sort of the cell's slots by original particle id, and reset of
+// the fill cursor for the next rebuild
 __global__ void k_md_cellsort(const float4* __restrict__ xs, MdGeom g, const int* __restrict__ start,
+                              const MdRep* __restrict__ rep, int* __restrict__ cursor,
                               int* __restrict__ order) {
     const int r = blockIdx.y;
+    if (!rep[r].flag) return;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.ncm) return;
-    const size_t cb = (size_t)r * (g.ncm + 1);
+    if (c >= g.ncell) return;
+    const size_t cb = (size_t)r * (g.ncell + 1);
+    cursor[cb + c] = 0;
     const int s = start[cb + c], e = start[cb + c + 1];
     if (e - s < 2) return;
     int* ord = order + (size_t)r * g.np;
@@ -233,47 +284,83 @@ __global__ void k_md_cellsort(const float4* __restrict__ xs, MdGeom g, const int
     }
 }
 
-__global__ void k_md_gather(const int* __restrict__ order, MdGeom g, const float4* __restrict__ xs0,
-                            const float4* __restrict__ vs0, const float4* __restrict__ ru0,
-                            float4* __restrict__ xs1, float4* __restrict__ vs1,
-                            float4* __restrict__ ru1, float4* __restrict__ refi) {
+__global__ void k_md_gather(const int* __restrict__ order, MdGeom g, const MdRep* __restrict__ rep,
+                            const float4* __restrict__ xs0, const float4* __restrict__ vs0,
+                            const float4* __restrict__ ru0, float4* __restrict__ xs1,
+                            float4* __restrict__ vs1, float4* __restrict__ ru1) {
     const int r = blockIdx.y;
+    if (!rep[r].flag) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= g.np) return;
     const size_t o = (size_t)r * g.np + p;
     if (p >= g.n) {
         const float4 pad = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        xs1[o] = pad; vs1[o] = make_float4(0.f, 0.f, 0.f, 1.f); ru1[o] = pad; refi[o] = pad;
+        xs1[o] = pad; vs1[o] = make_float4(0.f, 0.f, 0.f, 1.f); ru1[o] = pad;
         return;
     }
     const size_t q = (size_t)r * g.np + order[o];
-    const float4 a = xs0[q];
-    xs1[o] = a; vs1[o] = vs0[q]; ru1[o] = ru0[q]; refi[o] = a;
+    xs1[o] = xs0[q]; vs1[o] = vs0[q]; ru1[o] = ru0[q];
+}
+
+// copy the gathered arrays back over the live ones (and take the rebuild reference positions)
+__global__ void k_md_adopt(MdGeom g, const MdRep* __restrict__ rep, const float4* __restrict__ xs1,
+                           const float4* __restrict__ vs1, const float4* __restrict__ ru1,
+                           float4* __restrict__ xs, float4* __restrict__ vs, float4* __restrict__ ru,
+                           float4* __restrict__ refi) {
+    const int r = blockIdx.y;
+    if (!rep[r].flag) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.np) return;
+    const size_t o = (size_t)r * g.np + p;
+    const float4 a = xs1[o];
+    xs[o] = a; refi[o] = a; vs[o] = vs1[o]; ru[o] = ru1[o];
+}
+
+// replicas whose tables are rebuilt without a sort (capacity regrow, flag bit 1): the positions the
+// new tables are built from become their rebuild reference
+__global__ void k_md_take_ref(MdGeom g, const MdRep* __restrict__ rep, const float4* __restrict__ xs,
+                              float4* __restrict__ refi) {
+    const int r = blockIdx.y;
+    if (!(rep[r].flag & 2)) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.np) return;
+    const size_t o = (size_t)r * g.np + p;
+    refi[o] = xs[o];
 }
 
 // ---------------------------------------------------------------------------------------------
 // table build: one warp per block of 32 particles
+//   1. candidates: particles of every cell the block's bounding box (+R) touches, filtered by
+//      their distance to the box, queued in shared memory;
+//   2. dense test: every candidate against the 32 particles of the block (one ballot word per
+//      candidate); candidates nobody needs are dropped;
+//   3. tiles: kept candidate k goes to tile k mod T, slot k / T; the 32 ballot words of a tile are
+//      transposed into one mask per i lane.
 // ---------------------------------------------------------------------------------------------
-#define BW 4          // warps per CTA in the build kernel
-#define QCAP 2048     // candidate queue entries per warp
-
 __device__ __forceinline__ float axis_gap(float v, float lo, float hi) {
     return fmaxf(0.f, fmaxf(lo - v, v - hi));
 }
 
-__global__ void __launch_bounds__(BW * 32)
-k_md_build(const float4* __restrict__ xs_all, const int* __restrict__ start_all, MdGeom g, float R,
-           int tcap, uint32_t* __restrict__ tiles_all, int* __restrict__ ntiles_all,
-           uint8_t* __restrict__ generic_all, float4* __restrict__ bcenter_all, float drift,
-           MdCtrl* __restrict__ ctrl) {
-    __shared__ uint32_t queue[BW][QCAP];
-    __shared__ uint32_t idxbuf[BW][32];
+__global__ void __launch_bounds__(128)
+k_md_build(const float4* __restrict__ xs_all, const int2* __restrict__ range_all, MdGeom g, float R,
+           float drift, int tcap, int qcap, uint32_t* __restrict__ tiles_all,
+           int* __restrict__ ntiles_all, uint8_t* __restrict__ generic_all,
+           float4* __restrict__ bcenter_all, MdRep* __restrict__ rep) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int r = blockIdx.y;
+    if (!rep[r].flag) return;
+    const int nw = blockDim.x >> 5;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * BW + w;
+    const int b = blockIdx.x * nw + w;
     if (b >= g.nblk) return;
+    // per-warp shared memory: stage[32] float4 | queue[qcap] | colmask[qcap]
+    unsigned char* base = smem_raw + (size_t)w * (512 + 8 * (size_t)qcap);
+    float4* stage = reinterpret_cast<float4*>(base);
+    uint32_t* queue = reinterpret_cast<uint32_t*>(base + 512);
+    uint32_t* colmask = queue + qcap;
+
     const float4* xs = xs_all + (size_t)r * g.np;
-    const int* start = start_all + (size_t)r * (g.ncm + 1);
+    const int2* range = range_all + (size_t)r * g.ncell;
     uint32_t* tiles = tiles_all + ((size_t)r * g.nblk + b) * tcap * 64;
     const int i = b * 32 + lane;
     const float4 xi = xs[i];
@@ -282,99 +369,54 @@ k_md_build(const float4* __restrict__ xs_all, const int* __restrict__ start_all,
     const float lox = warp_min(valid ? xi.x : INF), hix = warp_max(valid ? xi.x : -INF);
     const float loy = warp_min(valid ? xi.y : INF), hiy = warp_max(valid ? xi.y : -INF);
     const float loz = warp_min(valid ? xi.z : INF), hiz = warp_max(valid ? xi.z : -INF);
-    const float Rm = R * (1.0f + 2e-5f) + 1e-6f;
+    const float Rm = R * (1.0f + 2e-5f) + 1e-6f;   // conservative: the tables may hold extra pairs
+    const float Rm2 = Rm * Rm;
     int c0x = (int)floorf((lox - Rm) * g.inv_cx), c1x = (int)floorf((hix + Rm) * g.inv_cx);
     int c0y = (int)floorf((loy - Rm) * g.inv_cy), c1y = (int)floorf((hiy + Rm) * g.inv_cy);
     int c0z = (int)floorf((loz - Rm) * g.inv_cz), c1z = (int)floorf((hiz + Rm) * g.inv_cz);
     int nx = c1x - c0x + 1, ny = c1y - c0y + 1, nz = c1z - c0z + 1;
     bool gen = false;
-    if (nx >= g.ncx) { nx = g.ncx; c0x = 0; gen = true; }
-    if (ny >= g.ncy) { ny = g.ncy; c0y = 0; gen = true; }
-    if (nz >= g.ncz) { nz = g.ncz; c0z = 0; gen = true; }
+    if (nx >= g.nb) { nx = g.nb; c0x = 0; gen = true; }
+    if (ny >= g.nb) { ny = g.nb; c0y = 0; gen = true; }
+    if (nz >= g.nb) { nz = g.nb; c0z = 0; gen = true; }
     // non-generic blocks resolve periodic images per TILE (force kernel): everything the block can
     // interact with until the next rebuild must stay within half a box of the block centre
     if (0.5f * (hix - lox) + Rm + drift >= g.box.hx || 0.5f * (hiy - loy) + Rm + drift >= g.box.hy ||
         0.5f * (hiz - loz) + Rm + drift >= g.box.hz)
         gen = true;
+    const float bcx = 0.5f * (lox + hix), bcy = 0.5f * (loy + hiy), bcz = 0.5f * (loz + hiz);
     const int total = nx * ny * nz;
-    const float Rm2 = Rm * Rm;
+    const int nbm = g.nb - 1;
 
-    int qn = 0;        // queue fill (warp uniform)
-    int nslots = 0;    // table slots used (warp uniform)
-    uint32_t cur = 0;  // mask bits of the tile being filled
+    // ---- 1. candidate queue ----
+    int qn = 0;
     bool ovf = false;
-    unsigned long long pairs = 0;
-
-    // drains the queue: every candidate is tested against the 32 particles of the block
-    auto drain = [&]() {
-        __syncwarp();
-        for (int q = 0; q < qn; ++q) {
-            const uint32_t code = queue[w][q];
-            const int p = (int)(code & 0xffffffu);
-            const float4 xj = xs[p];
-            bool hit = false;
-            if (valid && p != i) {
-                float rx, ry, rz, d;
-                ref_displacement<true>(xi.x, xi.y, xi.z, xj.x, xj.y, xj.z, g.box, rx, ry, rz, d);
-                hit = d < R;
-            }
-            const unsigned bal = __ballot_sync(FULL, hit);
-            if (bal) {
-                const int k = nslots & 31;
-                if (lane == 0) idxbuf[w][k] = code;
-                if (hit) { cur |= 1u << k; ++pairs; }
-                ++nslots;
-                if (k == 31) {
-                    __syncwarp();
-                    const int t = (nslots >> 5) - 1;
-                    if (t < tcap) {
-                        tiles[(size_t)t * 64 + lane] = idxbuf[w][lane];
-                        tiles[(size_t)t * 64 + 32 + lane] = cur;
-                    } else {
-                        ovf = true;
-                    }
-                    cur = 0;
-                    __syncwarp();
-                }
-            }
-        }
-        qn = 0;
-        __syncwarp();
-    };
-
     for (int cb = 0; cb < total; cb += 32) {
         const int c = cb + lane;
         int s = 0, e = 0;
-        uint32_t img = IMG_NONE;
         float shx = 0.f, shy = 0.f, shz = 0.f;
         if (c < total) {
             const int iz = c % nz, iy = (c / nz) % ny, ix = c / (nz * ny);
-            int ux = c0x + ix, uy = c0y + iy, uz = c0z + iz;  // unwrapped cell coordinates
-            int wx = ux, wy = uy, wz = uz, sx = 1, sy = 1, sz = 1;
-            if (wx < 0) { wx += g.ncx; sx = 0; } else if (wx >= g.ncx) { wx -= g.ncx; sx = 2; }
-            if (wy < 0) { wy += g.ncy; sy = 0; } else if (wy >= g.ncy) { wy -= g.ncy; sy = 2; }
-            if (wz < 0) { wz += g.ncz; sz = 0; } else if (wz >= g.ncz) { wz -= g.ncz; sz = 2; }
+            const int ux = c0x + ix, uy = c0y + iy, uz = c0z + iz;  // unwrapped cell coordinates
             // cell-level prefilter in unwrapped coordinates
             const float gx = axis_gap((ux + 0.5f) * g.cx, lox - 0.5f * g.cx, hix + 0.5f * g.cx);
             const float gy = axis_gap((uy + 0.5f) * g.cy, loy - 0.5f * g.cy, hiy + 0.5f * g.cy);
             const float gz = axis_gap((uz + 0.5f) * g.cz, loz - 0.5f * g.cz, hiz + 0.5f * g.cz);
             if (gen || gx * gx + gy * gy + gz * gz < Rm2 * 1.0001f) {
-                const int m = (int)morton3(wx, wy, wz);
-                s = start[m]; e = start[m + 1];
-                img = (uint32_t)(sx * 9 + sy * 3 + sz);
-                shx = (sx - 1) * g.box.lx; shy = (sy - 1) * g.box.ly; shz = (sz - 1) * g.box.lz;
+                const int2 se = range[(((ux & nbm) * g.nb) + (uy & nbm)) * g.nb + (uz & nbm)];
+                s = se.x; e = se.y;
+                shx = (float)(ux >> g.bits) * g.box.lx;   // arithmetic shift: -1, 0 or +1 images
+                shy = (float)(uy >> g.bits) * g.box.ly;
+                shz = (float)(uz >> g.bits) * g.box.lz;
             }
         }
-        // lock-step over the cells' particles so queue positions are deterministic
-        int maxlen = e - s;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL, maxlen, o));
+        const int maxlen = warp_max_i(e - s);
         for (int k = 0; k < maxlen; ++k) {
             bool push = false;
             const int p = s + k;
             if (p < e) {
                 if (gen) {
-                    push = true;  // small box: no image bookkeeping, exact test decides
+                    push = true;  // small box: the dense test decides
                 } else {
                     const float4 xj = xs[p];
                     const float dx = axis_gap(xj.x + shx, lox, hix);
@@ -384,61 +426,203 @@ k_md_build(const float4* __restrict__ xs_all, const int* __restrict__ start_all,
                 }
             }
             const unsigned bal = __ballot_sync(FULL, push);
-            if (push) queue[w][qn + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)p | (img << 24);
+            const int pos = qn + __popc(bal & ((1u << lane) - 1u));
+            if (push) {
+                if (pos < qcap) queue[pos] = (uint32_t)p; else ovf = true;
+            }
             qn += __popc(bal);
-            if (qn + 32 > QCAP) drain();
         }
     }
-    drain();
-    // flush the partially filled tile, padding with the lane's own particle and empty masks
-    const int k = nslots & 31;
-    if (k != 0) {
-        __syncwarp();
-        const int t = nslots >> 5;
-        if (t < tcap) {
-            tiles[(size_t)t * 64 + lane] = lane < k ? idxbuf[w][lane] : ((uint32_t)(b * 32) | (IMG_NONE << 24));
-            tiles[(size_t)t * 64 + 32 + lane] = cur;
-        } else {
-            ovf = true;
+    ovf = __any_sync(FULL, ovf);
+    if (qn > qcap) qn = qcap;
+    __syncwarp();
+
+    // ---- 2. dense test ----
+    int kept = 0;
+    unsigned long long pairs = 0;
+    for (int q0 = 0; q0 < qn; q0 += 32) {
+        const int cnt = min(32, qn - q0);
+        if (lane < cnt) {
+            const int p = (int)queue[q0 + lane];
+            float4 xj = xs[p];
+            if (!gen) {
+                xj.x -= g.box.lx * rintf((xj.x - bcx) * g.inv_lx);
+                xj.y -= g.box.ly * rintf((xj.y - bcy) * g.inv_ly);
+                xj.z -= g.box.lz * rintf((xj.z - bcz) * g.inv_lz);
+            }
+            xj.w = __int_as_float(p);
+            stage[lane] = xj;
         }
+        __syncwarp();
+        for (int k = 0; k < cnt; ++k) {
+            const float4 xj = stage[k];
+            const int p = __float_as_int(xj.w);
+            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            if (gen) {
+                dx -= g.box.lx * rintf(dx * g.inv_lx);
+                dy -= g.box.ly * rintf(dy * g.inv_ly);
+                dz -= g.box.lz * rintf(dz * g.inv_lz);
+            }
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            const bool hit = valid && p != i && r2 < Rm2;
+            const unsigned bal = __ballot_sync(FULL, hit);
+            if (bal) {
+                // kept <= q0 + k: the slot being overwritten has already been consumed
+                if (lane == 0) { queue[kept] = (uint32_t)p; colmask[kept] = bal; }
+                ++kept;
+                pairs += hit ? 1ull : 0ull;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- 3. tiles ----
+    const int T = (kept + 31) >> 5;
+    if (T > tcap) ovf = true;
+    const int Tw = min(T, tcap);
+    for (int t = 0; t < Tw; ++t) {
+        const int k = lane * T + t;            // round-robin deal: tile t takes t, T+t, 2T+t, ...
+        const bool have = k < kept;
+        const uint32_t myB = have ? colmask[k] : 0u;
+        uint32_t myIdx = have ? queue[k] : (uint32_t)(b * 32);
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+            const unsigned wv = __ballot_sync(FULL, (myB >> l) & 1u);
+            if (lane == l) mine = wv;
+        }
+        const int trips = warp_max_i(__popc(mine));
+        if (lane == 0) myIdx |= (uint32_t)trips << 24;
+        tiles[(size_t)t * 64 + lane] = myIdx;
+        tiles[(size_t)t * 64 + 32 + lane] = mine;
     }
     if (lane == 0) {
-        ntiles_all[(size_t)r * g.nblk + b] = min((nslots + 31) >> 5, tcap);
+        ntiles_all[(size_t)r * g.nblk + b] = Tw;
         generic_all[(size_t)r * g.nblk + b] = gen ? 1 : 0;
-        bcenter_all[(size_t)r * g.nblk + b] = make_float4(0.5f * (lox + hix), 0.5f * (loy + hiy), 0.5f * (loz + hiz), 0.f);
-        if (ovf) atomicExch(&ctrl->overflow, 1);
+        bcenter_all[(size_t)r * g.nblk + b] = make_float4(bcx, bcy, bcz, 0.f);
+        if (ovf) atomicExch(&rep[r].overflow, 1);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(FULL, pairs, o);
-    if (lane == 0 && pairs) atomicAdd(&ctrl->cand_pairs2, pairs);
+    if (lane == 0 && pairs) atomicAdd(&rep[r].cand_pairs2, pairs);
 }
 
 // ---------------------------------------------------------------------------------------------
 // force / energy over the tiles
 // ---------------------------------------------------------------------------------------------
 struct LjConst {
-    float sig2;      // sigma^2
-    float eps24;     // 24 eps
-    float eps4;      // 4 eps
-    float rc;        // cutoff (exact predicate)
-    float rc2_lo, rc2_hi;  // guard band around cutoff^2 for the fast predicate
+    float c12f, c6f;   // 48 eps sigma^12, 24 eps sigma^6:  f/r = inv * inv3 * (c12f * inv3 - c6f)
+    float c12e, c6e;   // 4 eps sigma^12, 4 eps sigma^6:    e   = inv3 * (c12e * inv3 - c6e)
+    float rc;          // cutoff (exact predicate)
+    float rc2_lo, rc2_hi;  // fast predicate: r2 < rc2_lo is inside, r2 >= rc2_hi is outside, the band
+                           // in between is decided with the reference's exact predicate
 };
 
-#define FW 8  // warps per CTA in the force kernel
+// which replicas / which step a force launch serves
+#define FMODE_STEP 0   // step s of the loop: replicas with lo <= s < halt
+#define FMODE_REDO 1   // after a rebuild: replicas with flag set, step = rep.redo_step
+#define FMODE_ALL  2   // every replica, no step (set_state, energy(), force_only)
+
+#define FW 4  // warps per CTA in the force kernel
+
+template <bool ENERGY, bool GEN>
+__device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, const uint32_t* __restrict__ tp,
+                                             int nt, const float4 xi0, const float4 xi, const float4 bc,
+                                             const MdGeom& g, const LjConst& lj, int lane, float& fx,
+                                             float& fy, float& fz, float& e_acc, unsigned& npair) {
+    for (int t = 0; t < nt; ++t, tp += 64) {
+        const uint32_t code = tp[lane];
+        uint32_t m = tp[32 + lane];
+        const int j = (int)(code & 0xffffffu);
+        const int trips = (int)(__shfl_sync(FULL, code, 0) >> 24);
+        float4 xj = xs[j];
+        if (!GEN) {
+            // positions are wrapped every step (integrators.py:239), so a particle may have jumped
+            // by a box length since the build: images are resolved against the block centre, once
+            // per particle per tile instead of once per pair
+            xj.x -= g.box.lx * rintf((xj.x - bc.x) * g.inv_lx);
+            xj.y -= g.box.ly * rintf((xj.y - bc.y) * g.inv_ly);
+            xj.z -= g.box.lz * rintf((xj.z - bc.z) * g.inv_lz);
+        }
+        uint32_t bandmask = 0u;   // pairs within a few ulps of the cutoff, decided after the loop
+        for (int it = 0; it < trips; ++it) {
+            const uint32_t iso = m & (0u - m);     // lowest set bit (0 when this lane is done)
+            m ^= iso;
+            const int bit = 31 - __clz(iso);       // -1 when done: the shuffles read lane 31
+            const float sx = __shfl_sync(FULL, xj.x, bit);
+            const float sy = __shfl_sync(FULL, xj.y, bit);
+            const float sz = __shfl_sync(FULL, xj.z, bit);
+            float dx = xi.x - sx, dy = xi.y - sy, dz = xi.z - sz;
+            if (GEN) {
+                dx -= g.box.lx * rintf(dx * g.inv_lx);
+                dy -= g.box.ly * rintf(dy * g.inv_ly);
+                dz -= g.box.lz * rintf(dz * g.inv_lz);
+            }
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            const bool in = (iso != 0u) && (r2 < lj.rc2_lo);
+            if (!in && r2 < lj.rc2_hi) bandmask |= iso;   // iso == 0 for finished lanes: no effect
+            const float inv = rcp_approx(r2);
+            const float inv3 = inv * inv * inv;
+            float f = (inv * inv3) * fmaf(lj.c12f, inv3, -lj.c6f);
+            f = in ? f : 0.f;
+            fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
+            if (ENERGY) {
+                const float e = inv3 * fmaf(lj.c12e, inv3, -lj.c6e);
+                e_acc += in ? e : 0.f;
+                npair += in ? 1u : 0u;
+            }
+        }
+        if (__any_sync(FULL, bandmask != 0u)) {
+            // rare: decide with the reference's exact fp32 predicate (neighbors.py:69-81, :782)
+            while (bandmask) {
+                const int bit = __ffs(bandmask) - 1;
+                bandmask &= bandmask - 1u;
+                const int jj = (int)(tp[bit] & 0xffffffu);
+                float4 xo = xs[jj];
+                float rx, ry, rz, d;
+                ref_displacement<true>(xi0.x, xi0.y, xi0.z, xo.x, xo.y, xo.z, g.box, rx, ry, rz, d);
+                if (d < lj.rc) {
+                    if (!GEN) {
+                        xo.x -= g.box.lx * rintf((xo.x - bc.x) * g.inv_lx);
+                        xo.y -= g.box.ly * rintf((xo.y - bc.y) * g.inv_ly);
+                        xo.z -= g.box.lz * rintf((xo.z - bc.z) * g.inv_lz);
+                    }
+                    float dx = xi.x - xo.x, dy = xi.y - xo.y, dz = xi.z - xo.z;
+                    if (GEN) {
+                        dx -= g.box.lx * rintf(dx * g.inv_lx);
+                        dy -= g.box.ly * rintf(dy * g.inv_ly);
+                        dz -= g.box.lz * rintf(dz * g.inv_lz);
+                    }
+                    const float inv = 1.0f / (dx * dx + dy * dy + dz * dz);
+                    const float inv3 = inv * inv * inv;
+                    const float f = (inv * inv3) * fmaf(lj.c12f, inv3, -lj.c6f);
+                    fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
+                    if (ENERGY) { e_acc += inv3 * fmaf(lj.c12e, inv3, -lj.c6e); ++npair; }
+                }
+            }
+        }
+    }
+}
 
 template <bool ENERGY>
 __global__ void __launch_bounds__(FW * 32)
 k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
            float4* __restrict__ refu_all, const uint32_t* __restrict__ tiles_all,
            const int* __restrict__ ntiles_all, const uint8_t* __restrict__ generic_all,
-           const float4* __restrict__ bcenter_all, MdGeom g, LjConst lj, int tcap, MdCtrl* __restrict__ ctrl, MdRep* __restrict__ rep, int step,
-           int honor_halt, double* __restrict__ energy_out) {
-    __shared__ uint32_t sj[FW][32];
+           const float4* __restrict__ bcenter_all, MdGeom g, LjConst lj, int tcap,
+           MdRep* __restrict__ rep, int mode, int step_arg, int report_interval, int n_rep,
+           double* __restrict__ energy_out) {
     __shared__ double red[FW];
     __shared__ unsigned long long redn[FW];
-    // the tables are stale from step halt_step on: that step's forces are evaluated after the rebuild
-    if (honor_halt && *((volatile int*)&ctrl->halt_step) <= step) return;
     const int r = blockIdx.y;
+    int step = step_arg;
+    if (mode == FMODE_STEP) {
+        // the tables are stale from step `halt` on: that step's forces are evaluated after the rebuild
+        if (!(rep[r].lo <= step && step < *((volatile int*)&rep[r].halt))) return;
+    } else if (mode == FMODE_REDO) {
+        if (!rep[r].flag) return;
+        step = rep[r].redo_step;
+    }
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * FW + w;
     float e_acc = 0.f;
@@ -448,67 +632,22 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
         const int i = b * 32 + lane;
         const float4 xi0 = xs[i];
         float4 xi = xi0;
-        if (rep[r].user_step == step) {  // reference rebuild (neighbors.py:903-905 -> build)
+        if (step >= 0 && rep[r].user_step == step) {  // reference rebuild (neighbors.py:903-905 -> build)
             refu_all[(size_t)r * g.np + i] = xi0;
             if (b == 0 && lane == 0) rep[r].user_rebuilds++;
         }
         const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * tcap * 64;
         const int nt = ntiles_all[(size_t)r * g.nblk + b];
         const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
-        // positions are wrapped every step (integrators.py:239), so a particle may have jumped by a
-        // box length since the build: images are resolved against the block centre, once per
-        // particle per tile instead of once per pair
         const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
-        if (!gen) {
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (gen) {
+            md_tile_loop<ENERGY, true>(xs, tp, nt, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+        } else {
             xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
             xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
             xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
-        }
-        float fx = 0.f, fy = 0.f, fz = 0.f;
-        for (int t = 0; t < nt; ++t, tp += 64) {
-            const uint32_t code = tp[lane];
-            uint32_t m = tp[32 + lane];
-            const int j = (int)(code & 0xffffffu);
-            float4 xj = xs[j];
-            __syncwarp();
-            sj[w][lane] = (uint32_t)j;
-            if (!gen) {
-                xj.x -= g.box.lx * rintf((xj.x - bc.x) * g.inv_lx);
-                xj.y -= g.box.ly * rintf((xj.y - bc.y) * g.inv_ly);
-                xj.z -= g.box.lz * rintf((xj.z - bc.z) * g.inv_lz);
-            }
-            __syncwarp();
-            while (__any_sync(FULL, m != 0u)) {
-                const bool act = m != 0u;
-                const int bit = act ? (__ffs(m) - 1) : 0;
-                m &= m - 1u;
-                const float sx = __shfl_sync(FULL, xj.x, bit);
-                const float sy = __shfl_sync(FULL, xj.y, bit);
-                const float sz = __shfl_sync(FULL, xj.z, bit);
-                float dx = xi.x - sx, dy = xi.y - sy, dz = xi.z - sz;
-                if (gen) {
-                    dx -= g.box.lx * rintf(dx * g.inv_lx);
-                    dy -= g.box.ly * rintf(dy * g.inv_ly);
-                    dz -= g.box.lz * rintf(dz * g.inv_lz);
-                }
-                const float r2 = dx * dx + dy * dy + dz * dz;
-                bool in = act && r2 < lj.rc2_hi;
-                if (in && r2 > lj.rc2_lo) {
-                    // within a few ulps of the cutoff: decide with the reference's exact predicate
-                    const float4 xo = xs[sj[w][bit]];
-                    float rx, ry, rz, d;
-                    ref_displacement<true>(xi0.x, xi0.y, xi0.z, xo.x, xo.y, xo.z, g.box, rx, ry, rz, d);
-                    in = d < lj.rc;
-                }
-                if (in) {
-                    const float inv = rcp_approx(r2);
-                    const float s2 = lj.sig2 * inv;
-                    const float s6 = s2 * s2 * s2;
-                    const float f = (lj.eps24 * inv) * (s6 * (2.0f * s6 - 1.0f));
-                    fx += f * dx; fy += f * dy; fz += f * dz;
-                    if (ENERGY) { e_acc += lj.eps4 * (s6 * (s6 - 1.0f)); ++npair; }
-                }
-            }
+            md_tile_loop<ENERGY, false>(xs, tp, nt, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
         }
         fs_all[(size_t)r * g.np + i] = make_float4(fx, fy, fz, 0.5f * e_acc);
     }
@@ -521,8 +660,14 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
             double s = 0.0;
             unsigned long long c = 0;
             for (int k = 0; k < FW; ++k) { s += red[k]; c += redn[k]; }
-            if (s != 0.0) atomicAdd(&energy_out[r], s);
-            if (c) atomicAdd(&ctrl->int_pairs2, c);
+            double* slot = nullptr;
+            if (energy_out) {
+                if (mode == FMODE_ALL) slot = energy_out + r;
+                else if (report_interval > 0 && step >= 0 && step % report_interval == 0)
+                    slot = energy_out + (size_t)(step / report_interval) * n_rep + r;
+            }
+            if (slot && s != 0.0) atomicAdd(slot, s);
+            if (c) atomicAdd(&rep[r].int_pairs2, c);
         }
     }
 }
@@ -534,11 +679,11 @@ __global__ void __launch_bounds__(256)
 k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float4* __restrict__ fs_all,
            const float4* __restrict__ refi_all, const float4* __restrict__ refu_all, MdGeom g,
            float h, float a, float b, float half_skin_user, float half_skin_int2, int step,
-           int trailing, MdCtrl* __restrict__ ctrl, MdRep* __restrict__ rep) {
+           MdRep* __restrict__ rep) {
     __shared__ uint32_t sk[2];
-    // a halt raised by ANOTHER block of this same launch (halt_step == step) must not stop us
-    if (*((volatile int*)&ctrl->halt_step) < step) return;
     const int r = blockIdx.y;
+    // a halt raised by ANOTHER block of this same launch (halt == step) must not stop us
+    if (!(rep[r].lo <= step && step <= *((volatile int*)&rep[r].halt))) return;
     if (threadIdx.x == 0) {
         uint32_t c0, c1, s0, s1;
         threefry_split(rep[r].key[step & 1][0], rep[r].key[step & 1][1], c0, c1, s0, s1);
@@ -546,6 +691,7 @@ k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float
         if (blockIdx.x == 0) { rep[r].key[(step + 1) & 1][0] = c0; rep[r].key[(step + 1) & 1][1] = c1; }
     }
     __syncthreads();
+    const int trailing = step > 0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool moved_int = false, moved_user = false;
     if (i < g.np) {
@@ -593,7 +739,7 @@ k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float
     const int any_int = __syncthreads_or(moved_int);
     const int any_user = __syncthreads_or(moved_user);
     if (threadIdx.x == 0) {
-        if (any_int) atomicMin(&ctrl->halt_step, step);
+        if (any_int) atomicMin(&rep[r].halt, step);
         if (any_user) rep[r].user_step = step;
     }
 }
@@ -615,16 +761,21 @@ __global__ void k_md_kick(float4* __restrict__ vs_all, const float4* __restrict_
 // ---------------------------------------------------------------------------------------------
 static int md_alloc(chx_ljmd* md) {
     const size_t np = (size_t)md->R * md->g.np;
-    for (int k = 0; k < 2; ++k) {
-        CHX_CUDA(cudaMalloc(&md->xs[k], np * sizeof(float4)));
-        CHX_CUDA(cudaMalloc(&md->vs[k], np * sizeof(float4)));
-        CHX_CUDA(cudaMalloc(&md->refu[k], np * sizeof(float4)));
-    }
+    CHX_CUDA(cudaMalloc(&md->xs, np * sizeof(float4)));
+    CHX_CUDA(cudaMalloc(&md->vs, np * sizeof(float4)));
+    CHX_CUDA(cudaMalloc(&md->refu, np * sizeof(float4)));
+    CHX_CUDA(cudaMalloc(&md->xs_t, np * sizeof(float4)));
+    CHX_CUDA(cudaMalloc(&md->vs_t, np * sizeof(float4)));
+    CHX_CUDA(cudaMalloc(&md->ru_t, np * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->fs, np * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->refi, np * sizeof(float4)));
-    const size_t nc = (size_t)md->R * (md->g.ncm + 1);
+    const int ncell = md->g.ncell;
+    const size_t nc = (size_t)md->R * (ncell + 1);
     CHX_CUDA(cudaMalloc(&md->cell_count, nc * sizeof(int)));
     CHX_CUDA(cudaMalloc(&md->cell_start, nc * sizeof(int)));
+    CHX_CUDA(cudaMalloc(&md->cell_range, (size_t)md->R * ncell * sizeof(int2)));
+    CHX_CUDA(cudaMalloc(&md->lin2h, ncell * sizeof(int)));
+    CHX_CUDA(cudaMalloc(&md->h2lin, ncell * sizeof(int)));
     CHX_CUDA(cudaMalloc(&md->cell_of, np * sizeof(int)));
     CHX_CUDA(cudaMalloc(&md->order, np * sizeof(int)));
     const size_t nb = (size_t)md->R * md->g.nblk;
@@ -632,84 +783,139 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->ntiles, nb * sizeof(int)));
     CHX_CUDA(cudaMalloc(&md->generic, nb));
     CHX_CUDA(cudaMalloc(&md->bcenter, nb * sizeof(float4)));
-    CHX_CUDA(cudaMalloc(&md->ctrl, sizeof(MdCtrl)));
     CHX_CUDA(cudaMalloc(&md->rep, md->R * sizeof(MdRep)));
-    CHX_CUDA(cudaMalloc(&md->e_scratch, md->R * sizeof(double)));
-    CHX_CUDA(cudaMallocHost(&md->ctrl_host, sizeof(MdCtrl)));
     CHX_CUDA(cudaMallocHost(&md->rep_host, md->R * sizeof(MdRep)));
-    CHX_CUDA(cudaMemset(md->ctrl, 0, sizeof(MdCtrl)));
     CHX_CUDA(cudaMemset(md->rep, 0, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMemset(md->fs, 0, np * sizeof(float4)));
+    CHX_CUDA(cudaMemset(md->cell_count, 0, nc * sizeof(int)));
+    // Hilbert tables
+    std::vector<int> l2h(ncell), h2l(ncell);
+    const int nbd = md->g.nb;
+    for (int x = 0; x < nbd; ++x)
+        for (int y = 0; y < nbd; ++y)
+            for (int z = 0; z < nbd; ++z) {
+                const int lin = (x * nbd + y) * nbd + z;
+                const int h = (int)hilbert_rank((uint32_t)x, (uint32_t)y, (uint32_t)z, md->g.bits);
+                l2h[lin] = h; h2l[h] = lin;
+            }
+    CHX_CUDA(cudaMemcpy(md->lin2h, l2h.data(), ncell * sizeof(int), cudaMemcpyHostToDevice));
+    CHX_CUDA(cudaMemcpy(md->h2lin, h2l.data(), ncell * sizeof(int), cudaMemcpyHostToDevice));
     return CHX_OK;
 }
 
 static LjConst md_lj(const chx_ljmd* md) {
     LjConst c;
-    c.sig2 = md->p.sigma * md->p.sigma;
-    c.eps24 = 24.0f * md->p.epsilon;
-    c.eps4 = 4.0f * md->p.epsilon;
+    const double sg = md->p.sigma, ep = md->p.epsilon;
+    const double s6 = sg * sg * sg * sg * sg * sg;
+    c.c12f = (float)(48.0 * ep * s6 * s6);
+    c.c6f = (float)(24.0 * ep * s6);
+    c.c12e = (float)(4.0 * ep * s6 * s6);
+    c.c6e = (float)(4.0 * ep * s6);
     c.rc = md->p.cutoff;
     const double rc2 = (double)md->p.cutoff * (double)md->p.cutoff;
-    c.rc2_lo = (float)(rc2 * (1.0 - 2e-6));
-    c.rc2_hi = (float)(rc2 * (1.0 + 2e-6));
+    // fast r2 (FMA, block-centred coordinates) vs the reference's rounded d: a few ulps of the
+    // largest coordinate involved; generous band, the exact path is rare either way
+    const double lmax = fmax(md->p.lx, fmax(md->p.ly, md->p.lz));
+    const double band = rc2 * 4e-6 + 8.0 * 1.2e-7 * lmax * md->p.cutoff;
+    c.rc2_lo = (float)(rc2 - band);
+    c.rc2_hi = (float)(rc2 + band);
     return c;
 }
 
-// sort + table build from the live buffers; grows the table capacity on overflow
+static int md_upload_rep(chx_ljmd* md) {
+    CHX_CUDA(cudaMemcpyAsync(md->rep, md->rep_host, md->R * sizeof(MdRep), cudaMemcpyHostToDevice,
+                             md->ctx->stream));
+    return CHX_OK;
+}
+static int md_download_rep(chx_ljmd* md) {
+    CHX_CUDA(cudaMemcpyAsync(md->rep_host, md->rep, md->R * sizeof(MdRep), cudaMemcpyDeviceToHost,
+                             md->ctx->stream));
+    CHX_CUDA(cudaStreamSynchronize(md->ctx->stream));
+    return CHX_OK;
+}
+
+static size_t md_build_smem(int nw, int qcap) { return (size_t)nw * (512 + 8 * (size_t)qcap); }
+
+// sort + table build for the replicas whose rep_host[r].flag is set (rep_host must already be
+// uploaded); grows the table capacity on overflow.  Leaves rep_host refreshed.
 static int md_rebuild(chx_ljmd* md) {
     chx_ctx* ctx = md->ctx;
     const MdGeom& g = md->g;
     cudaStream_t st = ctx->stream;
     const int R = md->R;
     const dim3 gp(chx_div_up(g.np, 256), R);
-    const int a = md->cur, b = 1 - md->cur;
-    CHX_CUDA(cudaMemsetAsync(md->cell_count, 0, (size_t)R * (g.ncm + 1) * sizeof(int), st));
-    k_md_cellcount<<<gp, 256, 0, st>>>(md->xs[a], g, md->cell_of, md->cell_count);
+    k_md_cellcount<<<gp, 256, 0, st>>>(md->xs, g, md->lin2h, md->rep, md->cell_of, md->cell_count);
     CHX_LAUNCHED(ctx);
-    k_md_scan<<<R, 1024, 0, st>>>(md->cell_count, md->cell_start, g.ncm);
+    k_md_scan<<<R, 1024, 0, st>>>(md->cell_count, md->cell_start, md->cell_range, md->h2lin, g.ncell, md->rep);
     CHX_LAUNCHED(ctx);
-    k_md_place<<<gp, 256, 0, st>>>(md->cell_of, g, md->cell_start, md->cell_count, md->order);
+    k_md_place<<<gp, 256, 0, st>>>(md->cell_of, g, md->cell_start, md->rep, md->cell_count, md->order);
     CHX_LAUNCHED(ctx);
-    k_md_cellsort<<<dim3(chx_div_up(g.ncm, 128), R), 128, 0, st>>>(md->xs[a], g, md->cell_start, md->order);
+    k_md_cellsort<<<dim3(chx_div_up(g.ncell, 128), R), 128, 0, st>>>(md->xs, g, md->cell_start, md->rep,
+                                                                     md->cell_count, md->order);
     CHX_LAUNCHED(ctx);
-    k_md_gather<<<gp, 256, 0, st>>>(md->order, g, md->xs[a], md->vs[a], md->refu[a], md->xs[b],
-                                    md->vs[b], md->refu[b], md->refi);
+    k_md_gather<<<gp, 256, 0, st>>>(md->order, g, md->rep, md->xs, md->vs, md->refu, md->xs_t, md->vs_t, md->ru_t);
     CHX_LAUNCHED(ctx);
-    md->cur = b;
+    k_md_adopt<<<gp, 256, 0, st>>>(g, md->rep, md->xs_t, md->vs_t, md->ru_t, md->xs, md->vs, md->refu, md->refi);
+    CHX_LAUNCHED(ctx);
     const float R_list = md->p.cutoff + md->internal_skin;
-    for (int attempt = 0; attempt < 6; ++attempt) {
-        CHX_CUDA(cudaMemsetAsync(&md->ctrl->overflow, 0, sizeof(int), st));
-        CHX_CUDA(cudaMemsetAsync(&md->ctrl->cand_pairs2, 0, sizeof(unsigned long long), st));
-        k_md_build<<<dim3(chx_div_up(g.nblk, BW), R), BW * 32, 0, st>>>(
-            md->xs[b], md->cell_start, g, R_list, md->tcap, md->tiles, md->ntiles, md->generic, md->bcenter,
-            md->internal_skin, md->ctrl);
-        CHX_LAUNCHED(ctx);
-        CHX_CUDA(cudaMemcpyAsync(md->ctrl_host, md->ctrl, sizeof(MdCtrl), cudaMemcpyDeviceToHost, st));
-        CHX_CUDA(cudaStreamSynchronize(st));
-        if (!md->ctrl_host->overflow) {
-            md->rebuilds++;
-            return CHX_OK;
+    bool regrown = false;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        int nw = 4;
+        while (nw > 1 && md_build_smem(nw, md->qcap) > 200 * 1024) nw >>= 1;
+        const size_t smem = md_build_smem(nw, md->qcap);
+        if (smem > 220 * 1024) {
+            chx_set_error("neighbour table build needs %zu bytes of shared memory per warp", smem);
+            return CHX_NEIGHBOR_OVERFLOW;
         }
+        CHX_CUDA(cudaFuncSetAttribute(k_md_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_md_build<<<dim3(chx_div_up(g.nblk, nw), R), nw * 32, smem, st>>>(
+            md->xs, md->cell_range, g, R_list, md->internal_skin, md->tcap, md->qcap, md->tiles, md->ntiles,
+            md->generic, md->bcenter, md->rep);
+        CHX_LAUNCHED(ctx);
+        int rc = md_download_rep(md);
+        if (rc != CHX_OK) return rc;
+        bool ovf = false;
+        for (int r = 0; r < R; ++r) ovf = ovf || (md->rep_host[r].flag && md->rep_host[r].overflow);
+        if (!ovf) {
+            md->rebuilds++;
+            if (regrown) {
+                for (int r = 0; r < R; ++r) md->rep_host[r].flag &= 1;
+                rc = md_upload_rep(md);
+            }
+            return rc;
+        }
+        // grow and rebuild the flagged replicas again (their sorted state is already in place)
         md->tcap *= 2;
+        md->qcap *= 2;
         CHX_CUDA(cudaFree(md->tiles));
         CHX_CUDA(cudaMalloc(&md->tiles, (size_t)R * g.nblk * md->tcap * 64 * sizeof(uint32_t)));
+        for (int r = 0; r < R; ++r) {
+            // tables of replicas that were NOT flagged are gone with the old allocation: rebuild all
+            if (!(md->rep_host[r].flag & 1)) md->rep_host[r].flag |= 2;
+            md->rep_host[r].overflow = 0;
+            md->rep_host[r].cand_pairs2 = 0;
+        }
+        regrown = true;
+        rc = md_upload_rep(md);
+        if (rc != CHX_OK) return rc;
+        k_md_take_ref<<<gp, 256, 0, st>>>(g, md->rep, md->xs, md->refi);
+        CHX_LAUNCHED(ctx);
     }
     chx_set_error("neighbour table overflow: more than %d candidates per block", md->tcap * 32);
     return CHX_NEIGHBOR_OVERFLOW;
 }
 
-static int md_force(chx_ljmd* md, int step, bool energy, int honor_halt, double* e_dev) {
+static int md_force(chx_ljmd* md, int mode, int step, bool energy, int report_interval, double* e_dev) {
     const MdGeom& g = md->g;
     const dim3 gf(chx_div_up(g.nblk, FW), md->R);
-    const int c = md->cur;
     if (energy)
         k_md_force<true><<<gf, FW * 32, 0, md->ctx->stream>>>(
-            md->xs[c], md->fs, md->refu[c], md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md), md->tcap,
-            md->ctrl, md->rep, step, honor_halt, e_dev);
+            md->xs, md->fs, md->refu, md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md), md->tcap,
+            md->rep, mode, step, report_interval, md->R, e_dev);
     else
         k_md_force<false><<<gf, FW * 32, 0, md->ctx->stream>>>(
-            md->xs[c], md->fs, md->refu[c], md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md), md->tcap,
-            md->ctrl, md->rep, step, honor_halt, e_dev);
+            md->xs, md->fs, md->refu, md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md), md->tcap,
+            md->rep, mode, step, report_interval, md->R, e_dev);
     CHX_LAUNCHED(md->ctx);
     return CHX_OK;
 }
@@ -726,33 +932,33 @@ int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
     md->ctx = ctx;
     md->p = *p;
     md->R = p->n_replicas;
-    md->cur = 0;
-    md->internal_skin = (p->internal_skin > 0.f && p->internal_skin <= p->skin) ? p->internal_skin : p->skin;
+    // internal skin: a tuning knob (fewer candidate pairs vs more frequent table rebuilds)
+    float skin_int = p->internal_skin > 0.f ? p->internal_skin : 0.35f * p->sigma;
+    if (p->skin > 0.f && skin_int > p->skin) skin_int = p->skin;
+    md->internal_skin = skin_int;
     MdGeom& g = md->g;
     g.box = make_box(p->lx, p->ly, p->lz);
     g.inv_lx = 1.0f / p->lx; g.inv_ly = 1.0f / p->ly; g.inv_lz = 1.0f / p->lz;
     g.n = p->n;
     g.nblk = chx_div_up(p->n, 32);
     g.np = g.nblk * 32;
-    // ~4 particles per fine cell, at most 64 cells per edge (6 Morton bits)
+    // 2^bits cells per edge, about 8 particles per cell, at most 128 cells per edge
+    g.bits = 0;
+    while (g.bits < 7 && (double)(1u << (3 * (g.bits + 1))) * 6.0 <= (double)p->n) ++g.bits;
+    g.nb = 1 << g.bits;
+    g.ncell = g.nb * g.nb * g.nb;
+    g.cx = p->lx / g.nb; g.cy = p->ly / g.nb; g.cz = p->lz / g.nb;
+    g.inv_cx = g.nb / p->lx; g.inv_cy = g.nb / p->ly; g.inv_cz = g.nb / p->lz;
+    // initial table capacity: 1.5x the mean number of candidates of a compact block
     const double vol = (double)p->lx * p->ly * p->lz;
-    const double edge = cbrt(4.0 * vol / (double)p->n);
-    auto pick = [&](double L) { int c = (int)floor(L / edge); return c < 1 ? 1 : (c > 64 ? 64 : c); };
-    g.ncx = pick(p->lx); g.ncy = pick(p->ly); g.ncz = pick(p->lz);
-    int mx = g.ncx > g.ncy ? g.ncx : g.ncy; mx = mx > g.ncz ? mx : g.ncz;
-    g.bits = 1;
-    while ((1 << g.bits) < mx) ++g.bits;
-    g.ncm = 1 << (3 * g.bits);
-    g.cx = p->lx / g.ncx; g.cy = p->ly / g.ncy; g.cz = p->lz / g.ncz;
-    g.inv_cx = g.ncx / p->lx; g.inv_cy = g.ncy / p->ly; g.inv_cz = g.ncz / p->lz;
-    // initial table capacity: 2x the mean number of candidates of a compact block
     const double rho = (double)p->n / vol;
     const double Rl = p->cutoff + md->internal_skin;
     const double a = cbrt(32.0 / rho);
     const double mink = a * a * a + 6 * a * a * Rl + 3 * M_PI * a * Rl * Rl + 4.0 / 3.0 * M_PI * Rl * Rl * Rl;
     double cand = mink * rho;
     if (cand > p->n) cand = p->n;
-    md->tcap = (int)(2.0 * cand / 32.0) + 4;
+    md->tcap = (int)(1.5 * cand / 32.0) + 4;
+    md->qcap = ((int)(2.5 * cand) + 256 + 31) & ~31;
     md->rebuilds = 0; md->steps = 0; md->have_state = false;
     md->launches0 = ctx->launches;
     int rc = md_alloc(md);
@@ -764,11 +970,12 @@ int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
 int chx_ljmd_destroy(chx_ljmd* md) {
     if (!md) return CHX_OK;
     cudaStreamSynchronize(md->ctx->stream);
-    for (int k = 0; k < 2; ++k) { cudaFree(md->xs[k]); cudaFree(md->vs[k]); cudaFree(md->refu[k]); }
-    cudaFree(md->fs); cudaFree(md->refi); cudaFree(md->cell_count); cudaFree(md->cell_start);
+    cudaFree(md->xs); cudaFree(md->vs); cudaFree(md->refu); cudaFree(md->xs_t); cudaFree(md->vs_t);
+    cudaFree(md->ru_t); cudaFree(md->fs); cudaFree(md->refi); cudaFree(md->cell_count);
+    cudaFree(md->cell_start); cudaFree(md->cell_range); cudaFree(md->lin2h); cudaFree(md->h2lin);
     cudaFree(md->cell_of); cudaFree(md->order); cudaFree(md->tiles); cudaFree(md->ntiles);
-    cudaFree(md->generic); cudaFree(md->bcenter); cudaFree(md->ctrl); cudaFree(md->rep); cudaFree(md->e_scratch);
-    cudaFreeHost(md->ctrl_host); cudaFreeHost(md->rep_host);
+    cudaFree(md->generic); cudaFree(md->bcenter); cudaFree(md->rep);
+    cudaFreeHost(md->rep_host);
     delete md;
     return CHX_OK;
 }
@@ -783,15 +990,19 @@ int chx_ljmd_set_state(chx_ljmd* md, const float* x, const float* v, const float
         md->rep_host[r] = MdRep();
         md->rep_host[r].kT = kT_per_replica_host ? kT_per_replica_host[r] : md->p.kT;
         md->rep_host[r].user_step = -1;
+        md->rep_host[r].lo = 0;
+        md->rep_host[r].halt = HALT_NONE;
+        md->rep_host[r].flag = 1;
+        md->rep_host[r].redo_step = -2;
     }
-    CHX_CUDA(cudaMemcpyAsync(md->rep, md->rep_host, md->R * sizeof(MdRep), cudaMemcpyHostToDevice, st));
-    CHX_CUDA(cudaMemsetAsync(md->ctrl, 0, sizeof(MdCtrl), st));
-    const dim3 gp(chx_div_up(g.np, 256), md->R);
-    k_md_import<<<gp, 256, 0, st>>>(x, v, mass, g, md->xs[md->cur], md->vs[md->cur], md->refu[md->cur]);
-    CHX_LAUNCHED(ctx);
-    int rc = md_rebuild(md);
+    int rc = md_upload_rep(md);
     if (rc != CHX_OK) return rc;
-    rc = md_force(md, -2, false, 0, nullptr);
+    const dim3 gp(chx_div_up(g.np, 256), md->R);
+    k_md_import<<<gp, 256, 0, st>>>(x, v, mass, g, md->xs, md->vs, md->refu);
+    CHX_LAUNCHED(ctx);
+    rc = md_rebuild(md);
+    if (rc != CHX_OK) return rc;
+    rc = md_force(md, FMODE_ALL, -2, false, 0, nullptr);
     if (rc != CHX_OK) return rc;
     md->have_state = true;
     return CHX_OK;
@@ -802,11 +1013,10 @@ int chx_ljmd_get_state(chx_ljmd* md, float* x, float* v, float* force, float* re
     const MdGeom& g = md->g;
     const dim3 gp(chx_div_up(g.np, 256), md->R);
     cudaStream_t st = md->ctx->stream;
-    const int c = md->cur;
-    if (x) { k_md_export_ids<<<gp, 256, 0, st>>>(md->xs[c], md->xs[c], g, x); CHX_LAUNCHED(md->ctx); }
-    if (v) { k_md_export_ids<<<gp, 256, 0, st>>>(md->vs[c], md->xs[c], g, v); CHX_LAUNCHED(md->ctx); }
-    if (force) { k_md_export_ids<<<gp, 256, 0, st>>>(md->fs, md->xs[c], g, force); CHX_LAUNCHED(md->ctx); }
-    if (ref_x) { k_md_export_ids<<<gp, 256, 0, st>>>(md->refu[c], md->xs[c], g, ref_x); CHX_LAUNCHED(md->ctx); }
+    if (x) { k_md_export_ids<<<gp, 256, 0, st>>>(md->xs, md->xs, g, x); CHX_LAUNCHED(md->ctx); }
+    if (v) { k_md_export_ids<<<gp, 256, 0, st>>>(md->vs, md->xs, g, v); CHX_LAUNCHED(md->ctx); }
+    if (force) { k_md_export_ids<<<gp, 256, 0, st>>>(md->fs, md->xs, g, force); CHX_LAUNCHED(md->ctx); }
+    if (ref_x) { k_md_export_ids<<<gp, 256, 0, st>>>(md->refu, md->xs, g, ref_x); CHX_LAUNCHED(md->ctx); }
     return CHX_OK;
 }
 
@@ -822,16 +1032,19 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     const bool report = energies_dev != nullptr && report_interval > 0;
     const int n_reports = report ? (nsteps + report_interval - 1) / report_interval : 0;
     CHX_REQUIRE(!report || n_reports <= n_reports_capacity, "energy buffer too small");
+    const int rint = report ? report_interval : 0;
     // upload loop keys (parity 0), reset per-run control
-    CHX_CUDA(cudaMemcpyAsync(md->rep_host, md->rep, R * sizeof(MdRep), cudaMemcpyDeviceToHost, st));
-    CHX_CUDA(cudaStreamSynchronize(st));
+    int rc = md_download_rep(md);
+    if (rc != CHX_OK) return rc;
     for (int r = 0; r < R; ++r) {
-        md->rep_host[r].key[0][0] = keys_host[2 * r];
-        md->rep_host[r].key[0][1] = keys_host[2 * r + 1];
-        md->rep_host[r].user_step = -1;
+        MdRep& q = md->rep_host[r];
+        q.key[0][0] = keys_host[2 * r];
+        q.key[0][1] = keys_host[2 * r + 1];
+        q.user_step = -1;
+        q.lo = 0; q.halt = HALT_NONE; q.flag = 0; q.redo_step = -2;
     }
-    CHX_CUDA(cudaMemcpyAsync(md->rep, md->rep_host, R * sizeof(MdRep), cudaMemcpyHostToDevice, st));
-    CHX_CUDA(cudaMemsetAsync(&md->ctrl->halt_step, 0x7f, sizeof(int), st));
+    rc = md_upload_rep(md);
+    if (rc != CHX_OK) return rc;
     if (report) CHX_CUDA(cudaMemsetAsync(energies_dev, 0, sizeof(double) * R * n_reports, st));
 
     const float dt = md->p.dt, gamma = md->p.gamma;
@@ -845,40 +1058,60 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     const dim3 gb(chx_div_up(g.np, 256), R);
     const int CH = 32;
 
-    auto force_at = [&](int s, int honor) -> int {
-        const bool en = report && (s % report_interval == 0);
-        // energies are stored [report][replica]; the kernel indexes energy_out[r]
-        double* e = en ? energies_dev + (size_t)(s / report_interval) * R : nullptr;
-        return md_force(md, s, en, honor, e);
+    auto launch_steps = [&](int s0, int s1) -> int {
+        for (int s = s0; s < s1; ++s) {
+            k_md_baoab<<<gb, 256, 0, st>>>(md->xs, md->vs, md->fs, md->refi, md->refu, g, h, a, bcoef,
+                                           hs_user, hs_int2, s, md->rep);
+            CHX_LAUNCHED(ctx);
+            const bool en = report && (s % report_interval == 0);
+            int rc2 = md_force(md, FMODE_STEP, s, en, rint, energies_dev);
+            if (rc2 != CHX_OK) return rc2;
+        }
+        return CHX_OK;
     };
 
     int t = 0;
     while (t < nsteps) {
-        const int chunk = nsteps - t < CH ? nsteps - t : CH;
-        for (int s = t; s < t + chunk; ++s) {
-            k_md_baoab<<<gb, 256, 0, st>>>(md->xs[md->cur], md->vs[md->cur], md->fs, md->refi,
-                                           md->refu[md->cur], g, h, a, bcoef, hs_user, hs_int2, s,
-                                           s > 0 ? 1 : 0, md->ctrl, md->rep);
-            CHX_LAUNCHED(ctx);
-            int rc = force_at(s, 1);
+        const int te = nsteps - t < CH ? nsteps : t + CH;
+        rc = launch_steps(t, te);
+        if (rc != CHX_OK) return rc;
+        rc = md_download_rep(md);
+        if (rc != CHX_OK) return rc;
+        // replicas whose tables went stale inside the chunk: rebuild, redo that step's forces, catch up
+        for (;;) {
+            int first = HALT_NONE;
+            for (int r = 0; r < R; ++r) {
+                MdRep& q = md->rep_host[r];
+                if (q.halt < te) {
+                    q.flag = 1; q.redo_step = q.halt; q.lo = q.halt + 1; q.halt = HALT_NONE;
+                    q.overflow = 0; q.cand_pairs2 = 0;
+                    if (q.redo_step < first) first = q.redo_step;
+                } else {
+                    q.flag = 0; q.lo = HALT_NONE;   // done with this chunk
+                }
+            }
+            if (first == HALT_NONE) break;
+            rc = md_upload_rep(md);
+            if (rc != CHX_OK) return rc;
+            rc = md_rebuild(md);
+            if (rc != CHX_OK) return rc;
+            rc = md_force(md, FMODE_REDO, -2, report, rint, energies_dev);
+            if (rc != CHX_OK) return rc;
+            rc = launch_steps(first + 1, te);
+            if (rc != CHX_OK) return rc;
+            rc = md_download_rep(md);
             if (rc != CHX_OK) return rc;
         }
-        CHX_CUDA(cudaMemcpyAsync(md->ctrl_host, md->ctrl, sizeof(MdCtrl), cudaMemcpyDeviceToHost, st));
-        CHX_CUDA(cudaStreamSynchronize(st));
-        const int hs = md->ctrl_host->halt_step;
-        if (hs == HALT_NONE) { t += chunk; continue; }
-        int rc = md_rebuild(md);
+        for (int r = 0; r < R; ++r) { md->rep_host[r].lo = te; md->rep_host[r].flag = 0; }
+        rc = md_upload_rep(md);
         if (rc != CHX_OK) return rc;
-        CHX_CUDA(cudaMemsetAsync(&md->ctrl->halt_step, 0x7f, sizeof(int), st));
-        rc = force_at(hs, 0);
-        if (rc != CHX_OK) return rc;
-        t = hs + 1;
+        t = te;
     }
     // trailing B of the last step (integrators.py:195)
-    k_md_kick<<<chx_div_up((long long)R * g.np, 256), 256, 0, st>>>(md->vs[md->cur], md->fs, g, h, R);
+    k_md_kick<<<chx_div_up((long long)R * g.np, 256), 256, 0, st>>>(md->vs, md->fs, g, h, R);
     CHX_LAUNCHED(ctx);
-    CHX_CUDA(cudaMemcpyAsync(md->rep_host, md->rep, R * sizeof(MdRep), cudaMemcpyDeviceToHost, st));
-    CHX_CUDA(cudaStreamSynchronize(st));
+    rc = md_download_rep(md);
+    if (rc != CHX_OK) return rc;
     for (int r = 0; r < R; ++r) {
         keys_host[2 * r] = md->rep_host[r].key[nsteps & 1][0];
         keys_host[2 * r + 1] = md->rep_host[r].key[nsteps & 1][1];
@@ -891,21 +1124,28 @@ int chx_ljmd_energy(chx_ljmd* md, double* energy_dev) {
     CHX_REQUIRE(md && md->have_state && energy_dev, "engine has no state or energy_dev is NULL");
     cudaStream_t st = md->ctx->stream;
     CHX_CUDA(cudaMemsetAsync(energy_dev, 0, sizeof(double) * md->R, st));
-    CHX_CUDA(cudaMemsetAsync(&md->ctrl->int_pairs2, 0, sizeof(unsigned long long), st));
-    return md_force(md, -2, true, 0, energy_dev);
+    int rc = md_download_rep(md);
+    if (rc != CHX_OK) return rc;
+    for (int r = 0; r < md->R; ++r) md->rep_host[r].int_pairs2 = 0;
+    rc = md_upload_rep(md);
+    if (rc != CHX_OK) return rc;
+    return md_force(md, FMODE_ALL, -2, true, 0, energy_dev);
 }
 
 int chx_ljmd_stats(chx_ljmd* md, long long* stats_host) {
     CHX_REQUIRE(md && stats_host, "NULL argument");
-    cudaStream_t st = md->ctx->stream;
-    CHX_CUDA(cudaMemcpyAsync(md->ctrl_host, md->ctrl, sizeof(MdCtrl), cudaMemcpyDeviceToHost, st));
-    CHX_CUDA(cudaMemcpyAsync(md->rep_host, md->rep, md->R * sizeof(MdRep), cudaMemcpyDeviceToHost, st));
-    CHX_CUDA(cudaStreamSynchronize(st));
+    int rc = md_download_rep(md);
+    if (rc != CHX_OK) return rc;
     long long user = 0;
-    for (int r = 0; r < md->R; ++r) user += md->rep_host[r].user_rebuilds;
+    unsigned long long cand2 = 0, int2 = 0;
+    for (int r = 0; r < md->R; ++r) {
+        user += md->rep_host[r].user_rebuilds;
+        cand2 += md->rep_host[r].cand_pairs2;
+        int2 += md->rep_host[r].int_pairs2;
+    }
     stats_host[0] = md->rebuilds;
-    stats_host[1] = (long long)(md->ctrl_host->cand_pairs2 / 2);
-    stats_host[2] = (long long)(md->ctrl_host->int_pairs2 / 2);
+    stats_host[1] = (long long)(cand2 / 2);
+    stats_host[2] = (long long)(int2 / 2);
     stats_host[3] = md->steps;
     stats_host[4] = md->ctx->launches - md->launches0;
     stats_host[5] = user;
@@ -939,7 +1179,7 @@ extern "C" {
 int chx_ljmd_force_only(chx_ljmd* md, int repeats) {
     CHX_REQUIRE(md && md->have_state, "engine has no state");
     for (int k = 0; k < repeats; ++k) {
-        int rc = md_force(md, -2, false, 0, nullptr);
+        int rc = md_force(md, FMODE_ALL, -2, false, 0, nullptr);
         if (rc != CHX_OK) return rc;
     }
     return CHX_OK;

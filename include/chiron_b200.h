@@ -169,8 +169,9 @@ typedef struct {
     float cutoff, skin;    /* nm; rebuild when any displacement >= skin/2 (neighbors.py:864) */
     float dt, gamma, kT;   /* ps, 1/ps, kJ/mol */
     int n_replicas;        /* >= 1: independent replicas batched in one launch (blockIdx.y) */
-    float internal_skin;   /* 0 = use `skin`; otherwise the (smaller) skin of the engine's own
-                              neighbour tables -- a tuning knob, results do not depend on it */
+    float internal_skin;   /* skin of the engine's own neighbour tables, capped at `skin`; 0 = pick
+                              automatically (0.35 sigma).  A tuning knob: the pair set evaluated
+                              each step (d < cutoff, exact predicate) does not depend on it */
 } chx_ljmd_params;
 
 int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out);

@@ -481,8 +481,18 @@ def test_fused_engine_force_and_energy_vs_bruteforce(cuda_device):
         assert np.isclose(e, e_ref, rtol=1e-5)
         assert np.allclose(_np(F), F_ref, rtol=1e-5, atol=1e-5 * float(np.abs(F_ref).max()))
         assert st["interacting_pairs"] == n_int
-        rows = pairs.neighbor_rows(x, box, rc + 0.5)
-        assert st["candidate_pairs"] == sum(r.size for r in rows)
+        # the engine's own tables are conservative (fast predicate with a safety margin) on the
+        # internal skin: at least every pair within rc + skin_int, nothing beyond the margin
+        for skin_int in (0.5, 0.12):
+            e2 = LJLangevinEngine(n, np.diag(box), sigma, eps, rc, 0.5, 0.001, 1.0, 2.494, internal_skin=skin_int)
+            e2.set_state(x, np.zeros_like(x), np.full(n, 39.948, f32))
+            cand = e2.stats()["candidate_pairs"]
+            lo = sum(r.size for r in pairs.neighbor_rows(x, box, rc + skin_int))
+            hi = sum(r.size for r in pairs.neighbor_rows(x, box, (rc + skin_int) * (1 + 4e-5) + 2e-6))
+            assert lo <= cand <= hi
+            _, _, F2, _ = e2.get_state(want_force=True)
+            assert np.allclose(_np(F2), F_ref, rtol=1e-5, atol=1e-5 * float(np.abs(F_ref).max()))
+            e2.close()
         eng.close()
 
 
