@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "--fmad=true",               # predicates use __f*_rn intrinsics, which are never contracted
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
-]
+] + os.environ.get("CHX_NVCC_EXTRA", "").split()
 
 
 def _sources():

@@ -28,6 +28,7 @@
 // tracked exactly and independently (refu / user_step), so the nbr_list object handed back to
 // the caller is what the reference would hold.  The cutoff predicate d < rc uses the reference's
 // exact fp32 operation order whenever a pair is within a few ulps of the cutoff.
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 
@@ -77,6 +78,12 @@ struct chx_ljmd {
     float internal_skin;
     long long rebuilds, steps, launches0;
     bool have_state;
+    int* step_base;                  // device int: first step of the chunk a graph replay runs
+    cudaStream_t cap_stream;
+    cudaGraphExec_t chunk_graph;     // CH x (BAOAB, force) captured once; re-captured when tcap changes
+    int chunk_graph_tcap;
+    bool no_graph;                   // CHX_MD_NOGRAPH=1: launch every kernel directly
+    bool packed;                     // packed-fp32 (FFMA2) inner loop; CHX_MD_SCALAR=1 selects the scalar one
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -199,7 +206,7 @@ __global__ void k_md_cellcount(const float4* __restrict__ xs, MdGeom g, const in
     atomicAdd(&count[(size_t)r * (g.ncell + 1) + h], 1);
 }
 
-// one CTA per replica: exclusive scan over the cells in Hilbert order, 1024 cells per pass
+// one CTA per replica: exclusive scan over the cells in Hilbert order, 4096 cells per pass
 __global__ void __launch_bounds__(1024)
 k_md_scan(int* __restrict__ count, int* __restrict__ start, int2* __restrict__ range,
           const int* __restrict__ h2lin, int ncell, const MdRep* __restrict__ rep) {
@@ -212,10 +219,13 @@ k_md_scan(int* __restrict__ count, int* __restrict__ start, int2* __restrict__ r
     range += (size_t)r * ncell;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     int base = 0;
-    for (int c0 = 0; c0 < ncell; c0 += 1024) {
-        const int c = c0 + t;
-        const int v = c < ncell ? count[c] : 0;
-        int inc = v;
+    for (int c0 = 0; c0 < ncell; c0 += 4096) {
+        const int c = c0 + 4 * t;
+        int v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = c + u < ncell ? count[c + u] : 0;
+        const int mine = v[0] + v[1] + v[2] + v[3];
+        int inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int u = __shfl_up_sync(FULL, inc, o);
@@ -234,11 +244,15 @@ k_md_scan(int* __restrict__ count, int* __restrict__ start, int2* __restrict__ r
             if (lane == 31) total = s;
         }
         __syncthreads();
-        const int excl = base + inc - v + (w > 0 ? wsum[w - 1] : 0);
-        if (c < ncell) {
-            start[c] = excl;
-            count[c] = 0;
-            range[h2lin[c]] = make_int2(excl, excl + v);
+        int excl = base + inc - mine + (w > 0 ? wsum[w - 1] : 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (c + u < ncell) {
+                start[c + u] = excl;
+                count[c + u] = 0;
+                range[h2lin[c + u]] = make_int2(excl, excl + v[u]);
+            }
+            excl += v[u];
         }
         base += total;
         __syncthreads();
@@ -437,42 +451,55 @@ k_md_build(const float4* __restrict__ xs_all, const int2* __restrict__ range_all
     if (qn > qcap) qn = qcap;
     __syncwarp();
 
-    // ---- 2. dense test ----
+    // ---- 2. dense test: one candidate per lane against the 32 particles of the block ----
+    {
+        float4 me = xi;
+        if (!gen) {
+            me.x -= g.box.lx * rintf((me.x - bcx) * g.inv_lx);
+            me.y -= g.box.ly * rintf((me.y - bcy) * g.inv_ly);
+            me.z -= g.box.lz * rintf((me.z - bcz) * g.inv_lz);
+        }
+        stage[lane] = me;
+    }
+    const unsigned validmask = __ballot_sync(FULL, valid);
+    __syncwarp();
     int kept = 0;
     unsigned long long pairs = 0;
     for (int q0 = 0; q0 < qn; q0 += 32) {
-        const int cnt = min(32, qn - q0);
-        if (lane < cnt) {
-            const int p = (int)queue[q0 + lane];
-            float4 xj = xs[p];
-            if (!gen) {
-                xj.x -= g.box.lx * rintf((xj.x - bcx) * g.inv_lx);
-                xj.y -= g.box.ly * rintf((xj.y - bcy) * g.inv_ly);
-                xj.z -= g.box.lz * rintf((xj.z - bcz) * g.inv_lz);
-            }
-            xj.w = __int_as_float(p);
-            stage[lane] = xj;
+        const bool have = q0 + lane < qn;
+        const int p = have ? (int)queue[q0 + lane] : b * 32;
+        float4 xj = xs[p];
+        if (!gen) {
+            xj.x -= g.box.lx * rintf((xj.x - bcx) * g.inv_lx);
+            xj.y -= g.box.ly * rintf((xj.y - bcy) * g.inv_ly);
+            xj.z -= g.box.lz * rintf((xj.z - bcz) * g.inv_lz);
         }
-        __syncwarp();
-        for (int k = 0; k < cnt; ++k) {
-            const float4 xj = stage[k];
-            const int p = __float_as_int(xj.w);
-            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        uint32_t col = 0u;   // bit k: particle k of the block is within Rm of this candidate
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float4 xk = stage[k];
+            float dx = xk.x - xj.x, dy = xk.y - xj.y, dz = xk.z - xj.z;
             if (gen) {
                 dx -= g.box.lx * rintf(dx * g.inv_lx);
                 dy -= g.box.ly * rintf(dy * g.inv_ly);
                 dz -= g.box.lz * rintf(dz * g.inv_lz);
             }
             const float r2 = dx * dx + dy * dy + dz * dz;
-            const bool hit = valid && p != i && r2 < Rm2;
-            const unsigned bal = __ballot_sync(FULL, hit);
-            if (bal) {
-                // kept <= q0 + k: the slot being overwritten has already been consumed
-                if (lane == 0) { queue[kept] = (uint32_t)p; colmask[kept] = bal; }
-                ++kept;
-                pairs += hit ? 1ull : 0ull;
-            }
+            col |= (r2 < Rm2 ? 1u : 0u) << k;
         }
+        col &= validmask;
+        const unsigned self = (unsigned)(p - b * 32);
+        if (self < 32u) col &= ~(1u << self);
+        if (!have) col = 0u;
+        const unsigned bal = __ballot_sync(FULL, col != 0u);
+        // every lane has read its queue entry: the compacted list can overwrite the queue in place
+        if (col != 0u) {
+            const int pos = kept + __popc(bal & ((1u << lane) - 1u));
+            queue[pos] = (uint32_t)p;
+            colmask[pos] = col;
+        }
+        kept += __popc(bal);
+        pairs += (unsigned long long)__popc(col);
         __syncwarp();
     }
 
@@ -483,18 +510,20 @@ k_md_build(const float4* __restrict__ xs_all, const int2* __restrict__ range_all
     for (int t = 0; t < Tw; ++t) {
         const int k = lane * T + t;            // round-robin deal: tile t takes t, T+t, 2T+t, ...
         const bool have = k < kept;
-        const uint32_t myB = have ? colmask[k] : 0u;
+        uint32_t x = have ? colmask[k] : 0u;   // column word of slot `lane`: bit i = particle i
         uint32_t myIdx = have ? queue[k] : (uint32_t)(b * 32);
-        uint32_t mine = 0u;
+        // 32x32 bit transpose across the warp: afterwards lane i holds the mask of particle i
+        uint32_t m = 0x0000ffffu;
 #pragma unroll
-        for (int l = 0; l < 32; ++l) {
-            const unsigned wv = __ballot_sync(FULL, (myB >> l) & 1u);
-            if (lane == l) mine = wv;
+        for (int j = 16; j > 0; j >>= 1) {
+            const uint32_t y = __shfl_xor_sync(FULL, x, j);
+            x = (lane & j) ? ((x & (m << j)) | ((y >> j) & m)) : ((x & m) | ((y & m) << j));
+            m ^= m << (j >> 1);
         }
-        const int trips = warp_max_i(__popc(mine));
+        const int trips = warp_max_i(__popc(x));
         if (lane == 0) myIdx |= (uint32_t)trips << 24;
         tiles[(size_t)t * 64 + lane] = myIdx;
-        tiles[(size_t)t * 64 + 32 + lane] = mine;
+        tiles[(size_t)t * 64 + 32 + lane] = x;
     }
     if (lane == 0) {
         ntiles_all[(size_t)r * g.nblk + b] = Tw;
@@ -523,19 +552,34 @@ struct LjConst {
 #define FMODE_REDO 1   // after a rebuild: replicas with flag set, step = rep.redo_step
 #define FMODE_ALL  2   // every replica, no step (set_state, energy(), force_only)
 
-#define FW 4  // warps per CTA in the force kernel
+#ifndef CHX_FW
+#define CHX_FW 1
+#endif
+#define FW CHX_FW  // warps per CTA in the force kernel
 
-template <bool ENERGY, bool GEN>
+template <bool ENERGY, bool GEN, bool PACKED>
 __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, const uint32_t* __restrict__ tp,
                                              int nt, const float4 xi0, const float4 xi, const float4 bc,
                                              const MdGeom& g, const LjConst& lj, int lane, float& fx,
                                              float& fy, float& fz, float& e_acc, unsigned& npair) {
+    // software pipeline over the tiles: index/mask words are fetched two tiles ahead and the j
+    // positions one tile ahead, so the L2/HBM latency of a tile hides behind the previous one
+    if (nt <= 0) return;
+    uint32_t code_n = tp[lane], m_n = tp[32 + lane];
+    float4 xj_n = xs[code_n & 0xffffffu];
+    const int t1 = nt > 1 ? 1 : 0;
+    uint32_t code_nn = tp[t1 * 64 + lane], m_nn = tp[t1 * 64 + 32 + lane];
     for (int t = 0; t < nt; ++t, tp += 64) {
-        const uint32_t code = tp[lane];
-        uint32_t m = tp[32 + lane];
-        const int j = (int)(code & 0xffffffu);
+        const uint32_t code = code_n;
+        uint32_t m = m_n;
+        float4 xj = xj_n;
+        code_n = code_nn; m_n = m_nn;
+        xj_n = xs[code_n & 0xffffffu];
+        {
+            const int t2 = (t + 2 < nt ? 2 : nt - 1 - t) * 64;
+            code_nn = tp[t2 + lane]; m_nn = tp[t2 + 32 + lane];
+        }
         const int trips = (int)(__shfl_sync(FULL, code, 0) >> 24);
-        float4 xj = xs[j];
         if (!GEN) {
             // positions are wrapped every step (integrators.py:239), so a particle may have jumped
             // by a box length since the build: images are resolved against the block centre, once
@@ -545,33 +589,86 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
             xj.z -= g.box.lz * rintf((xj.z - bc.z) * g.inv_lz);
         }
         uint32_t bandmask = 0u;   // pairs within a few ulps of the cutoff, decided after the loop
-        for (int it = 0; it < trips; ++it) {
-            const uint32_t iso = m & (0u - m);     // lowest set bit (0 when this lane is done)
-            m ^= iso;
-            const int bit = 31 - __clz(iso);       // -1 when done: the shuffles read lane 31
-            const float sx = __shfl_sync(FULL, xj.x, bit);
-            const float sy = __shfl_sync(FULL, xj.y, bit);
-            const float sz = __shfl_sync(FULL, xj.z, bit);
-            float dx = xi.x - sx, dy = xi.y - sy, dz = xi.z - sz;
-            if (GEN) {
-                dx -= g.box.lx * rintf(dx * g.inv_lx);
-                dy -= g.box.ly * rintf(dy * g.inv_ly);
-                dz -= g.box.lz * rintf(dz * g.inv_lz);
+        if (GEN || !PACKED) {
+            for (int it = 0; it < trips; ++it) {
+                const uint32_t iso = m & (0u - m);     // lowest set bit (0 when this lane is done)
+                m ^= iso;
+                const int bit = 31 - __clz(iso);       // -1 when done: the shuffles read lane 31
+                const float sx = __shfl_sync(FULL, xj.x, bit);
+                const float sy = __shfl_sync(FULL, xj.y, bit);
+                const float sz = __shfl_sync(FULL, xj.z, bit);
+                float dx = xi.x - sx, dy = xi.y - sy, dz = xi.z - sz;
+                if (GEN) {
+                    dx -= g.box.lx * rintf(dx * g.inv_lx);
+                    dy -= g.box.ly * rintf(dy * g.inv_ly);
+                    dz -= g.box.lz * rintf(dz * g.inv_lz);
+                }
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                const bool in = (iso != 0u) && (r2 < lj.rc2_lo);
+                if (!in && r2 < lj.rc2_hi) bandmask |= iso;   // iso == 0 for finished lanes: no effect
+                const float inv = rcp_approx(r2);
+                const float inv3 = inv * inv * inv;
+                float f = (inv * inv3) * fmaf(lj.c12f, inv3, -lj.c6f);
+                f = in ? f : 0.f;
+                fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
+                if (ENERGY) {
+                    const float e = inv3 * fmaf(lj.c12e, inv3, -lj.c6e);
+                    e_acc += in ? e : 0.f;
+                    npair += in ? 1u : 0u;
+                }
             }
-            const float r2 = dx * dx + dy * dy + dz * dz;
-            const bool in = (iso != 0u) && (r2 < lj.rc2_lo);
-            if (!in && r2 < lj.rc2_hi) bandmask |= iso;   // iso == 0 for finished lanes: no effect
-            const float inv = rcp_approx(r2);
-            const float inv3 = inv * inv * inv;
-            float f = (inv * inv3) * fmaf(lj.c12f, inv3, -lj.c6f);
-            f = in ? f : 0.f;
-            fx = fmaf(f, dx, fx); fy = fmaf(f, dy, fy); fz = fmaf(f, dz, fz);
-            if (ENERGY) {
-                const float e = inv3 * fmaf(lj.c12e, inv3, -lj.c6e);
-                e_acc += in ? e : 0.f;
-                npair += in ? 1u : 0u;
+        } else {
+            // two set bits per trip, arithmetic on packed fp32 pairs (FFMA2/FMUL2/FADD2 of sm_100:
+            // one issue slot for two pairs -- this loop is issue bound, not FMA-pipe bound)
+            const float2 xix = make_float2(xi.x, xi.x), xiy = make_float2(xi.y, xi.y), xiz = make_float2(xi.z, xi.z);
+            const float2 c12f = make_float2(lj.c12f, lj.c12f), c6f = make_float2(-lj.c6f, -lj.c6f);
+            const float2 neg1 = make_float2(-1.f, -1.f);
+            float2 fx2 = make_float2(0.f, 0.f), fy2 = fx2, fz2 = fx2, e2 = fx2;
+            const int trips2 = (trips + 1) >> 1;
+            for (int it = 0; it < trips2; ++it) {
+                const uint32_t iso0 = m & (0u - m);
+                m ^= iso0;
+                const uint32_t iso1 = m & (0u - m);
+                m ^= iso1;
+                const int b0 = 31 - __clz(iso0), b1 = 31 - __clz(iso1);
+                float2 sx, sy, sz;
+                sx.x = __shfl_sync(FULL, xj.x, b0); sx.y = __shfl_sync(FULL, xj.x, b1);
+                sy.x = __shfl_sync(FULL, xj.y, b0); sy.y = __shfl_sync(FULL, xj.y, b1);
+                sz.x = __shfl_sync(FULL, xj.z, b0); sz.y = __shfl_sync(FULL, xj.z, b1);
+                const float2 dx = __ffma2_rn(sx, neg1, xix);
+                const float2 dy = __ffma2_rn(sy, neg1, xiy);
+                const float2 dz = __ffma2_rn(sz, neg1, xiz);
+                float2 r2 = __fmul2_rn(dx, dx);
+                r2 = __ffma2_rn(dy, dy, r2);
+                r2 = __ffma2_rn(dz, dz, r2);
+                const bool in0 = (iso0 != 0u) && (r2.x < lj.rc2_lo);
+                const bool in1 = (iso1 != 0u) && (r2.y < lj.rc2_lo);
+                if (!in0 && r2.x < lj.rc2_hi) bandmask |= iso0;
+                if (!in1 && r2.y < lj.rc2_hi) bandmask |= iso1;
+                float2 inv;
+                inv.x = rcp_approx(r2.x); inv.y = rcp_approx(r2.y);
+                const float2 inv3 = __fmul2_rn(__fmul2_rn(inv, inv), inv);
+                float2 f = __fmul2_rn(__fmul2_rn(inv, inv3), __ffma2_rn(c12f, inv3, c6f));
+                f.x = in0 ? f.x : 0.f;
+                f.y = in1 ? f.y : 0.f;
+                fx2 = __ffma2_rn(f, dx, fx2); fy2 = __ffma2_rn(f, dy, fy2); fz2 = __ffma2_rn(f, dz, fz2);
+                if (ENERGY) {
+                    const float2 c12e = make_float2(lj.c12e, lj.c12e), c6e = make_float2(-lj.c6e, -lj.c6e);
+                    float2 e = __fmul2_rn(inv3, __ffma2_rn(c12e, inv3, c6e));
+                    e.x = in0 ? e.x : 0.f;
+                    e.y = in1 ? e.y : 0.f;
+                    e2 = __fadd2_rn(e2, e);
+                    npair += (in0 ? 1u : 0u) + (in1 ? 1u : 0u);
+                }
             }
+            fx += fx2.x + fx2.y; fy += fy2.x + fy2.y; fz += fz2.x + fz2.y;
+            if (ENERGY) e_acc += e2.x + e2.y;
         }
+        // keep the unused .w of the prefetched float4 live through the tile: otherwise ptxas reuses
+        // that register as a temporary right after the LDG.128 is issued and the write-after-write
+        // hazard stalls the warp for the full load latency (seen as long_scoreboard at the tile top)
+        // (w holds a particle id, never 0x7fffffff: the branch is dead but ptxas cannot know)
+        if (__float_as_int(xj_n.w) == 0x7fffffff) fx = __int_as_float(0x7fc00000);
         if (__any_sync(FULL, bandmask != 0u)) {
             // rare: decide with the reference's exact fp32 predicate (neighbors.py:69-81, :782)
             while (bandmask) {
@@ -604,18 +701,18 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
     }
 }
 
-template <bool ENERGY>
+template <bool ENERGY, bool PACKED>
 __global__ void __launch_bounds__(FW * 32)
 k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
            float4* __restrict__ refu_all, const uint32_t* __restrict__ tiles_all,
            const int* __restrict__ ntiles_all, const uint8_t* __restrict__ generic_all,
            const float4* __restrict__ bcenter_all, MdGeom g, LjConst lj, int tcap,
-           MdRep* __restrict__ rep, int mode, int step_arg, int report_interval, int n_rep,
-           double* __restrict__ energy_out) {
+           MdRep* __restrict__ rep, int mode, int step_arg, const int* __restrict__ step_base,
+           int report_interval, int n_rep, double* __restrict__ energy_out) {
     __shared__ double red[FW];
     __shared__ unsigned long long redn[FW];
     const int r = blockIdx.y;
-    int step = step_arg;
+    int step = step_arg + (step_base ? *step_base : 0);   // graph replays read the chunk's first step
     if (mode == FMODE_STEP) {
         // the tables are stale from step `halt` on: that step's forces are evaluated after the rebuild
         if (!(rep[r].lo <= step && step < *((volatile int*)&rep[r].halt))) return;
@@ -642,12 +739,12 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
         const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
         float fx = 0.f, fy = 0.f, fz = 0.f;
         if (gen) {
-            md_tile_loop<ENERGY, true>(xs, tp, nt, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+            md_tile_loop<ENERGY, true, PACKED>(xs, tp, nt, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
         } else {
             xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
             xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
             xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
-            md_tile_loop<ENERGY, false>(xs, tp, nt, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+            md_tile_loop<ENERGY, false, PACKED>(xs, tp, nt, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
         }
         fs_all[(size_t)r * g.np + i] = make_float4(fx, fy, fz, 0.5f * e_acc);
     }
@@ -678,10 +775,11 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
 __global__ void __launch_bounds__(256)
 k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float4* __restrict__ fs_all,
            const float4* __restrict__ refi_all, const float4* __restrict__ refu_all, MdGeom g,
-           float h, float a, float b, float half_skin_user, float half_skin_int2, int step,
-           MdRep* __restrict__ rep) {
+           float h, float a, float b, float half_skin_user, float half_skin_int2, int step_arg,
+           const int* __restrict__ step_base, MdRep* __restrict__ rep) {
     __shared__ uint32_t sk[2];
     const int r = blockIdx.y;
+    const int step = step_arg + (step_base ? *step_base : 0);
     // a halt raised by ANOTHER block of this same launch (halt == step) must not stop us
     if (!(rep[r].lo <= step && step <= *((volatile int*)&rep[r].halt))) return;
     if (threadIdx.x == 0) {
@@ -744,6 +842,8 @@ k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float
     }
 }
 
+__global__ void k_md_setbase(int* base, int value) { *base = value; }
+
 __global__ void k_md_kick(float4* __restrict__ vs_all, const float4* __restrict__ fs_all, MdGeom g,
                           float h, int R) {
     const size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -784,6 +884,8 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->generic, nb));
     CHX_CUDA(cudaMalloc(&md->bcenter, nb * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->rep, md->R * sizeof(MdRep)));
+    CHX_CUDA(cudaMalloc(&md->step_base, sizeof(int)));
+    md->chunk_graph = nullptr; md->chunk_graph_tcap = -1; md->cap_stream = nullptr;
     CHX_CUDA(cudaMallocHost(&md->rep_host, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMemset(md->rep, 0, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMemset(md->fs, 0, np * sizeof(float4)));
@@ -905,17 +1007,20 @@ static int md_rebuild(chx_ljmd* md) {
     return CHX_NEIGHBOR_OVERFLOW;
 }
 
-static int md_force(chx_ljmd* md, int mode, int step, bool energy, int report_interval, double* e_dev) {
+static int md_force(chx_ljmd* md, int mode, int step, bool energy, int report_interval, double* e_dev,
+                    const int* step_base = nullptr) {
     const MdGeom& g = md->g;
     const dim3 gf(chx_div_up(g.nblk, FW), md->R);
-    if (energy)
-        k_md_force<true><<<gf, FW * 32, 0, md->ctx->stream>>>(
-            md->xs, md->fs, md->refu, md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md), md->tcap,
-            md->rep, mode, step, report_interval, md->R, e_dev);
-    else
-        k_md_force<false><<<gf, FW * 32, 0, md->ctx->stream>>>(
-            md->xs, md->fs, md->refu, md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md), md->tcap,
-            md->rep, mode, step, report_interval, md->R, e_dev);
+#define MD_FORCE_LAUNCH(E, P)                                                                       \
+    k_md_force<E, P><<<gf, FW * 32, 0, md->ctx->stream>>>(                                           \
+        md->xs, md->fs, md->refu, md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md),    \
+        md->tcap, md->rep, mode, step, step_base, report_interval, md->R, e_dev)
+    if (md->packed) {
+        if (energy) MD_FORCE_LAUNCH(true, true); else MD_FORCE_LAUNCH(false, true);
+    } else {
+        if (energy) MD_FORCE_LAUNCH(true, false); else MD_FORCE_LAUNCH(false, false);
+    }
+#undef MD_FORCE_LAUNCH
     CHX_LAUNCHED(md->ctx);
     return CHX_OK;
 }
@@ -960,6 +1065,8 @@ int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
     md->tcap = (int)(1.5 * cand / 32.0) + 4;
     md->qcap = ((int)(2.5 * cand) + 256 + 31) & ~31;
     md->rebuilds = 0; md->steps = 0; md->have_state = false;
+    { const char* e = getenv("CHX_MD_SCALAR"); md->packed = !(e && e[0] == '1'); }
+    { const char* e = getenv("CHX_MD_NOGRAPH"); md->no_graph = e && e[0] == '1'; }
     md->launches0 = ctx->launches;
     int rc = md_alloc(md);
     if (rc != CHX_OK) { delete md; return rc; }
@@ -974,7 +1081,9 @@ int chx_ljmd_destroy(chx_ljmd* md) {
     cudaFree(md->ru_t); cudaFree(md->fs); cudaFree(md->refi); cudaFree(md->cell_count);
     cudaFree(md->cell_start); cudaFree(md->cell_range); cudaFree(md->lin2h); cudaFree(md->h2lin);
     cudaFree(md->cell_of); cudaFree(md->order); cudaFree(md->tiles); cudaFree(md->ntiles);
-    cudaFree(md->generic); cudaFree(md->bcenter); cudaFree(md->rep);
+    cudaFree(md->generic); cudaFree(md->bcenter); cudaFree(md->rep); cudaFree(md->step_base);
+    if (md->chunk_graph) cudaGraphExecDestroy(md->chunk_graph);
+    if (md->cap_stream) cudaStreamDestroy(md->cap_stream);
     cudaFreeHost(md->rep_host);
     delete md;
     return CHX_OK;
@@ -1058,22 +1167,54 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     const dim3 gb(chx_div_up(g.np, 256), R);
     const int CH = 32;
 
-    auto launch_steps = [&](int s0, int s1) -> int {
+    auto launch_steps = [&](int s0, int s1, const int* base) -> int {
         for (int s = s0; s < s1; ++s) {
-            k_md_baoab<<<gb, 256, 0, st>>>(md->xs, md->vs, md->fs, md->refi, md->refu, g, h, a, bcoef,
-                                           hs_user, hs_int2, s, md->rep);
+            k_md_baoab<<<gb, 256, 0, ctx->stream>>>(md->xs, md->vs, md->fs, md->refi, md->refu, g, h, a,
+                                                    bcoef, hs_user, hs_int2, s, base, md->rep);
             CHX_LAUNCHED(ctx);
             const bool en = report && (s % report_interval == 0);
-            int rc2 = md_force(md, FMODE_STEP, s, en, rint, energies_dev);
+            int rc2 = md_force(md, FMODE_STEP, s, en, rint, energies_dev, base);
             if (rc2 != CHX_OK) return rc2;
         }
+        return CHX_OK;
+    };
+    // full chunks without energy reports replay one CUDA graph of CH x (BAOAB, force): the kernels
+    // read the chunk's first step from device memory, so the same graph serves every chunk
+    const bool use_graph = !report && !md->no_graph;
+    auto launch_chunk_graph = [&](int s0) -> int {
+        if (md->chunk_graph && md->chunk_graph_tcap != md->tcap) {
+            cudaGraphExecDestroy(md->chunk_graph);
+            md->chunk_graph = nullptr;
+        }
+        if (!md->chunk_graph) {
+            cudaGraph_t graph = nullptr;
+            const long long l0 = ctx->launches;
+            // captured on a private stream (the caller's may be the legacy default stream, which
+            // cannot be captured); the graph itself is launched on the caller's stream
+            if (!md->cap_stream) CHX_CUDA(cudaStreamCreateWithFlags(&md->cap_stream, cudaStreamNonBlocking));
+            CHX_CUDA(cudaStreamBeginCapture(md->cap_stream, cudaStreamCaptureModeRelaxed));
+            ctx->stream = md->cap_stream;
+            int rc2 = launch_steps(0, CH, md->step_base);
+            ctx->stream = st;
+            cudaError_t ce = cudaStreamEndCapture(md->cap_stream, &graph);
+            ctx->launches = l0;
+            if (rc2 != CHX_OK) { if (graph) cudaGraphDestroy(graph); return rc2; }
+            CHX_CUDA(ce);
+            CHX_CUDA(cudaGraphInstantiate(&md->chunk_graph, graph, 0));
+            CHX_CUDA(cudaGraphDestroy(graph));
+            md->chunk_graph_tcap = md->tcap;
+        }
+        k_md_setbase<<<1, 1, 0, st>>>(md->step_base, s0);
+        CHX_LAUNCHED(ctx);
+        CHX_CUDA(cudaGraphLaunch(md->chunk_graph, st));
+        ctx->launches += 2 * CH;
         return CHX_OK;
     };
 
     int t = 0;
     while (t < nsteps) {
         const int te = nsteps - t < CH ? nsteps : t + CH;
-        rc = launch_steps(t, te);
+        rc = (use_graph && te - t == CH) ? launch_chunk_graph(t) : launch_steps(t, te, nullptr);
         if (rc != CHX_OK) return rc;
         rc = md_download_rep(md);
         if (rc != CHX_OK) return rc;
@@ -1097,7 +1238,7 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
             if (rc != CHX_OK) return rc;
             rc = md_force(md, FMODE_REDO, -2, report, rint, energies_dev);
             if (rc != CHX_OK) return rc;
-            rc = launch_steps(first + 1, te);
+            rc = launch_steps(first + 1, te, nullptr);
             if (rc != CHX_OK) return rc;
             rc = md_download_rep(md);
             if (rc != CHX_OK) return rc;
@@ -1159,18 +1300,34 @@ int chx_ljmd_stats(chx_ljmd* md, long long* stats_host) {
 // ---------------------------------------------------------------------------------------------
 // measurement hooks
 // ---------------------------------------------------------------------------------------------
+template <bool PACKED>
 __global__ void __launch_bounds__(256) k_fma_peak(int iters, float* __restrict__ sink) {
-    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
-    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
     const float b = 0.999f, c = 1e-3f;
-    for (int i = 0; i < iters; ++i) {
+    float s;
+    if (PACKED) {   // FFMA2: two fp32 FMAs per lane per instruction
+        float2 a0 = make_float2(threadIdx.x * 1e-3f, 0.5f), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
+        a1.x += 1.f; a2.x += 2.f; a3.x += 3.f; a4.x += 4.f; a5.x += 5.f; a6.x += 6.f; a7.x += 7.f;
+        const float2 b2 = make_float2(b, b), c2 = make_float2(c, c);
+        for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
-            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+            for (int u = 0; u < 4; ++u) {
+                a0 = __ffma2_rn(a0, b2, c2); a1 = __ffma2_rn(a1, b2, c2); a2 = __ffma2_rn(a2, b2, c2); a3 = __ffma2_rn(a3, b2, c2);
+                a4 = __ffma2_rn(a4, b2, c2); a5 = __ffma2_rn(a5, b2, c2); a6 = __ffma2_rn(a6, b2, c2); a7 = __ffma2_rn(a7, b2, c2);
+            }
         }
+        s = a0.x + a1.x + a2.x + a3.x + a4.x + a5.x + a6.x + a7.x + a0.y + a1.y + a2.y + a3.y + a4.y + a5.y + a6.y + a7.y;
+    } else {
+        float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+        float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+                a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+            }
+        }
+        s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     }
-    const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 12345.678f) sink[0] = s;
 }
 
@@ -1186,13 +1343,14 @@ int chx_ljmd_force_only(chx_ljmd* md, int repeats) {
 }
 
 int chx_fma_peak(chx_ctx* ctx, int iters, double* flops_host) {
-    CHX_REQUIRE(ctx && iters > 0, "bad argument");
+    CHX_REQUIRE(ctx && iters != 0, "bad argument");
     float* sink = (float*)chx_scratch(ctx, 256);
     if (!sink) return CHX_CUDA_ERROR;
     const int blocks = ctx->sm_count * 8;
-    k_fma_peak<<<blocks, 256, 0, ctx->stream>>>(iters, sink);
+    if (iters < 0) k_fma_peak<true><<<blocks, 256, 0, ctx->stream>>>(-iters, sink);
+    else k_fma_peak<false><<<blocks, 256, 0, ctx->stream>>>(iters, sink);
     CHX_LAUNCHED(ctx);
-    if (flops_host) *flops_host = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+    if (flops_host) *flops_host = 2.0 * 64.0 * fabs((double)iters) * 256.0 * (double)blocks;
     return CHX_OK;
 }
 

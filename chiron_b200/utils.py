@@ -39,9 +39,28 @@ def get_list_of_mass(topology: Topology):
     return mass * unit.amu
 
 
+_MASS_CACHE = {}
+
+
 def mass_tensor(topology, device=None) -> torch.Tensor:
+    """Masses (amu) as a float32 CUDA tensor.  The reference walks the topology atom by atom on
+    every `run` (`chiron/utils.py:106-113`); here the result is cached per topology object and
+    atom count, so repeated calls cost nothing."""
+    dev = torch.device(device) if device is not None else _lib.default_device()
+    key = (id(topology), topology.getNumAtoms(), str(dev))
+    hit = _MASS_CACHE.get(key)
+    if hit is not None and hit[0]() is topology:
+        return hit[1]
     m = get_list_of_mass(topology).value_in_unit_system(unit.md_unit_system)
-    return _lib.as_device_f32(np.asarray(m, dtype=np.float32), device)
+    t = _lib.as_device_f32(np.asarray(m, dtype=np.float32), dev)
+    try:
+        import weakref
+        if len(_MASS_CACHE) > 64:
+            _MASS_CACHE.clear()
+        _MASS_CACHE[key] = (weakref.ref(topology), t)
+    except TypeError:
+        pass
+    return t
 
 
 def kT_md(temperature) -> float:

@@ -194,7 +194,8 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
 int chx_ljmd_energy(chx_ljmd* md, double* energy_dev);
 /* Measurement hooks (bench.py roofline): launch the force kernel `repeats` times on the current
  * positions (asynchronous); run an FFMA-chain microbenchmark and return the fp32 FLOP count it
- * executed in *flops_host (asynchronous, time it with events on the context's stream). */
+ * executed in *flops_host (asynchronous, time it with events on the context's stream); a negative
+ * `iters` runs |iters| iterations of the packed FFMA2 variant. */
 int chx_ljmd_force_only(chx_ljmd* md, int repeats);
 int chx_fma_peak(chx_ctx* ctx, int iters, double* flops_host);
 /* Host statistics (8 values): [0]=table rebuilds, [1]=candidate pairs i<j (d<cutoff+internal skin)
