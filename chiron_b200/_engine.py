@@ -22,7 +22,10 @@ _SIGS = {
     "chx_ljmd_get_state": [_P, _P, _P, _P, _P],
     "chx_ljmd_run": [_P, _I, C.POINTER(C.c_uint32), _I, _P, _I],
     "chx_ljmd_energy": [_P, _P],
+    "chx_ljmd_set_kT": [_P, C.POINTER(C.c_float)],
+    "chx_ljmd_scale_velocities": [_P, C.POINTER(C.c_float)],
     "chx_ljmd_stats": [_P, C.POINTER(C.c_longlong)],
+    "chx_ljmd_table_stats": [_P, C.POINTER(C.c_longlong)],
     "chx_ljmd_force_only": [_P, _I],
     "chx_fma_peak": [_P, _I, C.POINTER(C.c_double)],
 }
@@ -107,6 +110,12 @@ class LJLangevinEngine:
         self._call("chx_ljmd_energy", _lib.ptr(e))
         return e
 
+    def set_kT(self, kT_per_replica):
+        self._call("chx_ljmd_set_kT", (C.c_float * self.R)(*[float(t) for t in kT_per_replica]))
+
+    def scale_velocities(self, scale_per_replica):
+        self._call("chx_ljmd_scale_velocities", (C.c_float * self.R)(*[float(t) for t in scale_per_replica]))
+
     def force_only(self, repeats=1):
         self._call("chx_ljmd_force_only", int(repeats))
 
@@ -115,7 +124,12 @@ class LJLangevinEngine:
         self._call("chx_ljmd_stats", s)
         keys = ("table_rebuilds", "candidate_pairs", "interacting_pairs", "steps", "launches",
                 "reference_rebuilds", "tile_capacity", "blocks")
-        return dict(zip(keys, [int(v) for v in s]))
+        out = dict(zip(keys, [int(v) for v in s]))
+        t = (C.c_longlong * 4)()
+        self._call("chx_ljmd_table_stats", t)
+        out.update(trip_slots=int(t[0]), list_words=int(t[1]), tile_bytes=int(t[2]), candidate_capacity=int(t[3]))
+        out["lane_utilisation"] = (2.0 * out["candidate_pairs"] / out["trip_slots"]) if out["trip_slots"] else 0.0
+        return out
 
 
 def run_fused_langevin(integrator, x, v, mass, potential, nbr_list, sampler_state, kT, dt, gamma, key,

@@ -1,0 +1,569 @@
+"""MultiStateSampler with chiron's interface (`chiron/multistate.py`), replica-sharded.
+
+What the reference does per iteration (`multistate.py:563-599`): mix replicas (a no-op stub,
+`:447-495`), propagate every replica serially through its MCMCSampler (`:497-510`), evaluate the
+R x K matrix of reduced potentials with R*K full energy calls (`:512-531`), report, run MBAR.
+
+Here the same methods exist with the same names and return values, and two things are new
+(SURVEY.md section 8e):
+
+* **replica sharding** -- with `torch.distributed` initialised, rank g owns a contiguous block of
+  replicas; it propagates only those and contributes their rows of the energy matrix, one
+  `all_gather` per sweep (NCCL on GPUs, gloo in CPU tests) gives every rank the full matrix;
+* **batched propagation** -- when every replica is LJPotential + NeighborListNsqrd +
+  LangevinDynamicsMove on the same system, the rank's replicas advance in ONE fused-engine launch
+  per step (replica = blockIdx.y, per-replica key and temperature) and the energy matrix of a
+  temperature ladder comes from one batched energy kernel (u_kl = beta_l U_k + beta_l p_l V_k).
+
+Replica exchange proper (`exchange="neighbors"`) is new design (the reference has none): even/odd
+neighbour swaps decided identically on every rank from a shared counter-based key, only state
+indices move, velocities are rescaled by sqrt(T_new / T_old).  `exchange=None` (default)
+reproduces the reference: `_mix_replicas` changes nothing.
+"""
+import copy
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import random, unit
+from .mcmc import LangevinDynamicsMove, MCMCSampler
+from .neighbors import PairsBase
+from .reporters import MultistateReporter
+from .states import SamplerState, ThermodynamicState, calculate_reduced_potential_at_states
+
+
+# ---------------------------------------------------------------------------------------------------
+# host logic shared by every rank (pure NumPy: covered by the gloo world_size-2 CPU tests)
+# ---------------------------------------------------------------------------------------------------
+def shard_bounds(n_replicas: int, world_size: int, rank: int):
+    """Contiguous block of replicas owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n_replicas, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_rows(local_rows: np.ndarray, n_replicas: int, group=None) -> np.ndarray:
+    """All-gather the (n_local, K) float64 rows of every rank into the (R, K) matrix.
+    Single process: returns the input.  Uses the backend of the default process group: NCCL moves
+    the rows through device memory over NVLink, gloo through host memory."""
+    import torch.distributed as dist
+    local_rows = np.ascontiguousarray(local_rows, dtype=np.float64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_rows
+    world = dist.get_world_size(group)
+    K = local_rows.shape[1]
+    n_max = max(shard_bounds(n_replicas, world, r)[1] - shard_bounds(n_replicas, world, r)[0] for r in range(world))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    send = torch.zeros((n_max, K), dtype=torch.float64, device=dev)
+    send[:local_rows.shape[0]] = torch.from_numpy(local_rows).to(dev)
+    recv = torch.empty((world * n_max, K), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.cpu().numpy().reshape(world, n_max, K)
+    out = np.empty((n_replicas, K), dtype=np.float64)
+    for r in range(world):
+        lo, hi = shard_bounds(n_replicas, world, r)
+        out[lo:hi] = recv[r, :hi - lo]
+    return out
+
+
+def neighbor_swaps(u_rk: np.ndarray, replica_states: np.ndarray, iteration: int, seed: int,
+                   n_accepted: Optional[np.ndarray] = None, n_proposed: Optional[np.ndarray] = None) -> np.ndarray:
+    """One round of neighbour replica exchange.  State pairs (s, s+1) with s = iteration mod 2, +2, ...;
+    the replicas i, j sitting in them swap with probability min(1, exp(-(u[i,s+1] + u[j,s]) + u[i,s] + u[j,s+1])).
+    The uniforms come from `jax.random.uniform(fold(seed, iteration), (n_pairs,))` (legacy threefry),
+    so every rank reaches the same decisions without communication.  Returns the new state of
+    every replica."""
+    states = np.array(replica_states, dtype=int)
+    K = u_rk.shape[1]
+    replica_at = np.empty(K, dtype=int)
+    replica_at[states] = np.arange(states.size)
+    pairs = list(range(int(iteration) % 2, K - 1, 2))
+    if not pairs:
+        return states
+    key = random.PRNGKey((int(seed) << 32) ^ int(iteration))
+    u01 = random.uniform_host(key, len(pairs))
+    for p, s in enumerate(pairs):
+        i, j = replica_at[s], replica_at[s + 1]
+        log_p = -(u_rk[i, s + 1] + u_rk[j, s]) + u_rk[i, s] + u_rk[j, s + 1]
+        accept = bool(log_p >= 0.0 or u01[p] < np.exp(log_p))
+        if n_proposed is not None:
+            n_proposed[s, s + 1] += 1
+            n_proposed[s + 1, s] += 1
+        if accept:
+            states[i], states[j] = s + 1, s
+            if n_accepted is not None:
+                n_accepted[s, s + 1] += 1
+                n_accepted[s + 1, s] += 1
+    return states
+
+
+# ---------------------------------------------------------------------------------------------------
+class MultiStateSampler:
+    def __init__(self, mcmc_sampler: MCMCSampler, reporter: MultistateReporter, exchange: Optional[str] = None,
+                 exchange_seed: int = 0, mcmc_iterations_per_sweep: Optional[int] = None):
+        from .analysis import MBAREstimator
+        self._thermodynamic_states = None
+        self._unsampled_states = None
+        self._sampler_states = None
+        self._replica_thermodynamic_states = None
+        self._iteration = None
+        self._energy_thermodynamic_states = None
+        self._neighborhoods = None
+        self._n_accepted_matrix = None
+        self._n_proposed_matrix = None
+        self._nbr_lists = None
+        self._reporter = reporter
+        self._metadata = None
+        self._mcmc_sampler = copy.deepcopy(mcmc_sampler)
+        self._online_estimator = None
+        self._offline_estimator = MBAREstimator()
+        if exchange not in (None, "neighbors"):
+            raise ValueError("exchange must be None (reference behaviour) or 'neighbors'")
+        self.exchange = exchange
+        self.exchange_seed = int(exchange_seed)
+        # the reference hands the multistate n_iterations to every MCMCSampler.run as ITS n_iterations
+        # (`multistate.py:441-443`); None replicates that, an int overrides it
+        self.mcmc_iterations_per_sweep = mcmc_iterations_per_sweep
+        self.use_batched_engine = True
+        self._batched = None
+        self._rank, self._world = 0, 1
+
+    # ---- properties (`multistate.py:86-176`) ----------------------------------------------------------
+    @property
+    def number_of_thermodynamic_states(self) -> int:
+        return 0 if self._thermodynamic_states is None else len(self._thermodynamic_states)
+
+    @property
+    def number_of_replicas(self) -> int:
+        return 0 if self._sampler_states is None else len(self._sampler_states)
+
+    @property
+    def iteration(self):
+        return self._iteration
+
+    @property
+    def mcmc_sampler(self):
+        return copy.deepcopy(self._mcmc_sampler)
+
+    @property
+    def sampler_states(self) -> Optional[List[SamplerState]]:
+        if self._sampler_states is None:
+            return None
+        self._sync_from_engine()
+        return copy.deepcopy(self._sampler_states)
+
+    @property
+    def is_periodic(self):
+        if self._sampler_states is None:
+            return None
+        self._is_periodic = self._sampler_states[0].box_vectors is not None
+        return self._is_periodic
+
+    @property
+    def is_completed(self):
+        return self._is_completed()
+
+    @property
+    def local_replica_range(self):
+        return shard_bounds(self.number_of_replicas, self._world, self._rank)
+
+    # ---- creation (`multistate.py:203-309`) ------------------------------------------------------------
+    def create(self, thermodynamic_states: List[ThermodynamicState], sampler_states: List[SamplerState],
+               nbr_lists: List[PairsBase]):
+        self._online_estimator = None
+        if len(thermodynamic_states) != len(sampler_states):
+            raise RuntimeError("Number of thermodynamic states and sampler states must be equal.")
+        self._allocate_variables(thermodynamic_states, sampler_states, nbr_lists)
+        self._reporter = MultistateReporter()      # the reference overwrites the user's reporter (App. B #10)
+
+    def _allocate_variables(self, thermodynamic_states, sampler_states, nbr_lists) -> None:
+        import torch.distributed as dist
+        self._thermodynamic_states = copy.deepcopy(thermodynamic_states)
+        self._sampler_states = copy.deepcopy(sampler_states)
+        self._nbr_lists = copy.deepcopy(nbr_lists)
+        assert len(self._thermodynamic_states) == len(self._sampler_states)
+        assert len(self._thermodynamic_states) == len(self._nbr_lists)
+        if dist.is_available() and dist.is_initialized():
+            self._rank, self._world = dist.get_rank(), dist.get_world_size()
+        lo, hi = self.local_replica_range
+        for r in range(lo, hi):       # initial build of the lists of the replicas this rank owns
+            self._nbr_lists[r].build(self._sampler_states[r].positions, self._sampler_states[r].box_vectors)
+        K = len(thermodynamic_states)
+        self._replica_thermodynamic_states = np.arange(K, dtype=int)
+        self._n_accepted_matrix = np.zeros([K, K], np.int64)
+        self._n_proposed_matrix = np.zeros([K, K], np.int64)
+        self._energy_thermodynamic_states = np.zeros([self.number_of_replicas, K], np.float64)
+        self._traj = [[] for _ in range(self.number_of_replicas)]
+        if isinstance(self._mcmc_sampler, MCMCSampler):
+            self._mcmc_sampler = [copy.deepcopy(self._mcmc_sampler) for _ in range(K)]
+        elif len(self._mcmc_sampler) != K:
+            raise RuntimeError(f"The number of MCMCMoves ({len(self._mcmc_sampler)}) and ThermodynamicStates "
+                               f"({K}) must be the same.")
+        self._iteration = 0
+        self._batched = None
+
+    # ---- minimisation (`multistate.py:311-412`; jaxopt replaced by steepest descent on the force kernel) -----
+    def _minimize_replica(self, replica_id: int, tolerance=1.0 * unit.kilojoules_per_mole / unit.nanometers,
+                          max_iterations: int = 1_000) -> None:
+        from loguru import logger as log
+        state_id = self._replica_thermodynamic_states[replica_id]
+        potential = self._thermodynamic_states[state_id].potential
+        sampler_state = self._sampler_states[replica_id]
+        nbr_list = self._nbr_lists[replica_id]
+        tol = float(tolerance.value_in_unit_system(unit.md_unit_system)) if isinstance(tolerance, unit.Quantity) else float(tolerance)
+        x = sampler_state.positions.clone()
+        has_ef = hasattr(potential, "compute_energy_and_force")
+
+        def energy_force(xx):
+            if has_ef:
+                try:
+                    e, f = potential.compute_energy_and_force(xx, nbr_list)
+                except TypeError:
+                    e, f = potential.compute_energy_and_force(xx)
+            else:
+                e, f = potential.compute_energy(xx, nbr_list), potential.compute_force(xx, nbr_list)
+            f = f if isinstance(f, torch.Tensor) else torch.zeros_like(xx)
+            return float(e), f
+
+        e, f = energy_force(x)
+        log.debug(f"Replica {replica_id + 1}/{self.number_of_replicas}: initial energy {e:8.3f} kJ/mol")
+        step = 1e-4
+        for _ in range(int(max_iterations)):
+            fmax = float(f.abs().max())
+            if fmax < tol:
+                break
+            x_try = x + step * f
+            e_try, f_try = energy_force(x_try)
+            if e_try <= e:
+                x, e, f = x_try, e_try, f_try
+                step *= 1.5
+            else:
+                step *= 0.25
+                if step < 1e-12:
+                    break
+        self._sampler_states[replica_id].positions = unit.Quantity(x, unit.nanometer)
+        if nbr_list is not None and nbr_list.check(self._sampler_states[replica_id].positions):
+            nbr_list.build(self._sampler_states[replica_id].positions, self._sampler_states[replica_id].box_vectors)
+        log.debug(f"Replica {replica_id + 1}/{self.number_of_replicas}: final energy {e:8.3f} kJ/mol")
+
+    def minimize(self, tolerance=1.0 * unit.kilojoules_per_mole / unit.nanometers, max_iterations: int = 1_000) -> None:
+        if self.number_of_replicas == 0:
+            raise RuntimeError("Cannot minimize replicas. The simulation must be created first.")
+        lo, hi = self.local_replica_range
+        for replica_id in range(lo, hi):
+            self._minimize_replica(replica_id, tolerance, max_iterations)
+        self._batched = None
+
+    # ---- propagation (`multistate.py:414-445, 497-510`) ---------------------------------------------------
+    def _mcmc_iterations(self):
+        return self.number_of_iterations if self.mcmc_iterations_per_sweep is None else self.mcmc_iterations_per_sweep
+
+    def _propagate_replica(self, replica_id: int):
+        state_id = self._replica_thermodynamic_states[replica_id]
+        (self._sampler_states[replica_id], self._thermodynamic_states[state_id],
+         self._nbr_lists[replica_id]) = self._mcmc_sampler[state_id].run(
+            self._sampler_states[replica_id], self._thermodynamic_states[state_id], self._mcmc_iterations(),
+            self._nbr_lists[replica_id])
+        self._traj[replica_id].append(self._sampler_states[replica_id].positions)
+
+    def _propagate_replicas(self) -> None:
+        from loguru import logger as log
+        log.debug("Propagating all replicas...")
+        lo, hi = self.local_replica_range
+        batched = self._batched_engine()
+        if batched is not None:
+            batched.propagate(self._mcmc_iterations())
+            return
+        for replica_id in range(lo, hi):
+            self._propagate_replica(replica_id)
+
+    # ---- energies (`multistate.py:178-201, 512-531`) -----------------------------------------------------
+    def _compute_replica_reduced_potential(self, replica_id: int) -> np.ndarray:
+        # the reference passes the SamplerState as nbr_list here (App. B #8); fixed
+        return calculate_reduced_potential_at_states(self._sampler_states[replica_id], self._thermodynamic_states,
+                                                     self._nbr_lists[replica_id])
+
+    def _compute_energies(self) -> None:
+        from loguru import logger as log
+        log.debug("Computing energy matrix for all replicas...")
+        lo, hi = self.local_replica_range
+        K = self.number_of_thermodynamic_states
+        batched = self._batched_engine()
+        if batched is not None:
+            rows = batched.reduced_potentials()
+        else:
+            rows = np.zeros((hi - lo, K))
+            for replica_id in range(lo, hi):
+                rows[replica_id - lo, :] = self._compute_replica_reduced_potential(replica_id)
+        self._energy_thermodynamic_states = gather_rows(rows, self.number_of_replicas)
+
+    # ---- mixing (`multistate.py:447-495`) ------------------------------------------------------------------
+    def _perform_swap_proposals(self):
+        if self.exchange is None:
+            return self._replica_thermodynamic_states        # reference: placeholder, nothing moves
+        old = self._replica_thermodynamic_states
+        new = neighbor_swaps(self._energy_thermodynamic_states, old, self._iteration, self.exchange_seed,
+                             self._n_accepted_matrix, self._n_proposed_matrix)
+        self._apply_state_change(old, new)
+        return new
+
+    def _apply_state_change(self, old, new):
+        """Replicas keep their coordinates; a replica that moved to another temperature gets its
+        velocities rescaled by sqrt(T_new / T_old)."""
+        lo, hi = self.local_replica_range
+        batched = self._batched_engine()
+        scales = {}
+        for r in range(lo, hi):
+            if old[r] != new[r]:
+                t_old = self._thermodynamic_states[old[r]].temperature
+                t_new = self._thermodynamic_states[new[r]].temperature
+                scales[r] = float(np.sqrt(float(t_new / t_old)))
+        if batched is not None:
+            batched.set_states(new, scales)
+        else:
+            for r, s in scales.items():
+                st = self._sampler_states[r]
+                if st._velocities is not None:
+                    st.velocities = unit.Quantity(st.velocities * s, unit.nanometer / unit.picosecond)
+
+    def _mix_replicas(self) -> np.ndarray:
+        from loguru import logger as log
+        log.debug("Mixing replicas...")
+        self._n_accepted_matrix[:, :] = 0
+        self._n_proposed_matrix[:, :] = 0
+        new_replica_states = self._perform_swap_proposals()
+        self._replica_thermodynamic_states = np.asarray(new_replica_states, dtype=int)
+        n_swaps_proposed = self._n_proposed_matrix.sum()
+        n_swaps_accepted = self._n_accepted_matrix.sum()
+        frac = n_swaps_accepted / n_swaps_proposed if n_swaps_proposed > 0 else 0.0
+        log.debug(f"Accepted {n_swaps_accepted}/{n_swaps_proposed} attempted swaps ({frac * 100.0:.1f}%)")
+        return new_replica_states
+
+    # ---- main loop (`multistate.py:533-599`) -----------------------------------------------------------------
+    def _is_completed(self, iteration_limit: Optional[int] = None) -> bool:
+        from loguru import logger as log
+        if iteration_limit is not None and self._iteration >= iteration_limit:
+            log.info(f"Reached iteration limit {iteration_limit} (current iteration {self._iteration})")
+            return True
+        return False
+
+    def run(self, n_iterations: int = 10) -> None:
+        from loguru import logger as log
+        log.info("Running simulation...")
+        self.number_of_iterations = n_iterations
+        if self._iteration == 0:
+            self._compute_energies()
+            self._report_iteration()
+        while not self._is_completed(n_iterations):
+            self._iteration += 1
+            log.info(f"Iteration {self._iteration}/{n_iterations}")
+            self._mix_replicas()
+            self._propagate_replicas()
+            self._compute_energies()
+            self._report_iteration()
+            self._update_analysis()
+        self._reporter.flush_buffer()
+
+    # ---- reporting / analysis (`multistate.py:601-742`) ------------------------------------------------------
+    def _report_energy_matrix(self):
+        return {"u_kn": self._energy_thermodynamic_states.T}
+
+    def _report_positions(self):
+        self._sync_from_engine()
+        lo, hi = self.local_replica_range
+        n_atoms = self._sampler_states[lo].positions.shape[0]
+        xyz = np.zeros((self.number_of_replicas, n_atoms, 3))
+        for replica_id in range(lo, hi):
+            xyz[replica_id] = self._sampler_states[replica_id].positions.detach().cpu().numpy()
+        return {"positions": xyz}
+
+    def _report(self, property: str):
+        if property == "positions":
+            return self._report_positions()
+        elif property == "u_kn":
+            return self._report_energy_matrix()
+        elif property == "state_index":
+            return {"state_index": np.array(self._replica_thermodynamic_states)}
+        return None
+
+    def _report_iteration(self):
+        prop = {}
+        for property in self._reporter.properties_to_report:
+            p = self._report(property)
+            if p:
+                prop.update(p)
+        self._reporter.report(prop)
+
+    def _update_analysis(self):
+        if self._offline_estimator:
+            N_k = [self._iteration] * self.number_of_thermodynamic_states
+            u_kn = self._reporter.get_property("u_kn")
+            self._offline_estimator.initialize(u_kn=u_kn, N_k=N_k)
+        elif self._online_estimator:
+            self._online_estimator.update()
+        else:
+            raise RuntimeError("No free energy estimator provided.")
+
+    @property
+    def f_k(self) -> np.ndarray:
+        if self._offline_estimator:
+            return self._offline_estimator.f_k
+        elif self._online_estimator:
+            return self._online_estimator.f_k
+        raise RuntimeError("No free energy estimator found.")
+
+    # ---- batched engine -----------------------------------------------------------------------------------------
+    def _batched_engine(self):
+        if self._batched is False:
+            return None
+        if self._batched is None:
+            self._batched = _BatchedLJReplicas.try_create(self) if self.use_batched_engine else False
+            if self._batched is None:
+                self._batched = False
+        return self._batched or None
+
+    def _sync_from_engine(self):
+        if self._batched:
+            self._batched.sync_states()
+
+
+class _BatchedLJReplicas:
+    """The rank's replicas in one `chx_ljmd` engine (replica = blockIdx.y)."""
+
+    @classmethod
+    def try_create(cls, ms: "MultiStateSampler"):
+        from . import _engine
+        from .neighbors import NeighborListNsqrd
+        from .potential import LJPotential
+        if not _engine.available():
+            return None
+        lo, hi = ms.local_replica_range
+        if hi <= lo:
+            return None
+        ts0, nl0, st0 = ms._thermodynamic_states[0], ms._nbr_lists[lo], ms._sampler_states[lo]
+        pot0 = ts0.potential
+        if not isinstance(pot0, LJPotential) or not isinstance(nl0, NeighborListNsqrd) or not nl0.space.periodic:
+            return None
+        if st0.box_vectors is None:
+            return None
+        box0 = st0.box_lengths_host()
+        sig = (pot0.sigma, pot0.epsilon, pot0.cutoff, nl0._skin_md(), st0.positions.shape[0])
+        for ts in ms._thermodynamic_states:
+            p = ts.potential
+            if not isinstance(p, LJPotential) or (p.sigma, p.epsilon, p.cutoff) != sig[:3] or ts.temperature is None:
+                return None
+        move = None
+        for sampler in ms._mcmc_sampler:
+            sched = sampler.move.move_schedule
+            if len(sched) != 1 or not isinstance(sched[0][1], LangevinDynamicsMove):
+                return None
+            m = sched[0][1]
+            if m.reporter is not None or m.save_traj_in_memory:
+                return None
+            par = (float(m.timestep.value_in_unit_system(unit.md_unit_system)),
+                   float(m.collision_rate.value_in_unit_system(unit.md_unit_system)), int(m.number_of_moves),
+                   bool(m.integrator.refresh_velocities))
+            if move is None:
+                move = par
+            elif move != par:
+                return None
+        for r in range(lo, hi):
+            st, nl = ms._sampler_states[r], ms._nbr_lists[r]
+            if (st.box_vectors is None or st.box_lengths_host() != box0 or st.positions.shape[0] != sig[4]
+                    or not isinstance(nl, NeighborListNsqrd) or nl._skin_md() != sig[3] or nl._cutoff_md() != sig[2]):
+                return None
+        return cls(ms, lo, hi, box0, sig, move)
+
+    def __init__(self, ms, lo, hi, box, sig, move):
+        from ._engine import LJLangevinEngine
+        from .utils import initialize_velocities, kT_md, mass_tensor
+        self.ms, self.lo, self.hi = ms, lo, hi
+        self.dt, self.gamma, self.nsteps, self.refresh = move
+        self.n = sig[4]
+        st0 = ms._sampler_states[lo]
+        dev = st0.positions.device
+        self.kT_of_state = [kT_md(ts.temperature) for ts in ms._thermodynamic_states]
+        states = ms._replica_thermodynamic_states
+        kts = [self.kT_of_state[states[r]] for r in range(lo, hi)]
+        self.engine = LJLangevinEngine(self.n, box, sig[0], sig[1], sig[2], sig[3], self.dt, self.gamma, kts[0],
+                                       n_replicas=hi - lo, device=dev)
+        topology = ms._thermodynamic_states[0].potential.topology
+        mass = mass_tensor(topology, dev)
+        xs, vs = [], []
+        self._pending_v_keys = {}
+        for r in range(lo, hi):
+            st = ms._sampler_states[r]
+            xs.append(st.positions)
+            if st._velocities is None or st.velocities.shape[0] != self.n:
+                vs.append(None)
+            else:
+                vs.append(st.velocities)
+        self._missing_v = [v is None for v in vs]
+        vs = [v if v is not None else torch.zeros_like(xs[0]) for v in vs]
+        self.engine.set_state(torch.stack(xs).contiguous(), torch.stack(vs).contiguous(), mass, kts)
+        self.mass = mass
+        self.topology = topology
+        self.box = box
+        self.volume = float(box[0] * box[1] * box[2])
+        self._dirty = False
+
+    def propagate(self, n_mcmc_iterations: int):
+        """`MCMCSampler.run` x n_iterations of the single LangevinDynamicsMove for every local replica:
+        per run the loop key is `sampler_state.new_PRNG_key` (integrators.py:124) and the state key
+        advances by that one split (App. B #6)."""
+        from .utils import initialize_velocities
+        ms = self.ms
+        for _ in range(int(n_mcmc_iterations)):
+            keys = np.zeros((self.hi - self.lo, 2), dtype=np.uint32)
+            for r in range(self.lo, self.hi):
+                keys[r - self.lo] = ms._sampler_states[r].new_PRNG_key
+            if self.refresh or any(self._missing_v):
+                x, v, _, _ = self.engine.get_state()
+                x = x.reshape(self.hi - self.lo, self.n, 3)
+                v = v.reshape(self.hi - self.lo, self.n, 3).clone()
+                states = ms._replica_thermodynamic_states
+                for r in range(self.lo, self.hi):
+                    if self.refresh or self._missing_v[r - self.lo]:
+                        T = ms._thermodynamic_states[states[r]].temperature
+                        v[r - self.lo] = initialize_velocities(T, self.topology, keys[r - self.lo]) \
+                            .value_in_unit_system(unit.md_unit_system)
+                kts = [self.kT_of_state[states[r]] for r in range(self.lo, self.hi)]
+                self.engine.set_state(x.contiguous(), v.contiguous(), self.mass, kts)
+                self._missing_v = [False] * (self.hi - self.lo)
+            self.engine.run(self.nsteps, keys)
+            self._dirty = True
+
+    def reduced_potentials(self) -> np.ndarray:
+        """(n_local, K): u_kl = beta_l (U_k + p_l V) from one batched energy kernel."""
+        ms = self.ms
+        U = self.engine.energy().cpu().numpy()               # kJ/mol per local replica
+        K = ms.number_of_thermodynamic_states
+        rows = np.zeros((self.hi - self.lo, K))
+        for l, ts in enumerate(ms._thermodynamic_states):
+            red = unit.Quantity(U, unit.kilojoule_per_mole) / unit.AVOGADRO_CONSTANT_NA
+            if ts.pressure is not None:
+                red = red + ts.pressure * (self.volume * unit.nanometer ** 3)
+            rows[:, l] = np.asarray(ts.beta * red, dtype=np.float64)
+        return rows
+
+    def set_states(self, new_states, velocity_scales: dict):
+        kts = [self.kT_of_state[new_states[r]] for r in range(self.lo, self.hi)]
+        self.engine.set_kT(kts)
+        if velocity_scales:
+            s = [velocity_scales.get(r, 1.0) for r in range(self.lo, self.hi)]
+            self.engine.scale_velocities(s)
+            self._dirty = True
+
+    def sync_states(self):
+        """Copy positions / velocities of the engine back into the SamplerState objects."""
+        if not self._dirty:
+            return
+        x, v, _, _ = self.engine.get_state()
+        x = x.reshape(self.hi - self.lo, self.n, 3)
+        v = v.reshape(self.hi - self.lo, self.n, 3)
+        for r in range(self.lo, self.hi):
+            st = self.ms._sampler_states[r]
+            st.positions = unit.Quantity(x[r - self.lo].clone(), unit.nanometer)
+            st.velocities = unit.Quantity(v[r - self.lo].clone(), unit.nanometer / unit.picosecond)
+        self._dirty = False

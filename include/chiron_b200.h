@@ -190,6 +190,11 @@ int chx_ljmd_get_state(chx_ljmd* md, float* x, float* v, float* force, float* re
  * Synchronises at the end. */
 int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_interval,
                  double* energies_dev, int n_reports_capacity);
+/* Replica exchange support (new; the reference's _perform_swap_proposals is a stub, multistate.py:447-460):
+ * change the temperature each replica is thermostatted at (kT, kJ/mol, (R) host floats) and rescale
+ * its velocities (v *= scale[r], e.g. sqrt(T_new / T_old)).  Coordinates never move between replicas. */
+int chx_ljmd_set_kT(chx_ljmd* md, const float* kT_per_replica_host);
+int chx_ljmd_scale_velocities(chx_ljmd* md, const float* scale_per_replica_host);
 /* Potential energy of the current positions per replica (double, device, (R)). Asynchronous. */
 int chx_ljmd_energy(chx_ljmd* md, double* energy_dev);
 /* Measurement hooks (bench.py roofline): launch the force kernel `repeats` times on the current
@@ -203,6 +208,11 @@ int chx_fma_peak(chx_ctx* ctx, int iters, double* flops_host);
  * [3]=steps run, [4]=kernel launches, [5]=reference rebuild events (neighbors.py:903-905) summed
  * over replicas, [6]=table capacity (tiles per block), [7]=blocks per replica.  Synchronises. */
 int chx_ljmd_stats(chx_ljmd* md, long long* stats_host8);
+/* Shape of the engine's neighbour tables (4 values): [0]=lane slots the force kernel spends on the
+ * tiles of the last build (32 lanes x 2 partners x packed trips; [1] of chx_ljmd_stats x 2 / this =
+ * lane utilisation), [1]=list words per tile, [2]=bytes per tile, [3]=candidate capacity per block.
+ * Synchronises. */
+int chx_ljmd_table_stats(chx_ljmd* md, long long* out4);
 
 #ifdef __cplusplus
 }

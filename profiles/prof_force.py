@@ -33,6 +33,16 @@ def main(n_side=64, steps=0, repeats=6):
         keys, _ = eng.run(steps, keys)
     eng.force_only(repeats)
     torch.cuda.synchronize()
+    if os.environ.get("TIME", "0") == "1":
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); eng.force_only(50); e1.record(); torch.cuda.synchronize()
+        t_force = e0.elapsed_time(e1) / 50 * 1e3
+        keys, _ = eng.run(200, keys)
+        torch.cuda.synchronize()
+        e0.record(); keys, _ = eng.run(1000, keys); e1.record(); torch.cuda.synchronize()
+        t_step = e0.elapsed_time(e1)
+        print("TIMING tag=%s force_us=%.2f step_us=%.2f steps_per_s=%.0f" % (
+            os.environ.get("TAG", ""), t_force, t_step, 1e6 / t_step))
     print(eng.stats())
 
 
