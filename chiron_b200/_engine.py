@@ -22,7 +22,7 @@ _SIGS = {
     "chx_ljmd_get_state": [_P, _P, _P, _P, _P],
     "chx_ljmd_run": [_P, _I, C.POINTER(C.c_uint32), _I, _P, _I],
     "chx_ljmd_energy": [_P, _P],
-    "chx_ljmd_set_kT": [_P, C.POINTER(C.c_float)],
+    "chx_ljmd_set_kt": [_P, C.POINTER(C.c_float)],
     "chx_ljmd_scale_velocities": [_P, C.POINTER(C.c_float)],
     "chx_ljmd_stats": [_P, C.POINTER(C.c_longlong)],
     "chx_ljmd_table_stats": [_P, C.POINTER(C.c_longlong)],
@@ -111,7 +111,7 @@ class LJLangevinEngine:
         return e
 
     def set_kT(self, kT_per_replica):
-        self._call("chx_ljmd_set_kT", (C.c_float * self.R)(*[float(t) for t in kT_per_replica]))
+        self._call("chx_ljmd_set_kt", (C.c_float * self.R)(*[float(t) for t in kT_per_replica]))
 
     def scale_velocities(self, scale_per_replica):
         self._call("chx_ljmd_scale_velocities", (C.c_float * self.R)(*[float(t) for t in scale_per_replica]))

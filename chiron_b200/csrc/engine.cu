@@ -1538,7 +1538,7 @@ int chx_ljmd_stats(chx_ljmd* md, long long* stats_host) {
     return CHX_OK;
 }
 
-int chx_ljmd_set_kT(chx_ljmd* md, const float* kT_per_replica_host) {
+int chx_ljmd_set_kt(chx_ljmd* md, const float* kT_per_replica_host) {
     CHX_REQUIRE(md && md->have_state && kT_per_replica_host, "engine has no state or kT is NULL");
     int rc = md_download_rep(md);
     if (rc != CHX_OK) return rc;

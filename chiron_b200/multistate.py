@@ -82,7 +82,7 @@ def neighbor_swaps(u_rk: np.ndarray, replica_states: np.ndarray, iteration: int,
     if not pairs:
         return states
     key = random.PRNGKey((int(seed) << 32) ^ int(iteration))
-    u01 = random.uniform_host(key, len(pairs))
+    u01 = random.uniform_host_n(key, len(pairs))
     for p, s in enumerate(pairs):
         i, j = replica_at[s], replica_at[s + 1]
         log_p = -(u_rk[i, s + 1] + u_rk[j, s]) + u_rk[i, s] + u_rk[j, s + 1]

@@ -50,20 +50,23 @@ def normal(key, shape=(), device=None) -> torch.Tensor:
     return out
 
 
-def uniform_host(key, n=None, minval=0.0, maxval=1.0):
-    """`random.uniform(key, shape, minval, maxval)` evaluated on the host in fp32: a scalar when `n` is
-    None (`shape=()`), else an (n,) float32 array."""
-    bits = _lib.random_bits_host(_as_key(key), 1 if n is None else int(n))
+def uniform_host_n(key, n, minval=0.0, maxval=1.0) -> np.ndarray:
+    """`random.uniform(key, (n,), minval, maxval)` evaluated on the host in fp32."""
+    bits = _lib.random_bits_host(_as_key(key), int(n))
     f = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
     lo, hi = np.float32(minval), np.float32(maxval)
-    out = np.maximum(lo, (f * np.float32(hi - lo)).astype(np.float32) + lo).astype(np.float32)
-    return np.float32(out[0]) if n is None else out
+    return np.maximum(lo, (f * np.float32(hi - lo)).astype(np.float32) + lo).astype(np.float32)
+
+
+def uniform_host(key, minval=0.0, maxval=1.0) -> np.float32:
+    """Scalar `random.uniform(key, minval=, maxval=)` evaluated on the host in fp32."""
+    return np.float32(uniform_host_n(key, 1, minval, maxval)[0])
 
 
 def uniform(key, shape=(), minval=0.0, maxval=1.0, device=None):
     shape = tuple(int(s) for s in (shape if hasattr(shape, "__len__") else (shape,)))
     if shape == ():
-        return uniform_host(key, None, minval, maxval)
+        return uniform_host(key, minval, maxval)
     key = _as_key(key)
     ctx = _lib.get_context(device)
     out = torch.empty(shape, dtype=torch.float32, device=ctx.device)

@@ -193,7 +193,7 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
 /* Replica exchange support (new; the reference's _perform_swap_proposals is a stub, multistate.py:447-460):
  * change the temperature each replica is thermostatted at (kT, kJ/mol, (R) host floats) and rescale
  * its velocities (v *= scale[r], e.g. sqrt(T_new / T_old)).  Coordinates never move between replicas. */
-int chx_ljmd_set_kT(chx_ljmd* md, const float* kT_per_replica_host);
+int chx_ljmd_set_kt(chx_ljmd* md, const float* kT_per_replica_host);
 int chx_ljmd_scale_velocities(chx_ljmd* md, const float* scale_per_replica_host);
 /* Potential energy of the current positions per replica (double, device, (R)). Asynchronous. */
 int chx_ljmd_energy(chx_ljmd* md, double* energy_dev);
