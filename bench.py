@@ -47,6 +47,8 @@ def parse_args():
     p.add_argument("--internal-skin", type=float, default=None)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-remd", action="store_true")
+    p.add_argument("--remd-sweeps", type=int, default=20)
     return p.parse_args()
 
 
@@ -106,78 +108,130 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle on a bounded sample of the same workload
+# CPU baseline: the C/OpenMP restatement of the reference algorithm (oracle/c) on a bounded sample
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_steps_per_s(x, box, rows=1536, repeats=2):
-    """Reference algorithm restated in NumPy (JAX unavailable): per-step cost = NeighborListNsqrd
-    calculate over the padded (N, M) list + masked LJ energy/force + BAOAB update; the O(N^2) build is
-    amortised over the measured rebuild interval.  Timed on `rows` rows of the N=262,144 system and
-    scaled by N/rows (both parts are row-separable)."""
-    import torch
-    from oracle import pairs, potentials as pot, jax_random as jr
+REF_REBUILD_INTERVAL = 150.0   # steps between reference rebuild events (`check()` true) at this state point,
+                               # measured by the engine's exact tracker (bench line: reference_rebuild_interval_steps)
+
+
+def cpu_reference_steps_per_s(x, box, v0, rebuild_interval=REF_REBUILD_INTERVAL, build_stride=24, n_steps=6):
+    """The reference algorithm on the host cores, all threads: per-step cost = `calculate` over the padded
+    (N, M) list + masked LJ energy + the autodiff-equivalent force + BAOAB with in-stream threefry noise +
+    `check` (measured on FULL-size steps as the difference between an (n_steps+2)-step and a 2-step run),
+    plus the O(N^2) build (measured on every `build_stride`-th row of the full system and scaled by the
+    number of pair tests) amortised over the rebuild interval.  The list the timed steps run on is
+    built with the oracle's cell-grid accelerator (not timed: it is not part of the reference)."""
+    from oracle import cport
     n = x.shape[0]
-    torch.set_num_threads(os.cpu_count() or 1)
-    sel = np.arange(rows)
-    t0 = time.perf_counter()
-    nbr_rows = pairs.neighbor_rows(x, box, RC + SKIN, rows=sel, chunk=256)     # O(rows * N) slice of build
-    t_build_rows = time.perf_counter() - t0
-    M = max(r.size for r in nbr_rows) + 10
-    nl = np.zeros((rows, M), dtype=np.int64)
-    mask = np.zeros((rows, M), dtype=np.int32)
-    for i, r in enumerate(nbr_rows):
-        nl[i, :r.size] = r
-        nl[i, r.size:] = r[0] if r.size else 0
-        mask[i, :r.size] = 1
-    best = 1e30
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        r, d = pairs.displacement(x[sel][:, None, :], x[nl], box)
-        m = (d < np.float32(RC)) & (mask != 0)
-        f = np.where(m, pot.lj_pair_force_scalar(d, SIGMA, EPS), 0).astype(np.float32)
-        fv = f[..., None] * r
-        F = np.zeros((n, 3), dtype=np.float32)
-        F[sel] += fv.sum(axis=1)
-        np.subtract.at(F, nl.reshape(-1), fv.reshape(-1, 3))
-        # BAOAB for the same rows (noise on the reference's stream)
-        xi = jr.normal(jr.PRNGKey(1), (rows, 3))
-        v = (0.5 * xi).astype(np.float32)
-        v = v + np.float32(0.0005) * F[sel] / np.float32(MASS)
-        xs = x[sel] + np.float32(0.0005) * v
-        xs = pairs.wrap(xs, box)
-        pairs.displacement(xs, x[sel], box)
-        best = min(best, time.perf_counter() - t0)
-    t_step = best * n / rows
-    t_build = t_build_rows * n / rows
-    rebuild_interval = 150.0            # measured by the GPU run at this state point (skin 0.5 nm)
+    kT = 8.314462618e-3 * TEMP_K
+    mass = np.full(n, MASS, np.float32)
+    key = np.array([0, 1234], np.uint32)
+    cport.set_build_mode(1)
+    try:
+        _, _, _, st_a = cport.langevin_lj(x, v0, mass, box, SIGMA, EPS, RC, SKIN, 400, kT, DT_PS, GAMMA, key, 2)
+        _, _, _, st_b = cport.langevin_lj(x, v0, mass, box, SIGMA, EPS, RC, SKIN, 400, kT, DT_PS, GAMMA, key, 2 + n_steps)
+    finally:
+        cport.set_build_mode(0)
+    t_step = max(1e-9, (st_b["t_steps_s"] - st_a["t_steps_s"]) / n_steps)
+    t_rows, tests = cport.time_reference_build_rows(x, box, np.float32(RC + SKIN), build_stride)
+    t_build = t_rows * (n * (n - 1) / 2.0) / max(1, tests)
     per_step = t_step + t_build / rebuild_interval
-    return 1.0 / per_step, {"t_step_s": t_step, "t_build_s": t_build, "rows": rows,
-                            "rebuild_interval_steps": rebuild_interval}
+    detail = {"t_step_s": t_step, "t_build_s": t_build, "build_rows_timed_s": t_rows, "build_row_stride": build_stride,
+              "full_size_steps_timed": n_steps, "rebuild_interval_steps": rebuild_interval,
+              "n_max_neighbors": int(st_b["M"]), "p_cand": int(st_b["p_cand"]), "threads": cport.num_threads()}
+    return 1.0 / per_step, detail
+
+
+CPU_SAMPLE = ("%d full-size BAOAB steps over the padded (N,M) reference list (calculate + masked LJ energy/force + "
+              "threefry noise + check) + every %d-th row of the O(N^2) build scaled by pair tests and amortised over "
+              "%g steps; C/OpenMP restatement of the reference algorithm (oracle/c), JAX not installable offline")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import __graft_entry__ as ge
+    ge.build_oracle()
+    from oracle import cport, jax_random as jr, dynamics as dyn
     lj, x, box = make_system(args.n_side, seed=4)
-    cores = os.cpu_count() or 1
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        v, detail = cpu_reference_steps_per_s(x, box, rows=1024, repeats=1)
+    v0 = dyn.maxwell_boltzmann(jr.PRNGKey(11), np.full(x.shape[0], MASS), TEMP_K)
+    vals, detail = [], None
+    reps = max(1, min(args.steps, 2))
+    for _ in range(reps):
+        v, detail = cpu_reference_steps_per_s(x, box, v0)
         vals.append(v)
     value = float(np.median(vals))
+    sample = CPU_SAMPLE % (detail["full_size_steps_timed"], detail["build_row_stride"], detail["rebuild_interval_steps"])
     line = {
         "impl": "reference", "metric": "LJ Langevin steps/s at N=262144", "value": value, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.inner / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "baoab_steps_per_bench_step": args.inner,
-                   "note": "reference algorithm restated in NumPy on the host (JAX/OpenMM cannot be installed offline); "
-                           "bounded sample: 1024 of 262144 list rows per step, scaled by N/rows"},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": "1024 rows of the padded (N,M) list per step + amortised O(N^2) build slice", **detail},
+                   "note": "reference ALGORITHM restated in C/OpenMP on the host cores (chiron's JAX code cannot be "
+                           "installed offline: jax, openmm, openmmtools absent); %d repetitions of the bounded sample" % reps},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": detail["threads"], "kind": "port",
+                         "sample": sample, **detail},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# replica exchange: BASELINE.json config 5 (64 temperatures x LJ N=8192), replicas sharded over the ranks
+# ---------------------------------------------------------------------------------------------------
+def bench_remd(dev, rank, world, sweeps=20, warmup=3, n_replicas=64, steps_per_sweep=100):
+    import torch
+    import torch.distributed as dist
+    from chiron_b200 import unit
+    from chiron_b200.mcmc import LangevinDynamicsMove, MCMCSampler, MoveSchedule
+    from chiron_b200.multistate import MultiStateSampler
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.reporters import MultistateReporter
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import LennardJonesFluid
+    from chiron_b200 import random as crandom
+    lj = LennardJonesFluid(cells=(16, 16, 32), reduced_density=RHO_STAR, sigma=SIGMA * unit.nanometer,
+                           epsilon=EPS_KCAL * unit.kilocalories_per_mole, seed=5)
+    potential = LJPotential(lj.topology, lj.sigma, lj.epsilon, RC * unit.nanometer)
+    temps = [TEMP_K * 2.0 ** (k / (n_replicas - 1.0)) for k in range(n_replicas)]
+    thermo = [ThermodynamicState(potential, temperature=t * unit.kelvin) for t in temps]
+    keys = crandom.split(crandom.PRNGKey(99), n_replicas)
+    states = [SamplerState(lj.positions, keys[k], box_vectors=lj.box_vectors) for k in range(n_replicas)]
+    nbrs = [NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=RC * unit.nanometer, skin=SKIN * unit.nanometer,
+                              n_max_neighbors=400, builder="cell") for _ in range(n_replicas)]
+    move = LangevinDynamicsMove(timestep=DT_PS * unit.picosecond, collision_rate=GAMMA / unit.picosecond,
+                                number_of_steps=steps_per_sweep)
+    ms = MultiStateSampler(MCMCSampler(MoveSchedule([("LangevinDynamicsMove", move)])), MultistateReporter(),
+                           exchange="neighbors", exchange_seed=17, mcmc_iterations_per_sweep=1)
+    ms.create(thermo, states, nbrs)
+    ms._offline_estimator = None      # MBAR is post-hoc analysis (pymbar in the reference), not part of a sweep
+    ms._online_estimator = type("NoAnalysis", (), {"update": lambda self: None, "f_k": None})()
+    ms._reporter._default_properties = ["u_kn", "state_index"]
+    ms.run(warmup)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    ms.run(warmup + sweeps)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    acc, prop = int(ms._n_accepted_matrix.sum()), int(ms._n_proposed_matrix.sum())
+    batched = bool(ms._batched)
+    return {"sweeps_per_s": sweeps / dt, "ms_per_sweep": 1e3 * dt / sweeps, "replicas": n_replicas,
+            "particles_per_replica": lj.n_particles, "baoab_steps_per_sweep": steps_per_sweep,
+            "replica_steps_per_s": sweeps * n_replicas * steps_per_sweep / dt,
+            "exchange": "even/odd neighbour swaps, one all_gather of the 64x64 reduced-potential matrix per sweep",
+            "last_sweep_swaps_accepted": acc, "last_sweep_swaps_proposed": prop, "batched_engine": batched,
+            "sweeps": sweeps, "api": "MultiStateSampler.run"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -329,14 +383,27 @@ def run_ours(args):
                "h2d_bytes_per_step": int(2 * n * 12 + 36), "d2h_bytes_per_step": int(2 * n * 12 + 8),
                "calls": ke, "api": "LangevinIntegrator.run(SamplerState[host], ThermodynamicState, number_of_steps=%d, nbr_list)" % S}
 
+    # ---- replica exchange (config 5), replicas sharded over the ranks -----------------------------------
+    remd = None
+    if not args.no_remd:
+        del eng
+        torch.cuda.empty_cache()
+        try:
+            remd = bench_remd(dev, rank, world, sweeps=args.remd_sweeps)
+        except Exception as exc:   # the headline number must survive a failure of the secondary workload
+            remd = {"error": repr(exc)}
+
     # ---- CPU baseline (rank 0, bounded sample) ------------------------------------------------------
     cpu = None
+    ref_events = st1["reference_rebuilds"] - st0["reference_rebuilds"]
+    ref_interval = (K * S / ref_events) if ref_events > 0 else None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, detail = cpu_reference_steps_per_s(x, box)
-        cpu = {"value": v, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": "%d of %d rows of the padded (N,M) list per step (calculate + masked LJ force + BAOAB) "
-                         "+ amortised O(N^2) build slice, scaled by N/rows; NumPy restatement of the reference "
-                         "algorithm, JAX unavailable" % (detail["rows"], n), **detail}
+        import __graft_entry__ as ge
+        ge.build_oracle()
+        v, detail = cpu_reference_steps_per_s(x, box, v0, rebuild_interval=ref_interval or REF_REBUILD_INTERVAL)
+        cpu = {"value": v, "unit": "steps/s", "cores": detail["threads"], "kind": "port",
+               "sample": CPU_SAMPLE % (detail["full_size_steps_timed"], detail["build_row_stride"],
+                                       detail["rebuild_interval_steps"]), **detail}
 
     if rank == 0:
         rebuilds = st1["table_rebuilds"] - st0["table_rebuilds"]
@@ -354,6 +421,8 @@ def run_ours(args):
             "pair_tests_per_s": p_cand * steps_per_s,
             "p_cand": p_cand, "p_int": p_int, "p_cand_internal_tables": p_cand_internal, "potential_energy_kj_mol": e_now,
             "table_rebuilds_in_timed_region": rebuilds,
+            "reference_rebuild_interval_steps": ref_interval,
+            "lane_utilisation": st_e.get("lane_utilisation"),
             "ms_per_baoab_step": ms_max / (K * S),
             "clocks": clocks.summary(),
             "e2e": e2e,
@@ -369,6 +438,7 @@ def run_ours(args):
                                  "frac": hbm_bytes / (ms_max / (K * S) * 1e-3) / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
             "cpu_baseline": cpu,
+            "remd": remd,
         }
         print(json.dumps(line))
     if world > 1:

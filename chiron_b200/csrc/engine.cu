@@ -71,8 +71,9 @@ struct chx_ljmd {
     int2* cell_range;                // per (x,y,z)-linear cell: [begin, end) in sorted order
     uint32_t* tiles;                 // nblk x tcap tiles of tstride words per replica (layout: k_md_deal)
     int* ntiles;
-    uint32_t *cand_idx, *cand_col;   // per block: ccap (candidate index, column word) pairs, k_md_cand -> k_md_deal
+    uint32_t *cand_idx, *cand_col;   // per block: ccap (candidate index, column word) pairs sorted by popcount
     int* cand_n;
+    uint16_t *memb, *tmeta;          // per tile: candidate number of every slot / max << 8 | fill (k_md_deal -> k_md_emit)
     uint8_t* generic;
     float4* bcenter;                 // per block: centre of its bounding box at the last build
     int tcap, qcap;                  // tiles per block / candidate queue entries per block
@@ -209,58 +210,65 @@ __global__ void k_md_cellcount(const float4* __restrict__ xs, MdGeom g, const in
     atomicAdd(&count[(size_t)r * (g.ncell + 1) + h], 1);
 }
 
-// one CTA per replica: exclusive scan over the cells in Hilbert order, 4096 cells per pass
+// one CTA per replica: exclusive scan over the cells in Hilbert order.  Warp w owns a chunk of 1024
+// consecutive cells (32 coalesced rows of 32); chunk totals are scanned across the block.
 __global__ void __launch_bounds__(1024)
 k_md_scan(int* __restrict__ count, int* __restrict__ start, int2* __restrict__ range,
           const int* __restrict__ h2lin, int ncell, const MdRep* __restrict__ rep) {
     __shared__ int wsum[32];
-    __shared__ int total;
+    __shared__ int carry;
     const int r = blockIdx.x;
     if (!rep[r].flag) return;
     count += (size_t)r * (ncell + 1);
     start += (size_t)r * (ncell + 1);
     range += (size_t)r * ncell;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    int base = 0;
-    for (int c0 = 0; c0 < ncell; c0 += 4096) {
-        const int c = c0 + 4 * t;
-        int v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = c + u < ncell ? count[c + u] : 0;
-        const int mine = v[0] + v[1] + v[2] + v[3];
-        int inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += u;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ncell; base += 32768) {
+        const int c0 = base + w * 1024;
+        int mine = 0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const int c = c0 + k * 32 + lane;
+            mine += c < ncell ? count[c] : 0;
         }
-        if (lane == 31) wsum[w] = inc;
+        mine = warp_sum(mine);
+        if (lane == 0) wsum[w] = mine;
         __syncthreads();
         if (w == 0) {
-            int s = wsum[lane];
+            const int v = wsum[lane];
+            int s = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int u = __shfl_up_sync(FULL, s, o);
                 if (lane >= o) s += u;
             }
-            wsum[lane] = s;
-            if (lane == 31) total = s;
+            wsum[lane] = s - v + carry;            // exclusive offset of chunk `lane`
+            if (lane == 31) carry += s;
         }
         __syncthreads();
-        int excl = base + inc - mine + (w > 0 ? wsum[w - 1] : 0);
+        int running = wsum[w];
+        for (int k = 0; k < 32; ++k) {
+            const int c = c0 + k * 32 + lane;
+            const int v = c < ncell ? count[c] : 0;
+            int inc = v;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (c + u < ncell) {
-                start[c + u] = excl;
-                count[c + u] = 0;
-                range[h2lin[c + u]] = make_int2(excl, excl + v[u]);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += u;
             }
-            excl += v[u];
+            const int excl = running + inc - v;
+            if (c < ncell) {
+                start[c] = excl;
+                count[c] = 0;
+                range[h2lin[c]] = make_int2(excl, excl + v);
+            }
+            running += __shfl_sync(FULL, inc, 31);
         }
-        base += total;
         __syncthreads();
     }
-    if (t == 0) start[ncell] = base;
+    if (t == 0) start[ncell] = carry;
 }
 
 __global__ void k_md_place(const int* __restrict__ cell_of, MdGeom g, const int* __restrict__ start,
@@ -369,8 +377,8 @@ k_md_cand(const float4* __restrict__ xs_all, const int2* __restrict__ range_all,
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * nw + w;
     if (b >= g.nblk) return;
-    // per-warp shared memory: stage[32] float4 | queue[qcap] | colmask[qcap]
-    unsigned char* base = smem_raw + (size_t)w * (512 + 8 * (size_t)qcap);
+    // per-warp shared memory: stage[32] float4 | queue[qcap] | colmask[qcap] | hist[40]
+    unsigned char* base = smem_raw + (size_t)w * (512 + 8 * (size_t)qcap + 160);
     float4* stage = reinterpret_cast<float4*>(base);
     uint32_t* queue = reinterpret_cast<uint32_t*>(base + 512);
     uint32_t* colmask = queue + qcap;
@@ -467,8 +475,6 @@ k_md_cand(const float4* __restrict__ xs_all, const int2* __restrict__ range_all,
     __syncwarp();
     int kept = 0;
     unsigned long long pairs = 0;
-    uint32_t* out_idx = cand_idx_all + rb * ccap;
-    uint32_t* out_col = cand_col_all + rb * ccap;
     for (int q0 = 0; q0 < qn; q0 += 32) {
         const bool have = q0 + lane < qn;
         const int p = have ? (int)queue[q0 + lane] : b * 32;
@@ -496,16 +502,60 @@ k_md_cand(const float4* __restrict__ xs_all, const int2* __restrict__ range_all,
         if (self < 32u) col &= ~(1u << self);
         if (!have) col = 0u;
         const unsigned bal = __ballot_sync(FULL, col != 0u);
+        // every lane has read its queue entry: the compacted list can overwrite the queue in place
         if (col != 0u) {
             const int pos = kept + __popc(bal & ((1u << lane) - 1u));
-            if (pos < ccap) { out_idx[pos] = (uint32_t)p; out_col[pos] = col; } else ovf = true;
+            queue[pos] = (uint32_t)p;
+            colmask[pos] = col;
         }
         kept += __popc(bal);
         pairs += (unsigned long long)__popc(col);
+        __syncwarp();
     }
-    ovf = __any_sync(FULL, ovf);
+    if (kept > ccap) { ovf = true; kept = ccap; }
+
+    // ---- 3. stable counting sort by decreasing column popcount (the deal wants heavy columns first) ----
+    int* hist = reinterpret_cast<int*>(colmask + qcap);
+    hist[lane] = 0;
+    if (lane == 0) hist[32] = 0;
+    __syncwarp();
+    for (int k = lane; k < kept; k += 32) atomicAdd(&hist[32 - __popc(colmask[k])], 1);
+    __syncwarp();
+    {
+        const int v = hist[lane];
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += u;
+        }
+        __syncwarp();
+        hist[lane] = inc - v;
+        if (lane == 31) hist[32] = inc;
+    }
+    __syncwarp();
+    uint32_t* out_idx = cand_idx_all + rb * ccap;
+    uint32_t* out_col = cand_col_all + rb * ccap;
+    const uint32_t rbase = (uint32_t)r * (uint32_t)g.np;   // tiles hold replica-absolute particle indices
+    const unsigned lt = (1u << lane) - 1u;
+    for (int k0 = 0; k0 < kept; k0 += 32) {
+        const int k = k0 + lane;
+        const bool have = k < kept;
+        const uint32_t col = have ? colmask[k] : 0u;
+        const int bin = have ? 32 - __popc(col) : 33;
+        const unsigned m = __match_any_sync(FULL, bin);
+        const int rank = __popc(m & lt);
+        const int at = have ? hist[bin] : 0;
+        __syncwarp();
+        if (have) {
+            out_idx[at + rank] = queue[k] + rbase;
+            out_col[at + rank] = col;
+            if (rank == 0) hist[bin] = at + __popc(m);
+        }
+        __syncwarp();
+    }
     if (lane == 0) {
-        cand_n_all[rb] = min(kept, ccap);
+        cand_n_all[rb] = kept;
         generic_all[rb] = gen ? 1 : 0;
         bcenter_all[rb] = make_float4(bcx, bcy, bcz, 0.f);
         if (ovf) atomicOr(&rep[r].overflow, 1);
@@ -521,187 +571,178 @@ k_md_cand(const float4* __restrict__ xs_all, const int2* __restrict__ range_all,
 //
 // A tile holds up to 31 candidates (slot 31 is the "no partner" sentinel).  The force kernel
 // spends max-over-lanes(partners in the tile) trips on a tile, so the deal minimises that max:
-// candidates are taken in order of decreasing column popcount (stable counting sort) and each
-// goes to the tile whose max lane count grows least (ties: emptier tile, lower index).  Each tile
-// keeps the mask of particles that sit at its max, so "does this candidate raise the max" is one AND
-// and the decision one REDUX.MIN per candidate.  Measured on the LJ bench state point: 84 % of the
-// lane slots do useful work against 67 % for a round-robin deal.
+// candidates come in order of decreasing column popcount (sorted by k_md_cand) and each goes to
+// the tile whose per-particle maximum grows least (ties: emptier tile, lower index).  Every tile
+// keeps the mask of particles that sit AT its max, so "does this candidate raise the max" is one
+// AND.  Measured on the LJ bench state point: 84-88 % of the lane slots do useful work against
+// 67 % for a round-robin deal.
 //
-// Tile layout (tstride = 32 * (1 + lw) words):
-//   word 0      [lane]  candidate index (bits 0..23); lane 31: trips << 24 | any valid index
-//   word 1 + k  [lane]  six 5-bit slot numbers (partners 6k .. 6k+5 of this lane, ascending slot),
-//                       unused entries = 31
+// The greedy is sequential per block, so the kernel is latency bound; EIGHT lanes share a block:
+// lane w of the group scans tiles w, w+8, ... and keeps the byte counters of particles 4w..4w+3 of
+// every tile (SWAR, one word per tile), 4 blocks per warp, 16 per CTA, warp-uniform control flow so
+// that the group reductions are plain full-mask shuffles.  Output: for every tile
+// the candidate number (position in the sorted list) of each slot, the tile's fill and trip count;
+// k_md_emit turns that into the tile words.
 // ---------------------------------------------------------------------------------------------
-#define DEAL_TMAX 64
 #define TILE_SLOTS 31
-#define DEAL_SEG (60 * TILE_SLOTS)
+#define DEAL_Q 8                      // lanes that share one block in k_md_deal
+#define DEAL_BPC (128 / DEAL_Q)       // blocks per CTA
 
-__host__ __device__ inline size_t md_deal_smem_per_warp(int ccap) {
-    // col[ccap] u32 | perm[ccap] u16 | memb[64*32] u16 | cnt[64*32] u8 | hist[40] int
-    return (size_t)ccap * 4 + (((size_t)ccap * 2 + 15) & ~(size_t)15) + DEAL_TMAX * 32 * 2 + DEAL_TMAX * 32 + 160;
+__host__ __device__ inline size_t md_deal_smem(int tcap) {
+    // per CTA: cnt[blocks][tcap][DEAL_Q] u32 (4 byte counters each) | at[blocks][tcap] u32 | cs[blocks][tcap] u32
+    return (size_t)DEAL_BPC * tcap * (DEAL_Q + 2) * sizeof(uint32_t);
 }
 
 __global__ void __launch_bounds__(128)
-k_md_deal(const uint32_t* __restrict__ cand_idx_all, const uint32_t* __restrict__ cand_col_all,
-          const int* __restrict__ cand_n_all, MdGeom g, int ccap, int tcap, int lw,
-          uint32_t* __restrict__ tiles_all, int* __restrict__ ntiles_all, MdRep* __restrict__ rep) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+k_md_deal(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ cand_n_all, MdGeom g,
+          int ccap, int tcap, int lw, uint16_t* __restrict__ memb_all, uint16_t* __restrict__ tmeta_all,
+          int* __restrict__ ntiles_all, MdRep* __restrict__ rep) {
+    extern __shared__ __align__(16) uint32_t deal_sm[];
     const int r = blockIdx.y;
     if (!rep[r].flag) return;
-    const int nw = blockDim.x >> 5;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * nw + w;
-    if (b >= g.nblk) return;
-    unsigned char* base = smem_raw + (size_t)w * md_deal_smem_per_warp(ccap);
-    uint32_t* col = reinterpret_cast<uint32_t*>(base);
-    uint16_t* perm = reinterpret_cast<uint16_t*>(base + (size_t)ccap * 4);
-    uint16_t* memb = reinterpret_cast<uint16_t*>(base + (size_t)ccap * 4 + (((size_t)ccap * 2 + 15) & ~(size_t)15));
-    uint8_t* cnt = reinterpret_cast<uint8_t*>(memb + DEAL_TMAX * 32);
-    int* hist = reinterpret_cast<int*>(cnt + DEAL_TMAX * 32);
+    const int grp = threadIdx.x / DEAL_Q, w = threadIdx.x % DEAL_Q;
+    const int b = blockIdx.x * DEAL_BPC + grp;
+    const bool exists = b < g.nblk;                // control flow below is warp-uniform: full-mask shuffles
+    uint32_t* cnt = deal_sm + ((size_t)grp * tcap) * DEAL_Q + w;                         // [tile * DEAL_Q]
+    uint32_t* at = deal_sm + (size_t)DEAL_BPC * tcap * DEAL_Q + (size_t)grp * tcap;
+    uint32_t* cs = deal_sm + (size_t)DEAL_BPC * tcap * (DEAL_Q + 1) + (size_t)grp * tcap;   // max << 8 | fill
+    for (int t = w; t < tcap; t += DEAL_Q) { at[t] = 0xffffffffu; cs[t] = 0u; }
+    for (int t = 0; t < tcap; ++t) cnt[t * DEAL_Q] = 0u;
+    __syncwarp();
 
+    const size_t rb = (size_t)r * g.nblk + (exists ? b : 0);
+    const uint32_t* in_col = cand_col_all + rb * ccap;
+    uint16_t* memb = memb_all + rb * (size_t)tcap * 32;
+    const int K = exists ? cand_n_all[rb] : 0;
+    const int cap = 6 * lw;
+    int T = (K + TILE_SLOTS - 1) / TILE_SLOTS;
+    bool ovf = T > tcap;
+    if (ovf) T = tcap;
+    const int Kw = __reduce_max_sync(FULL, K);
+    uint32_t c_next = K > 0 ? in_col[0] : 0u;
+    for (int q = 0; q < Kw; ++q) {
+        const bool active = q < K && !ovf;
+        const uint32_t c = c_next;
+        if (q + 1 < K) c_next = in_col[q + 1];
+        uint32_t best;
+        bool again;
+        do {
+            best = 0xffffffffu;
+            const int Tw = __reduce_max_sync(FULL, T);
+            for (int t = w; t < Tw; t += DEAL_Q) {
+                if (t < T) {
+                    const uint32_t m = cs[t];
+                    const uint32_t nm = (m >> 8) + ((c & at[t]) != 0u ? 1u : 0u);
+                    const uint32_t key = ((m & 0xffu) < TILE_SLOTS && nm <= (uint32_t)cap)
+                                             ? (nm << 18 | (m & 0xffu) << 12 | (uint32_t)t) : 0xffffffffu;
+                    best = min(best, key);
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < DEAL_Q; o <<= 1) best = min(best, __shfl_xor_sync(FULL, best, o));
+            again = false;
+            if (active && !ovf && best == 0xffffffffu) {
+                if (T < tcap && T < 4095) { ++T; again = true; }   // open one more tile
+                else ovf = true;
+            }
+        } while (__any_sync(FULL, again));
+        const bool place = active && !ovf;
+        const int tw = place ? (int)(best & 0xfffu) : 0, slot = (int)((best >> 12) & 0x3fu);
+        const uint32_t newmax = best >> 18;
+        // byte counters of my 4 particles in the winning tile: +1 where the column has a bit
+        const uint32_t b4 = place ? (c >> (4 * w)) & 0xfu : 0u;
+        const uint32_t cc = cnt[tw * DEAL_Q] + ((b4 * 0x00204081u) & 0x01010101u);
+        if (place) cnt[tw * DEAL_Q] = cc;
+        // which of them now sit at the tile's max: exact zero-byte test of (count ^ max)
+        uint32_t z = cc ^ (newmax * 0x01010101u);
+        z = ~(((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z | 0x7f7f7f7fu);
+        uint32_t eq = ((((z >> 7) * 0x00204081u) >> 21) & 0xfu) << (4 * w);
+#pragma unroll
+        for (int o = 1; o < DEAL_Q; o <<= 1) eq |= __shfl_xor_sync(FULL, eq, o);
+        if (place) {
+            if (w == (tw % DEAL_Q)) { at[tw] = eq; cs[tw] = newmax << 8 | (uint32_t)(slot + 1); }
+            if (w == 0) memb[tw * 32 + slot] = (uint16_t)q;
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    if (!exists) return;
+    uint16_t* tmeta = tmeta_all + rb * (size_t)tcap;
+    if (!ovf)
+        for (int t = w; t < T; t += DEAL_Q) tmeta[t] = (uint16_t)cs[t];     // max << 8 | fill
+    if (w == 0) {
+        ntiles_all[rb] = ovf ? 0 : T;
+        if (ovf) atomicOr(&rep[r].overflow, 2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// table build, part 3 (k_md_emit): one warp per block writes the tile words.
+//
+// Tile layout (tstride = 32 * (1 + lw) words):
+//   word 0      [lane]  replica-absolute particle index of the candidate in slot `lane` (bits 0..23);
+//                       lane 31: trips << 24 | any valid index
+//   word 1 + k  [lane]  six 5-bit slot numbers (partners 6k .. 6k+5 of this lane's particle,
+//                       ascending slot), unused entries = 31
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_md_emit(const uint32_t* __restrict__ cand_idx_all, const uint32_t* __restrict__ cand_col_all,
+          const uint16_t* __restrict__ memb_all, const uint16_t* __restrict__ tmeta_all,
+          const int* __restrict__ ntiles_all, MdGeom g, int ccap, int tcap, int lw,
+          uint32_t* __restrict__ tiles_all, MdRep* __restrict__ rep) {
+    const int r = blockIdx.y;
+    if (!rep[r].flag) return;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + w;
+    if (b >= g.nblk) return;
     const size_t rb = (size_t)r * g.nblk + b;
     const uint32_t* in_idx = cand_idx_all + rb * ccap;
     const uint32_t* in_col = cand_col_all + rb * ccap;
+    const uint16_t* memb = memb_all + rb * (size_t)tcap * 32;
+    const uint16_t* tmeta = tmeta_all + rb * (size_t)tcap;
     const int tstride = 32 * (1 + lw);
     uint32_t* tiles = tiles_all + rb * (size_t)(tcap + 2) * tstride;   // two pad tiles per block
-    const int K = cand_n_all[rb];
-    const int cap = 6 * lw;
-    const unsigned lt = (1u << lane) - 1u;
-
-    // ---- columns to shared memory, stable counting sort by decreasing popcount ----
-    for (int k = lane; k < K; k += 32) col[k] = in_col[k];
-    hist[lane] = 0;
-    if (lane == 0) hist[32] = 0;
-    __syncwarp();
-    for (int k = lane; k < K; k += 32) atomicAdd(&hist[32 - __popc(col[k])], 1);
-    __syncwarp();
-    {
-        const int v = hist[lane];
-        int inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += u;
-        }
-        __syncwarp();
-        hist[lane] = inc - v;
-        if (lane == 31) hist[32] = inc;
-    }
-    __syncwarp();
-    for (int k0 = 0; k0 < K; k0 += 32) {
-        const int k = k0 + lane;
-        const bool have = k < K;
-        const int bin = have ? 32 - __popc(col[k]) : 33;
-        const unsigned m = __match_any_sync(FULL, bin);
-        const int rank = __popc(m & lt);
-        const int at = have ? hist[bin] : 0;
-        __syncwarp();
-        if (have) {
-            perm[at + rank] = (uint16_t)k;
-            if (rank == 0) hist[bin] = at + __popc(m);
-        }
-        __syncwarp();
-    }
-
-    // ---- greedy deal, in segments of at most 64 tiles ----
-    // Two roles per lane: lane = particle i of the block (per-particle counts cnt[t][i], shared
-    // memory) and lane = owner of tiles `lane` and `lane + 32` (registers: the tile's max count,
-    // its fill, and the mask of particles that sit AT that max).  A candidate raises a tile's max
-    // iff its column word intersects that mask, so the whole decision is a few ALU ops and one
-    // REDUX.MIN; the mask is refreshed with one ballot.
-    const int nseg = (K + DEAL_SEG - 1) / DEAL_SEG;
-    int tile_base = 0;
-    bool ovf = false;
+    const int T = ntiles_all[rb];
+    const uint32_t filler = (uint32_t)r * (uint32_t)g.np + (uint32_t)(b * 32);
     unsigned long long slots = 0;
-    for (int seg = 0; seg < nseg && !ovf; ++seg) {
-        const int Ks = (K - seg + nseg - 1) / nseg;
-        int T = (Ks + TILE_SLOTS - 1) / TILE_SLOTS;
-        {
-            uint32_t* c4 = reinterpret_cast<uint32_t*>(cnt);
-#pragma unroll
-            for (int u = 0; u < DEAL_TMAX * 32 / 4 / 32; ++u) c4[u * 32 + lane] = 0u;
+    // one tile ahead: slot -> candidate number -> (index, column word)
+    int meta_n = T > 0 ? (int)tmeta[0] : 0;
+    int q_n = (T > 0 && lane < (meta_n & 0xff)) ? (int)memb[lane] : -1;
+    uint32_t idx_n = q_n >= 0 ? in_idx[q_n] : filler;
+    uint32_t col_n = q_n >= 0 ? in_col[q_n] : 0u;
+    for (int t = 0; t < T; ++t) {
+        const int trips = meta_n >> 8;
+        uint32_t myIdx = idx_n, x = col_n;
+        if (t + 1 < T) {
+            meta_n = (int)tmeta[t + 1];
+            q_n = lane < (meta_n & 0xff) ? (int)memb[(t + 1) * 32 + lane] : -1;
+            idx_n = q_n >= 0 ? in_idx[q_n] : filler;
+            col_n = q_n >= 0 ? in_col[q_n] : 0u;
         }
-        __syncwarp();
-        uint32_t atA = 0xffffffffu, atB = 0xffffffffu;   // particles at the max of tile lane / lane + 32
-        int cmA = 0, cmB = 0, szA = 0, szB = 0;
-        int k_next = Ks > 0 ? (int)perm[seg] : 0;
-        uint32_t c_next = Ks > 0 ? col[k_next] : 0u;
-        for (int q = 0; q < Ks; ++q) {
-            const int k = k_next;
-            const uint32_t c = c_next;
-            if (q + 1 < Ks) { k_next = (int)perm[seg + (q + 1) * nseg]; c_next = col[k_next]; }
-            uint32_t kmin;
-            for (;;) {
-                const int nmA = cmA + ((c & atA) != 0u ? 1 : 0);
-                const int nmB = cmB + ((c & atB) != 0u ? 1 : 0);
-                const uint32_t keyA = (lane < T && szA < TILE_SLOTS && nmA <= cap)
-                                          ? ((uint32_t)nmA << 16 | (uint32_t)szA << 8 | (uint32_t)lane) : 0xffffffffu;
-                const uint32_t keyB = (lane + 32 < T && szB < TILE_SLOTS && nmB <= cap)
-                                          ? ((uint32_t)nmB << 16 | (uint32_t)szB << 8 | (uint32_t)(lane + 32)) : 0xffffffffu;
-                kmin = __reduce_min_sync(FULL, min(keyA, keyB));
-                if (kmin != 0xffffffffu) break;
-                if (T < DEAL_TMAX && tile_base + T < tcap) { ++T; continue; }   // open one more tile
-                ovf = true;
-                break;
-            }
-            if (ovf) break;
-            const int tw = (int)(kmin & 0xffu), newmax = (int)(kmin >> 16), slot = (int)((kmin >> 8) & 0xffu);
-            const bool bbit = (c >> lane) & 1u;
-            int cc = -1;
-            if (bbit) { cc = (int)cnt[tw * 32 + lane] + 1; cnt[tw * 32 + lane] = (uint8_t)cc; }
-            const uint32_t newat = __ballot_sync(FULL, bbit && cc == newmax);
-            if (lane == (tw & 31)) {
-                if (tw < 32) { atA = newmax > cmA ? newat : (atA | newat); cmA = newmax; ++szA; }
-                else         { atB = newmax > cmB ? newat : (atB | newat); cmB = newmax; ++szB; }
-            }
-            if (lane == 0) memb[tw * 32 + slot] = (uint16_t)k;
-        }
-        __syncwarp();
-        if (ovf) break;
-        // ---- emit the tiles of this segment ----
-        int sz_n = __shfl_sync(FULL, szA, 0);
-        int k_n = lane < sz_n ? (int)memb[lane] : -1;
-        uint32_t idx_n = k_n >= 0 ? in_idx[k_n] : (uint32_t)(b * 32);
-        for (int t = 0; t < T; ++t) {
-            const int k = k_n;
-            uint32_t myIdx = idx_n;
-            const int trips = __shfl_sync(FULL, t < 32 ? cmA : cmB, t & 31);
-            if (t + 1 < T) {
-                sz_n = __shfl_sync(FULL, t + 1 < 32 ? szA : szB, (t + 1) & 31);
-                k_n = lane < sz_n ? (int)memb[(t + 1) * 32 + lane] : -1;
-                idx_n = k_n >= 0 ? in_idx[k_n] : (uint32_t)(b * 32);
-            }
-            uint32_t x = k >= 0 ? col[k] : 0u;                     // column word of slot `lane`
-            // 32x32 bit transpose across the warp: afterwards lane i holds the slot mask of particle i
-            uint32_t m = 0x0000ffffu;
+        // 32x32 bit transpose across the warp: afterwards lane i holds the slot mask of particle i
+        uint32_t m = 0x0000ffffu;
 #pragma unroll
-            for (int j = 16; j > 0; j >>= 1) {
-                const uint32_t y = __shfl_xor_sync(FULL, x, j);
-                x = (lane & j) ? ((x & (m << j)) | ((y >> j) & m)) : ((x & m) | ((y & m) << j));
-                m ^= m << (j >> 1);
-            }
-            if (lane == 31) myIdx |= (uint32_t)trips << 24;
-            uint32_t* tp = tiles + (size_t)(tile_base + t) * tstride;
-            tp[lane] = myIdx;
-            for (int wi = 0; wi < lw; ++wi) {
-                uint32_t wv = 0u;
-#pragma unroll
-                for (int f = 0; f < 6; ++f) {
-                    const int s = x ? __ffs(x) - 1 : 31;
-                    x &= x - 1u;
-                    wv |= (uint32_t)s << (5 * f);
-                }
-                tp[32 * (1 + wi) + lane] = wv;
-            }
-            slots += (unsigned long long)(32 * 2 * ((trips + 1) >> 1));
+        for (int j = 16; j > 0; j >>= 1) {
+            const uint32_t y = __shfl_xor_sync(FULL, x, j);
+            x = (lane & j) ? ((x & (m << j)) | ((y >> j) & m)) : ((x & m) | ((y & m) << j));
+            m ^= m << (j >> 1);
         }
-        tile_base += T;
+        if (lane == 31) myIdx |= (uint32_t)trips << 24;
+        uint32_t* tp = tiles + (size_t)t * tstride;
+        tp[lane] = myIdx;
+        for (int wi = 0; wi < lw; ++wi) {
+            uint32_t wv = 0u;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+                const int s = x ? __ffs(x) - 1 : 31;
+                x &= x - 1u;
+                wv |= (uint32_t)s << (5 * f);
+            }
+            tp[32 * (1 + wi) + lane] = wv;
+        }
+        slots += (unsigned long long)(32 * 2 * ((trips + 1) >> 1));
     }
-    if (lane == 0) {
-        ntiles_all[rb] = ovf ? 0 : tile_base;
-        if (ovf) atomicOr(&rep[r].overflow, 2);
-        else if (slots) atomicAdd(&rep[r].trip_slots, slots);
-    }
+    if (lane == 0 && slots) atomicAdd(&rep[r].trip_slots, slots);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -724,6 +765,10 @@ struct LjConst {
 #ifndef CHX_FW
 #define CHX_FW 1
 #endif
+#ifndef CHX_TRIP_UNROLL
+#define CHX_TRIP_UNROLL 1
+#endif
+constexpr int kTripUnroll = CHX_TRIP_UNROLL;   // unroll factor of the packed trip loop
 #define FW CHX_FW  // warps per CTA in the force kernel
 
 // partner number e of this lane in a tile: 5-bit field e % 6 of list word e / 6
@@ -733,9 +778,11 @@ __device__ __forceinline__ int tile_slot(const uint32_t* __restrict__ tp, uint32
     return (int)((wv >> (5 * (e - 6 * wi))) & 31u);
 }
 
-template <bool ENERGY, bool GEN>
+// xs: positions of ALL replicas (the tiles hold replica-absolute indices).  LW2: two list words per
+// tile (at most 12 partners per lane and tile), the common case, with the list kept in registers.
+template <bool ENERGY, bool GEN, bool LW2>
 __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, const uint32_t* __restrict__ tp,
-                                             int nt, int tstride, int lw, const float4 xi0, const float4 xi,
+                                             int nt, int tstride, const float4 xi0, const float4 xi,
                                              const float4 bc, const MdGeom& g, const LjConst& lj, int lane,
                                              float& fx, float& fy, float& fz, float& e_acc, unsigned& npair) {
     // software pipeline over the tiles: index/list words are fetched two tiles ahead and the j
@@ -813,12 +860,12 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
             // slot for two pairs -- this loop is issue bound)
             int rem = (trips + 1) >> 1;
             for (int wp = 0; rem > 0; wp += 2) {
-                const uint32_t wa = wp == 0 ? la : tp[32 * (1 + wp) + lane];
-                const uint32_t wb = wp == 0 ? lb : tp[32 * (2 + wp) + lane];
+                const uint32_t wa = (LW2 || wp == 0) ? la : tp[32 * (1 + wp) + lane];
+                const uint32_t wb = (LW2 || wp == 0) ? lb : tp[32 * (2 + wp) + lane];
                 uint32_t lo = wa | (wb << 30), hi = wb >> 2;   // 12 partners, 5 bits each
-                const int n2 = rem < 6 ? rem : 6;
+                const int n2 = LW2 ? rem : (rem < 6 ? rem : 6);
                 rem -= n2;
-#pragma unroll 1
+#pragma unroll kTripUnroll
                 for (int k2 = n2; k2 > 0; --k2) {
                     const int sa = (int)lo, sb = (int)(lo >> 5);   // SHFL.IDX reads the low 5 bits
                     lo = __funnelshift_r(lo, hi, 10);
@@ -929,18 +976,21 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
             if (b == 0 && lane == 0) rep[r].user_rebuilds++;
         }
         const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * (size_t)(tcap + 2) * tstride;
-        const int lw = tstride / 32 - 1;
+        const bool lw2 = tstride == 96;
         const int nt = ntiles_all[(size_t)r * g.nblk + b];
         const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
         const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
         float fx = 0.f, fy = 0.f, fz = 0.f;
         if (gen) {
-            md_tile_loop<ENERGY, true>(xs, tp, nt, tstride, lw, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+            md_tile_loop<ENERGY, true, false>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
         } else {
             xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
             xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
             xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
-            md_tile_loop<ENERGY, false>(xs, tp, nt, tstride, lw, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+            if (lw2)
+                md_tile_loop<ENERGY, false, true>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+            else
+                md_tile_loop<ENERGY, false, false>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
         }
         fs_all[(size_t)r * g.np + i] = make_float4(fx, fy, fz, 0.5f * e_acc);
     }
@@ -1095,6 +1145,8 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->cand_idx, nb * md_ccap(md) * sizeof(uint32_t)));
     CHX_CUDA(cudaMalloc(&md->cand_col, nb * md_ccap(md) * sizeof(uint32_t)));
     CHX_CUDA(cudaMalloc(&md->cand_n, nb * sizeof(int)));
+    CHX_CUDA(cudaMalloc(&md->memb, nb * md->tcap * 32 * sizeof(uint16_t)));
+    CHX_CUDA(cudaMalloc(&md->tmeta, nb * md->tcap * sizeof(uint16_t)));
     CHX_CUDA(cudaMalloc(&md->ntiles, nb * sizeof(int)));
     CHX_CUDA(cudaMalloc(&md->generic, nb));
     CHX_CUDA(cudaMalloc(&md->bcenter, nb * sizeof(float4)));
@@ -1153,7 +1205,7 @@ static int md_download_rep(chx_ljmd* md) {
     return CHX_OK;
 }
 
-static size_t md_build_smem(int nw, int qcap) { return (size_t)nw * (512 + 8 * (size_t)qcap); }
+static size_t md_build_smem(int nw, int qcap) { return (size_t)nw * (512 + 8 * (size_t)qcap + 160); }
 
 // sort + table build for the replicas whose rep_host[r].flag is set (rep_host must already be
 // uploaded); grows the table capacity on overflow.  Leaves rep_host refreshed.
@@ -1182,11 +1234,9 @@ static int md_rebuild(chx_ljmd* md) {
         int nw = 4;
         while (nw > 1 && md_build_smem(nw, md->qcap) > 200 * 1024) nw >>= 1;
         const size_t smem = md_build_smem(nw, md->qcap);
-        int nwd = 4;
-        while (nwd > 1 && nwd * md_deal_smem_per_warp(md_ccap(md)) > 100 * 1024) nwd >>= 1;
-        const size_t smem_d = nwd * md_deal_smem_per_warp(md_ccap(md));
+        const size_t smem_d = md_deal_smem(md->tcap);
         if (smem > 220 * 1024 || smem_d > 220 * 1024 || md_ccap(md) > 65535) {
-            chx_set_error("neighbour table build needs %zu / %zu bytes of shared memory per warp", smem, smem_d);
+            chx_set_error("neighbour table build needs %zu / %zu bytes of shared memory", smem, smem_d);
             return CHX_NEIGHBOR_OVERFLOW;
         }
         CHX_CUDA(cudaFuncSetAttribute(k_md_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1195,9 +1245,12 @@ static int md_rebuild(chx_ljmd* md) {
             md->cand_col, md->cand_n, md->generic, md->bcenter, md->rep);
         CHX_LAUNCHED(ctx);
         CHX_CUDA(cudaFuncSetAttribute(k_md_deal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
-        k_md_deal<<<dim3(chx_div_up(g.nblk, nwd), R), nwd * 32, smem_d, st>>>(
-            md->cand_idx, md->cand_col, md->cand_n, g, md_ccap(md), md->tcap, md->lw, md->tiles, md->ntiles,
-            md->rep);
+        k_md_deal<<<dim3(chx_div_up(g.nblk, DEAL_BPC), R), 128, smem_d, st>>>(
+            md->cand_col, md->cand_n, g, md_ccap(md), md->tcap, md->lw, md->memb, md->tmeta, md->ntiles, md->rep);
+        CHX_LAUNCHED(ctx);
+        k_md_emit<<<dim3(chx_div_up(g.nblk, 4), R), 128, 0, st>>>(
+            md->cand_idx, md->cand_col, md->memb, md->tmeta, md->ntiles, g, md_ccap(md), md->tcap, md->lw,
+            md->tiles, md->rep);
         CHX_LAUNCHED(ctx);
         int rc = md_download_rep(md);
         if (rc != CHX_OK) return rc;
@@ -1223,10 +1276,14 @@ static int md_rebuild(chx_ljmd* md) {
         CHX_CUDA(cudaFree(md->tiles));
         CHX_CUDA(cudaFree(md->cand_idx));
         CHX_CUDA(cudaFree(md->cand_col));
+        CHX_CUDA(cudaFree(md->memb));
+        CHX_CUDA(cudaFree(md->tmeta));
         CHX_CUDA(cudaMalloc(&md->tiles, md_tiles_bytes(md)));
         CHX_CUDA(cudaMemsetAsync(md->tiles, 0, md_tiles_bytes(md), st));
         CHX_CUDA(cudaMalloc(&md->cand_idx, nb * md_ccap(md) * sizeof(uint32_t)));
         CHX_CUDA(cudaMalloc(&md->cand_col, nb * md_ccap(md) * sizeof(uint32_t)));
+        CHX_CUDA(cudaMalloc(&md->memb, nb * md->tcap * 32 * sizeof(uint16_t)));
+        CHX_CUDA(cudaMalloc(&md->tmeta, nb * md->tcap * sizeof(uint16_t)));
         for (int r = 0; r < R; ++r) {
             // tables of replicas that were NOT flagged are gone with the old allocation: rebuild all
             if (!(md->rep_host[r].flag & 1)) md->rep_host[r].flag |= 2;
@@ -1264,6 +1321,7 @@ int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
     CHX_REQUIRE(ctx && p && out, "NULL argument");
     CHX_REQUIRE(p->n > 0 && p->n < (1 << 24), "n must be in (0, 2^24)");
     CHX_REQUIRE(p->n_replicas >= 1, "n_replicas must be >= 1");
+    CHX_REQUIRE((long long)p->n_replicas * (p->n + 32) < (1ll << 24), "n_replicas * n must be below 2^24");
     CHX_REQUIRE(p->lx > 0 && p->ly > 0 && p->lz > 0, "box must be positive");
     CHX_REQUIRE(p->cutoff > 0 && p->skin >= 0, "cutoff must be positive, skin non-negative");
     chx_ljmd* md = new chx_ljmd();
@@ -1322,7 +1380,7 @@ int chx_ljmd_destroy(chx_ljmd* md) {
     cudaFree(md->ru_t); cudaFree(md->fs); cudaFree(md->refi); cudaFree(md->cell_count);
     cudaFree(md->cell_start); cudaFree(md->cell_range); cudaFree(md->lin2h); cudaFree(md->h2lin);
     cudaFree(md->cell_of); cudaFree(md->order); cudaFree(md->tiles); cudaFree(md->ntiles);
-    cudaFree(md->cand_idx); cudaFree(md->cand_col); cudaFree(md->cand_n);
+    cudaFree(md->cand_idx); cudaFree(md->cand_col); cudaFree(md->cand_n); cudaFree(md->memb); cudaFree(md->tmeta);
     cudaFree(md->generic); cudaFree(md->bcenter); cudaFree(md->rep); cudaFree(md->step_base);
     if (md->chunk_graph) cudaGraphExecDestroy(md->chunk_graph);
     if (md->cap_stream) cudaStreamDestroy(md->cap_stream);

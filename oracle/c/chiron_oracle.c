@@ -113,6 +113,108 @@ int orc_nlist_build_rows(const float* x, int n, const float* box, int periodic, 
     return maxc;
 }
 
+/* Same arrays as orc_nlist_build_rows(row0=0,row1=n) through a cell grid (edge >= cutoff+skin, 27-cell
+ * sweep, exact predicate, rows sorted ascending).  NOT part of the reference algorithm: a set-up
+ * accelerator so that bench.py can obtain the reference's list at N = 262,144 without waiting for the
+ * O(N^2) build (which is timed separately on a row sample), and a cross-check of the N^2 builder. */
+static int cmp_u32(const void* a, const void* b) {
+    uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+int orc_nlist_build_cells(const float* x, int n, const float* box, float cutoff_plus_skin, int M,
+                          uint32_t* list, int32_t* mask, int32_t* nn) {
+    int nc[3];
+    for (int c = 0; c < 3; ++c) {
+        nc[c] = (int)floorf(box[c] / (cutoff_plus_skin * 1.0001f));
+        if (nc[c] < 3) return orc_nlist_build_rows(x, n, box, 1, cutoff_plus_skin, M, 0, n, list, mask, nn);
+        if (nc[c] > 256) nc[c] = 256;
+    }
+    const int ncell = nc[0] * nc[1] * nc[2];
+    int* cell_of = (int*)malloc(sizeof(int) * (size_t)n);
+    int* start = (int*)calloc((size_t)ncell + 1, sizeof(int));
+    int* order = (int*)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        int cc[3];
+        for (int c = 0; c < 3; ++c) {
+            float w = x[3 * (size_t)i + c] - floorf(x[3 * (size_t)i + c] / box[c]) * box[c];
+            int k = (int)floorf(w / box[c] * nc[c]);
+            cc[c] = k < 0 ? 0 : (k >= nc[c] ? nc[c] - 1 : k);
+        }
+        cell_of[i] = (cc[0] * nc[1] + cc[1]) * nc[2] + cc[2];
+        start[cell_of[i] + 1]++;
+    }
+    for (int c = 0; c < ncell; ++c) start[c + 1] += start[c];
+    int* cur = (int*)malloc(sizeof(int) * (size_t)ncell);
+    memcpy(cur, start, sizeof(int) * (size_t)ncell);
+    for (int i = 0; i < n; ++i) order[cur[cell_of[i]]++] = i;
+    free(cur);
+    int maxc = 0;
+#pragma omp parallel reduction(max : maxc)
+    {
+        int capn = 1024;
+        uint32_t* buf = (uint32_t*)malloc(sizeof(uint32_t) * capn);
+#pragma omp for schedule(dynamic, 64)
+        for (int i = 0; i < n; ++i) {
+            int cnt = 0;
+            const int ci = cell_of[i];
+            const int cz = ci % nc[2], cy = (ci / nc[2]) % nc[1], cx = ci / (nc[2] * nc[1]);
+            for (int dx = -1; dx <= 1; ++dx)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dz = -1; dz <= 1; ++dz) {
+                        const int ox = (cx + dx + nc[0]) % nc[0], oy = (cy + dy + nc[1]) % nc[1],
+                                  oz = (cz + dz + nc[2]) % nc[2];
+                        const int c = (ox * nc[1] + oy) * nc[2] + oz;
+                        for (int k = start[c]; k < start[c + 1]; ++k) {
+                            const int j = order[k];
+                            if (j <= i) continue;
+                            float r[3];
+                            if (disp(x + 3 * (size_t)i, x + 3 * (size_t)j, box, 1, r) < cutoff_plus_skin) {
+                                if (cnt == capn) { capn *= 2; buf = (uint32_t*)realloc(buf, sizeof(uint32_t) * capn); }
+                                buf[cnt++] = (uint32_t)j;
+                            }
+                        }
+                    }
+            qsort(buf, cnt, sizeof(uint32_t), cmp_u32);
+            uint32_t fill = cnt ? buf[0] : 0u;
+            if (fill == (uint32_t)i) fill += 1u;
+            if (list) {
+                uint32_t* row = list + (size_t)i * M;
+                int32_t* mrow = mask + (size_t)i * M;
+                for (int k = 0; k < M; ++k) { row[k] = k < cnt ? buf[k] : fill; mrow[k] = k < cnt ? 1 : 0; }
+            }
+            nn[i] = cnt;
+            if (cnt > maxc) maxc = cnt;
+        }
+        free(buf);
+    }
+    free(cell_of); free(start); free(order);
+    return maxc;
+}
+
+/* wall time of the reference O(N^2) row loop on the rows row0, row0+stride, ... (counts only) */
+double orc_nlist_time_rows(const float* x, int n, const float* box, float cutoff_plus_skin, int row0,
+                           int stride, long long* pair_tests) {
+    double t0 = 0.0;
+#ifdef _OPENMP
+    t0 = omp_get_wtime();
+#endif
+    long long tests = 0, hits = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : tests, hits)
+    for (int i = row0; i < n; i += stride) {
+        float r[3];
+        for (int j = i + 1; j < n; ++j)
+            hits += disp(x + 3 * (size_t)i, x + 3 * (size_t)j, box, 1, r) < cutoff_plus_skin;
+        tests += n - i - 1;
+    }
+    if (pair_tests) *pair_tests = tests + (hits & 0);   /* keep `hits` live */
+#ifdef _OPENMP
+    return omp_get_wtime() - t0;
+#else
+    return 0.0;
+#endif
+}
+
 int orc_nlist_check(const float* x, const float* ref, int n, const float* box, int periodic, float half_skin) {
     int any = 0;
 #pragma omp parallel for reduction(| : any)
@@ -277,12 +379,16 @@ static double now_s(void) {
 
 typedef struct { uint32_t* list; int32_t* mask; int32_t* nn; int M; float* ref; } nlist_t;
 
+static int g_build_mode = 0;   /* 0 = reference O(N^2) build, 1 = cell-grid set-up accelerator */
+void orc_set_build_mode(int mode) { g_build_mode = mode; }
+
 static void nlist_build(nlist_t* nl, const float* x, int n, const float* box, float cps) {
     /* growth loop of neighbors.py:709-729: while any(n == M): M = max(n) + 10 ; rebuild */
     for (;;) {
         nl->list = (uint32_t*)realloc(nl->list, sizeof(uint32_t) * (size_t)n * nl->M);
         nl->mask = (int32_t*)realloc(nl->mask, sizeof(int32_t) * (size_t)n * nl->M);
-        int maxc = orc_nlist_build_rows(x, n, box, 1, cps, nl->M, 0, n, nl->list, nl->mask, nl->nn);
+        int maxc = g_build_mode ? orc_nlist_build_cells(x, n, box, cps, nl->M, nl->list, nl->mask, nl->nn)
+                                : orc_nlist_build_rows(x, n, box, 1, cps, nl->M, 0, n, nl->list, nl->mask, nl->nn);
         int hit = 0;
         for (int i = 0; i < n; ++i) hit |= (nl->nn[i] == nl->M);
         if (!hit) break;

@@ -41,6 +41,11 @@ def lib():
         L.orc_nlist_build_rows.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, _ip]
         L.orc_nlist_build_rows.restype = C.c_int
+        L.orc_nlist_build_cells.argtypes = [_fp, C.c_int, _fp, C.c_float, C.c_int, C.c_void_p, C.c_void_p, _ip]
+        L.orc_nlist_build_cells.restype = C.c_int
+        L.orc_nlist_time_rows.argtypes = [_fp, C.c_int, _fp, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+        L.orc_nlist_time_rows.restype = C.c_double
+        L.orc_set_build_mode.argtypes = [C.c_int]
         L.orc_nlist_check.argtypes = [_fp, _fp, C.c_int, _fp, C.c_int, C.c_float]
         L.orc_lj_nlist.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                    C.c_int, _up, _ip, C.c_void_p, C.POINTER(C.c_longlong)]
@@ -110,6 +115,30 @@ def build_neighborlist(x, box, cutoff, skin, n_max_neighbors, periodic=True):
             break
         M = mx + 10
     return dict(neighbor_list=nl, neighbor_mask=mask, n_neighbors=nn, n_max_neighbors=M)
+
+
+def build_cells(x, box, cutoff_plus_skin, M):
+    """Cell-grid builder (set-up accelerator, same arrays as the reference build)."""
+    x = _f(x)
+    n = x.shape[0]
+    nl = np.empty((n, M), np.uint32)
+    mask = np.empty((n, M), np.int32)
+    nn = np.empty(n, np.int32)
+    mx = lib().orc_nlist_build_cells(x, n, _box3(box), float(cutoff_plus_skin), int(M), nl.ctypes.data, mask.ctypes.data, nn)
+    return nl, mask, nn, int(mx)
+
+
+def time_reference_build_rows(x, box, cutoff_plus_skin, stride, row0=0):
+    """(seconds, pair tests) of the reference's O(N^2) row loop on every `stride`-th row."""
+    x = _f(x)
+    tests = C.c_longlong(0)
+    t = lib().orc_nlist_time_rows(x, x.shape[0], _box3(box), float(cutoff_plus_skin), int(row0), int(stride), C.byref(tests))
+    return float(t), int(tests.value)
+
+
+def set_build_mode(mode):
+    """0: langevin_lj rebuilds with the reference's O(N^2) loop; 1: with the cell-grid accelerator."""
+    lib().orc_set_build_mode(int(mode))
 
 
 def check(x, ref, box, skin, periodic=True):

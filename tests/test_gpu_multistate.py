@@ -1,0 +1,143 @@
+"""MultiStateSampler on the GPU: the reference's own multistate tests (`chiron/tests/test_multistate.py`)
+re-stated against this implementation, plus the batched / replica-exchange paths that are new here."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup_sampler(n_steps=100, **kw):
+    from chiron_b200 import unit
+    from chiron_b200.mcmc import LangevinDynamicsMove, MCMCSampler, MoveSchedule
+    from chiron_b200.multistate import MultiStateSampler
+    from chiron_b200.neighbors import OrthogonalNonPeriodicSpace, PairListNsqrd
+    from chiron_b200.reporters import MultistateReporter
+    nbr_list = PairListNsqrd(OrthogonalNonPeriodicSpace(), cutoff=10.0 * unit.nanometer)
+    lang_move = LangevinDynamicsMove(timestep=1.0 * unit.femtoseconds, number_of_steps=n_steps)
+    reporter = MultistateReporter()
+    reporter.reset_reporter_file()
+    sampler = MCMCSampler(MoveSchedule([("LangevinDynamicsMove", lang_move)]))
+    return nbr_list, MultiStateSampler(mcmc_sampler=sampler, reporter=reporter, **kw)
+
+
+def _ho_minima(cuda_device, tmp_path):
+    """`ho_multistate_sampler_multiple_minima` (test_multistate.py:43-88)."""
+    from chiron_b200 import unit
+    from chiron_b200.potential import HarmonicOscillatorPotential
+    from chiron_b200.reporters import BaseReporter
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import HarmonicOscillator
+    from chiron_b200.utils import PRNG
+    BaseReporter.set_directory(str(tmp_path))
+    T = 300.0 * unit.kelvin
+    x0s = [unit.Quantity(np.array([[x0, 0.0, 0.0]]), unit.angstrom) for x0 in np.linspace(0.0, 1.0, 3)]
+    ho = HarmonicOscillator()
+    thermo = [ThermodynamicState(HarmonicOscillatorPotential(ho.topology, x0=x0), temperature=T) for x0 in x0s]
+    PRNG.set_seed(1234)
+    states = [SamplerState(ho.positions, PRNG.get_random_key()) for _ in x0s]
+    nbr_list, ms = _setup_sampler()
+    ms.create(thermodynamic_states=thermo, sampler_states=states, nbr_lists=[copy.deepcopy(nbr_list) for _ in x0s])
+    return ms
+
+
+def test_multistate_class_and_minimize(cuda_device, tmp_path):
+    ms = _ho_minima(cuda_device, tmp_path)
+    assert ms._iteration == 0 and ms.number_of_replicas == 3 and ms.number_of_thermodynamic_states == 3
+    assert ms._energy_thermodynamic_states.shape == (3, 3) and ms._n_proposed_matrix.shape == (3, 3)
+    with pytest.raises(RuntimeError):
+        ms.create(ms._thermodynamic_states, ms._sampler_states[:2], ms._nbr_lists)
+    ms.minimize()
+    x = [s.positions.cpu().numpy() for s in ms.sampler_states]
+    assert np.allclose(x[0], [[0.0, 0.0, 0.0]], atol=1e-4)
+    assert np.allclose(x[1], [[0.05, 0.0, 0.0]], atol=1e-2)       # test_multistate.py:196-205
+    assert np.allclose(x[2], [[0.1, 0.0, 0.0]], atol=1e-2)
+
+
+def test_multistate_run_free_energies(cuda_device, tmp_path):
+    """`test_multistate_run` (test_multistate.py:211-251): 4 oscillators of different stiffness, 20 iterations,
+    MBAR free energies within 0.1 of the analytic values."""
+    from chiron_b200 import unit
+    from chiron_b200.potential import HarmonicOscillatorPotential
+    from chiron_b200.reporters import BaseReporter
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import HarmonicOscillator
+    from chiron_b200.utils import PRNG
+    BaseReporter.set_directory(str(tmp_path))
+    ho = HarmonicOscillator()
+    T = 300.0 * unit.kelvin
+    kT = unit.BOLTZMANN_CONSTANT_kB * T * unit.AVOGADRO_CONSTANT_NA
+    sigmas = [unit.Quantity(2.0 + 0.2 * k, unit.angstrom) for k in range(4)]
+    thermo = [ThermodynamicState(HarmonicOscillatorPotential(ho.topology, k=kT / s ** 2), temperature=T) for s in sigmas]
+    PRNG.set_seed(1234)
+    states = [SamplerState(ho.positions, current_PRNG_key=PRNG.get_random_key()) for _ in sigmas]
+    f_i = np.array([-np.log(2 * np.pi * float(s / unit.angstroms) ** 2) * 1.5 for s in sigmas])
+    nbr_list, ms = _setup_sampler()
+    ms.create(thermo, states, [copy.deepcopy(nbr_list) for _ in sigmas])
+    n_iterations = 20
+    ms.run(n_iterations)
+    assert ms.iteration == n_iterations and ms.number_of_replicas == 4
+    u_kn = ms._reporter.get_property("u_kn")
+    assert u_kn.shape == (n_iterations + 1, 4, 4)                    # test_multistate.py:243
+    assert np.allclose((f_i - f_i[0]), ms.f_k, atol=0.1)             # test_multistate.py:251
+
+
+def _lj_replicas(n_rep, steps, tmp_path, batched, exchange=None, seed=3):
+    from chiron_b200 import random as crandom, unit
+    from chiron_b200.mcmc import LangevinDynamicsMove, MCMCSampler, MoveSchedule
+    from chiron_b200.multistate import MultiStateSampler
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.reporters import BaseReporter, MultistateReporter
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import LennardJonesFluid
+    BaseReporter.set_directory(str(tmp_path))
+    lj = LennardJonesFluid(nparticles=512, reduced_density=0.8, seed=seed)
+    pot = LJPotential(lj.topology, lj.sigma, lj.epsilon, 1.02 * unit.nanometer)
+    temps = [300.0 * 1.15 ** k for k in range(n_rep)]
+    thermo = [ThermodynamicState(pot, temperature=t * unit.kelvin) for t in temps]
+    keys = crandom.split(crandom.PRNGKey(77), n_rep)
+    states = [SamplerState(lj.positions, keys[k], box_vectors=lj.box_vectors) for k in range(n_rep)]
+    nbrs = [NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.02 * unit.nanometer, skin=0.3 * unit.nanometer,
+                              n_max_neighbors=200) for _ in range(n_rep)]
+    move = LangevinDynamicsMove(timestep=1.0 * unit.femtoseconds, number_of_steps=steps)
+    ms = MultiStateSampler(MCMCSampler(MoveSchedule([("LangevinDynamicsMove", move)])), MultistateReporter(),
+                           exchange=exchange, exchange_seed=5, mcmc_iterations_per_sweep=1)
+    ms.use_batched_engine = batched
+    ms.create(thermo, states, nbrs)
+    return ms, pot, temps
+
+
+def test_batched_replicas_match_serial_path(cuda_device, tmp_path):
+    """One engine launch for all replicas (blockIdx.y) == the reference's serial loop over replicas."""
+    a, _, _ = _lj_replicas(4, 25, tmp_path, batched=True)
+    b, _, _ = _lj_replicas(4, 25, tmp_path, batched=False)
+    a.run(2)
+    b.run(2)
+    assert a._batched and not b._batched
+    for sa, sb in zip(a.sampler_states, b.sampler_states):
+        xa, xb = sa.positions.cpu().numpy(), sb.positions.cpu().numpy()
+        assert np.allclose(xa, xb, atol=2e-5)
+        assert np.allclose(sa.velocities.cpu().numpy(), sb.velocities.cpu().numpy(), atol=2e-4)
+    assert np.allclose(a._energy_thermodynamic_states, b._energy_thermodynamic_states, rtol=1e-5)
+
+
+def test_replica_exchange_energy_matrix_and_swaps(cuda_device, tmp_path):
+    from chiron_b200 import unit
+    ms, pot, temps = _lj_replicas(6, 20, tmp_path, batched=True, exchange="neighbors")
+    ms.run(6)
+    states = ms._replica_thermodynamic_states
+    assert sorted(states.tolist()) == list(range(6))                 # one replica per state, always
+    # u[r, k] = U_r / (R T_k): the matrix the swaps used equals a direct energy evaluation
+    R = 8.314462618e-3
+    for r, st in enumerate(ms.sampler_states):
+        nl = ms._nbr_lists[r]
+        nl.build(st.positions, st.box_vectors)
+        U = float(pot.compute_energy(st.positions, nl))
+        assert np.allclose(ms._energy_thermodynamic_states[r], [U / (R * t) for t in temps], rtol=2e-5)
+    u = ms._reporter.get_property("u_kn")
+    assert u.shape == (7, 6, 6)
+    idx = ms._reporter.get_property("state_index")
+    assert idx.shape == (7, 6) and any(not np.array_equal(idx[0], row) for row in idx[1:])   # something swapped

@@ -101,3 +101,16 @@ def test_langevin_lj_matches_numpy_oracle():
     assert np.array_equal(key_o, key_c)
     assert np.allclose(xo, xc, atol=2e-6) and np.allclose(vo, vc, rtol=1e-4, atol=1e-5)
     assert stats["n_builds"] == nbr.n_builds
+
+
+def test_cell_grid_accelerator_gives_the_reference_arrays():
+    x, box = lattice(12, seed=9)                       # 1728 particles, 4 cells per edge
+    x = x + np.float32(30.0) * (np.arange(x.shape[0])[:, None] % 3 == 0)   # some particles outside [0, L)
+    cps = np.float32(1.02 + 0.3)
+    a = cport.build_rows(x, box, cps, 80)
+    b = cport.build_cells(x, box, cps, 80)
+    assert a[3] == b[3]
+    for u, v in zip(a[:3], b[:3]):
+        assert np.array_equal(u, v)
+    t, tests = cport.time_reference_build_rows(x, box, cps, stride=7)
+    assert tests == sum(x.shape[0] - i - 1 for i in range(0, x.shape[0], 7)) and t >= 0.0
