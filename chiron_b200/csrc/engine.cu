@@ -36,7 +36,8 @@
 #define HALT_NONE 0x7f7f7f7f  // "no halt" value of MdRep::halt
 
 struct MdRep {            // per replica control block
-    uint32_t key[2][2];   // loop key, double buffered by step parity
+    uint32_t key[2][2];   // loop key of step s in key[s & 1] (integrators.py:179), written two steps ahead
+    uint32_t sub[2][2];   // subkey of step s (the noise key) in sub[s & 1], written one step ahead
     int user_step;        // last step at which the reference rebuild condition fired
     int user_rebuilds;
     float kT;
@@ -585,6 +586,7 @@ k_md_cand(const float4* __restrict__ xs_all, const int2* __restrict__ range_all,
 // k_md_emit turns that into the tile words.
 // ---------------------------------------------------------------------------------------------
 #define TILE_SLOTS 31
+#define TILE_PAD 4                    // tiles allocated past tcap per block (force-kernel look-ahead)
 #define DEAL_Q 8                      // lanes that share one block in k_md_deal
 #define DEAL_BPC (128 / DEAL_Q)       // blocks per CTA
 
@@ -701,7 +703,7 @@ k_md_emit(const uint32_t* __restrict__ cand_idx_all, const uint32_t* __restrict_
     const uint16_t* memb = memb_all + rb * (size_t)tcap * 32;
     const uint16_t* tmeta = tmeta_all + rb * (size_t)tcap;
     const int tstride = 32 * (1 + lw);
-    uint32_t* tiles = tiles_all + rb * (size_t)(tcap + 2) * tstride;   // two pad tiles per block
+    uint32_t* tiles = tiles_all + rb * (size_t)(tcap + TILE_PAD) * tstride;   // two pad tiles per block
     const int T = ntiles_all[rb];
     const uint32_t filler = (uint32_t)r * (uint32_t)g.np + (uint32_t)(b * 32);
     unsigned long long slots = 0;
@@ -765,6 +767,9 @@ struct LjConst {
 #ifndef CHX_FW
 #define CHX_FW 1
 #endif
+#ifndef CHX_TILE_PREFETCH
+#define CHX_TILE_PREFETCH 1
+#endif
 #ifndef CHX_TRIP_UNROLL
 #define CHX_TRIP_UNROLL 1
 #endif
@@ -787,7 +792,7 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
                                              float& fx, float& fy, float& fz, float& e_acc, unsigned& npair) {
     // software pipeline over the tiles: index/list words are fetched two tiles ahead and the j
     // positions one tile ahead, so the L2/HBM latency of a tile hides behind the previous one.
-    // The table of a block is padded by two tiles, so the look-ahead never needs clamping.
+    // The table of a block is padded by TILE_PAD tiles, so the look-ahead never needs clamping.
     if (nt <= 0) return;
     const float INF = __int_as_float(0x7f800000);
     const float FAR = 1.0e18f;
@@ -798,6 +803,10 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
     pf += tstride;
     uint32_t code_nn = pf[0], la_nn = pf[32], lb_nn = pf[64];
     pf += tstride;
+#if CHX_TILE_PREFETCH
+    const int nlines = tstride >> 5;            // 128-byte lines per tile
+    if (lane < nlines) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 32 * lane));
+#endif
     // packed accumulators (partner 0 / partner 1 of a trip), folded into fx, fy, fz at the end
     float2 fx2 = make_float2(0.f, 0.f), fy2 = fx2, fz2 = fx2, e2 = fx2;
     const float2 xix = make_float2(xi.x, xi.x), xiy = make_float2(xi.y, xi.y), xiz = make_float2(xi.z, xi.z);
@@ -815,6 +824,11 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
         xj_n = xs[code_n & 0xffffffu];
         code_nn = pf[0]; la_nn = pf[32]; lb_nn = pf[64];
         pf += tstride;
+#if CHX_TILE_PREFETCH
+        // the tables are streamed from HBM once per step: pull the lines of the tile after next into
+        // L1 now (no register, no scoreboard), so the register loads above find them on chip
+        if (lane < nlines) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 32 * lane));
+#endif
         const int trips = (int)(__shfl_sync(FULL, code, 31) >> 24);
         if (!GEN) {
             // positions are wrapped every step (integrators.py:239), so a particle may have jumped
@@ -975,7 +989,7 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
             refu_all[(size_t)r * g.np + i] = xi0;
             if (b == 0 && lane == 0) rep[r].user_rebuilds++;
         }
-        const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * (size_t)(tcap + 2) * tstride;
+        const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * (size_t)(tcap + TILE_PAD) * tstride;
         const bool lw2 = tstride == 96;
         const int nt = ntiles_all[(size_t)r * g.nblk + b];
         const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
@@ -1023,18 +1037,19 @@ k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float
            const float4* __restrict__ refi_all, const float4* __restrict__ refu_all, MdGeom g,
            float h, float a, float b, float half_skin_user, float half_skin_int2, int step_arg,
            const int* __restrict__ step_base, MdRep* __restrict__ rep) {
-    __shared__ uint32_t sk[2];
     const int r = blockIdx.y;
     const int step = step_arg + (step_base ? *step_base : 0);
     // a halt raised by ANOTHER block of this same launch (halt == step) must not stop us
     if (!(rep[r].lo <= step && step <= *((volatile int*)&rep[r].halt))) return;
-    if (threadIdx.x == 0) {
+    // the noise key of this step was prepared by the previous launch; one thread prepares the next:
+    // (key(s+2), subkey(s+1)) = split(key(s+1)) -- nobody in this launch reads the slots it writes
+    const uint32_t sk0 = rep[r].sub[step & 1][0], sk1 = rep[r].sub[step & 1][1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         uint32_t c0, c1, s0, s1;
-        threefry_split(rep[r].key[step & 1][0], rep[r].key[step & 1][1], c0, c1, s0, s1);
-        sk[0] = s0; sk[1] = s1;
-        if (blockIdx.x == 0) { rep[r].key[(step + 1) & 1][0] = c0; rep[r].key[(step + 1) & 1][1] = c1; }
+        threefry_split(rep[r].key[(step + 1) & 1][0], rep[r].key[(step + 1) & 1][1], c0, c1, s0, s1);
+        rep[r].key[step & 1][0] = c0; rep[r].key[step & 1][1] = c1;
+        rep[r].sub[(step + 1) & 1][0] = s0; rep[r].sub[(step + 1) & 1][1] = s1;
     }
-    __syncthreads();
     const int trailing = step > 0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool moved_int = false, moved_user = false;
@@ -1049,7 +1064,7 @@ k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float
             const float kT = rep[r].kT;
             const float bs = __fmul_rn(b, __fsqrt_rn(__fdiv_rn(kT, m)));
             const unsigned long long total = 3ull * (unsigned long long)g.n;
-            const uint32_t k0 = sk[0], k1 = sk[1];
+            const uint32_t k0 = sk0, k1 = sk1;
             float xc[3] = {x.x, x.y, x.z}, vc[3] = {v.x, v.y, v.z};
             const float fc[3] = {f.x, f.y, f.z};
             const float L[3] = {g.box.lx, g.box.ly, g.box.lz};
@@ -1080,11 +1095,11 @@ k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float
             moved_int = dx * dx + dy * dy + dz * dz >= half_skin_int2;
         }
     }
-    const int any_int = __syncthreads_or(moved_int);
-    const int any_user = __syncthreads_or(moved_user);
-    if (threadIdx.x == 0) {
-        if (any_int) atomicMin(&rep[r].halt, step);
-        if (any_user) rep[r].user_step = step;
+    // rare events (a rebuild every few dozen steps): warp vote, then straight to the control block
+    const unsigned ev = __reduce_or_sync(FULL, (moved_int ? 1u : 0u) | (moved_user ? 2u : 0u));
+    if ((threadIdx.x & 31) == 0 && ev) {
+        if (ev & 1u) atomicMin(&rep[r].halt, step);
+        if (ev & 2u) rep[r].user_step = step;
     }
 }
 
@@ -1115,9 +1130,9 @@ __global__ void k_md_kick(float4* __restrict__ vs_all, const float4* __restrict_
 // ---------------------------------------------------------------------------------------------
 static inline int md_tstride(const chx_ljmd* md) { return 32 * (1 + md->lw); }
 static inline int md_ccap(const chx_ljmd* md) { return md->tcap * TILE_SLOTS; }
-// tiles of a block: tcap + 2 (the force kernel's look-ahead reads up to two tiles past the last one)
+// tiles of a block: tcap + TILE_PAD (the force kernel's look-ahead reads past the last tile)
 static inline size_t md_tiles_bytes(const chx_ljmd* md) {
-    return (size_t)md->R * md->g.nblk * (md->tcap + 2) * md_tstride(md) * sizeof(uint32_t);
+    return (size_t)md->R * md->g.nblk * (md->tcap + TILE_PAD) * md_tstride(md) * sizeof(uint32_t);
 }
 
 static int md_alloc(chx_ljmd* md) {
@@ -1449,6 +1464,7 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
         MdRep& q = md->rep_host[r];
         q.key[0][0] = keys_host[2 * r];
         q.key[0][1] = keys_host[2 * r + 1];
+        threefry_split(q.key[0][0], q.key[0][1], q.key[1][0], q.key[1][1], q.sub[0][0], q.sub[0][1]);
         q.user_step = -1;
         q.lo = 0; q.halt = HALT_NONE; q.flag = 0; q.redo_step = -2;
     }
