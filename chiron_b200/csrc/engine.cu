@@ -66,7 +66,7 @@ struct chx_ljmd {
     MdGeom g;
     int R;
     float4 *xs, *vs, *refu, *fs, *refi;
-    float4 *xs_t, *vs_t, *ru_t;      // gather targets of the sort
+    float4 *xs_t, *vs_t, *ru_t, *fs_t;   // gather targets of the sort
     int *lin2h, *h2lin;              // Hilbert rank of a cell / its inverse
     int *cell_count, *cell_start, *cell_of, *order;
     int2* cell_range;                // per (x,y,z)-linear cell: [begin, end) in sorted order
@@ -84,10 +84,11 @@ struct chx_ljmd {
     float internal_skin;
     long long rebuilds, steps, launches0;
     bool have_state;
+    bool tables_fresh;               // the tables were built and no step has run since
     int* step_base;                  // device int: first step of the chunk a graph replay runs
     cudaStream_t cap_stream;
     cudaGraphExec_t chunk_graph;     // CH x (BAOAB, force) captured once; re-captured when the table shape changes
-    int chunk_graph_tcap, chunk_graph_lw;
+    int chunk_graph_tcap, chunk_graph_lw, chunk_graph_ch;
     bool no_graph;                   // CHX_MD_NOGRAPH=1: launch every kernel directly
 };
 
@@ -312,8 +313,9 @@ __global__ void k_md_cellsort(const float4* __restrict__ xs, MdGeom g, const int
 
 __global__ void k_md_gather(const int* __restrict__ order, MdGeom g, const MdRep* __restrict__ rep,
                             const float4* __restrict__ xs0, const float4* __restrict__ vs0,
-                            const float4* __restrict__ ru0, float4* __restrict__ xs1,
-                            float4* __restrict__ vs1, float4* __restrict__ ru1) {
+                            const float4* __restrict__ ru0, const float4* __restrict__ fs0,
+                            float4* __restrict__ xs1, float4* __restrict__ vs1, float4* __restrict__ ru1,
+                            float4* __restrict__ fs1) {
     const int r = blockIdx.y;
     if (!rep[r].flag) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -322,24 +324,25 @@ __global__ void k_md_gather(const int* __restrict__ order, MdGeom g, const MdRep
     if (p >= g.n) {
         const float4 pad = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         xs1[o] = pad; vs1[o] = make_float4(0.f, 0.f, 0.f, 1.f); ru1[o] = pad;
+        fs1[o] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
     const size_t q = (size_t)r * g.np + order[o];
-    xs1[o] = xs0[q]; vs1[o] = vs0[q]; ru1[o] = ru0[q];
+    xs1[o] = xs0[q]; vs1[o] = vs0[q]; ru1[o] = ru0[q]; fs1[o] = fs0[q];
 }
 
 // copy the gathered arrays back over the live ones (and take the rebuild reference positions)
 __global__ void k_md_adopt(MdGeom g, const MdRep* __restrict__ rep, const float4* __restrict__ xs1,
                            const float4* __restrict__ vs1, const float4* __restrict__ ru1,
-                           float4* __restrict__ xs, float4* __restrict__ vs, float4* __restrict__ ru,
-                           float4* __restrict__ refi) {
+                           const float4* __restrict__ fs1, float4* __restrict__ xs, float4* __restrict__ vs,
+                           float4* __restrict__ ru, float4* __restrict__ fs, float4* __restrict__ refi) {
     const int r = blockIdx.y;
     if (!rep[r].flag) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= g.np) return;
     const size_t o = (size_t)r * g.np + p;
     const float4 a = xs1[o];
-    xs[o] = a; refi[o] = a; vs[o] = vs1[o]; ru[o] = ru1[o];
+    xs[o] = a; refi[o] = a; vs[o] = vs1[o]; ru[o] = ru1[o]; fs[o] = fs1[o];
 }
 
 // replicas whose tables are rebuilt without a sort (capacity regrow, flag bit 1): the positions the
@@ -622,6 +625,55 @@ k_md_deal(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ can
     if (ovf) T = tcap;
     const int Kw = __reduce_max_sync(FULL, K);
     uint32_t c_next = K > 0 ? in_col[0] : 0u;
+    // Fast path: at most 3 tiles per lane (T <= 24 for every block of the warp, no room to grow
+    // needed beyond that): the per-tile state lives in registers and the scan is straight-line code.
+    const bool fast = __reduce_max_sync(FULL, T) <= 3 * DEAL_Q - 3 && tcap >= 3 * DEAL_Q;
+    if (fast) {
+        uint32_t at0 = 0xffffffffu, at1 = 0xffffffffu, at2 = 0xffffffffu;   // tiles w, w + 8, w + 16
+        uint32_t cs0 = 0u, cs1 = 0u, cs2 = 0u;                               // max << 8 | fill
+        for (int q = 0; q < Kw; ++q) {
+            const bool active = q < K && !ovf;
+            const uint32_t c = c_next;
+            if (q + 1 < K) c_next = in_col[q + 1];
+            uint32_t best;
+            bool again;
+            do {
+#define DEAL_KEY(AT, CS, TI)                                                                              \
+                ({ const uint32_t nm_ = ((CS) >> 8) + ((c & (AT)) != 0u ? 1u : 0u);                            \
+                   ((TI) < T && ((CS) & 0xffu) < TILE_SLOTS && nm_ <= (uint32_t)cap)                          \
+                       ? (nm_ << 18 | ((CS) & 0xffu) << 12 | (uint32_t)(TI)) : 0xffffffffu; })
+                best = min(min(DEAL_KEY(at0, cs0, w), DEAL_KEY(at1, cs1, w + DEAL_Q)), DEAL_KEY(at2, cs2, w + 2 * DEAL_Q));
+#undef DEAL_KEY
+#pragma unroll
+                for (int o = 1; o < DEAL_Q; o <<= 1) best = min(best, __shfl_xor_sync(FULL, best, o));
+                again = false;
+                if (active && best == 0xffffffffu) {
+                    if (T < 3 * DEAL_Q && T < tcap) { ++T; again = true; }   // open one more tile
+                    else ovf = true;
+                }
+            } while (__any_sync(FULL, again));
+            const bool place = active && !ovf;
+            const int tw = place ? (int)(best & 0xfffu) : 0, slot = (int)((best >> 12) & 0x3fu);
+            const uint32_t newmax = best >> 18;
+            const uint32_t b4 = place ? (c >> (4 * w)) & 0xfu : 0u;
+            const uint32_t cc = cnt[tw * DEAL_Q] + ((b4 * 0x00204081u) & 0x01010101u);
+            if (place) cnt[tw * DEAL_Q] = cc;
+            uint32_t z = cc ^ (newmax * 0x01010101u);
+            z = ~(((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z | 0x7f7f7f7fu);
+            uint32_t eq = ((((z >> 7) * 0x00204081u) >> 21) & 0xfu) << (4 * w);
+#pragma unroll
+            for (int o = 1; o < DEAL_Q; o <<= 1) eq |= __shfl_xor_sync(FULL, eq, o);
+            if (place) {
+                const uint32_t ncs = newmax << 8 | (uint32_t)(slot + 1);
+                if (tw == w) { at0 = eq; cs0 = ncs; }
+                if (tw == w + DEAL_Q) { at1 = eq; cs1 = ncs; }
+                if (tw == w + 2 * DEAL_Q) { at2 = eq; cs2 = ncs; }
+                if (w == 0) memb[tw * 32 + slot] = (uint16_t)q;
+            }
+            __syncwarp();
+        }
+        cs[w] = cs0; cs[w + DEAL_Q] = cs1; cs[w + 2 * DEAL_Q] = cs2;
+    } else
     for (int q = 0; q < Kw; ++q) {
         const bool active = q < K && !ovf;
         const uint32_t c = c_next;
@@ -1143,6 +1195,7 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->xs_t, np * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->vs_t, np * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->ru_t, np * sizeof(float4)));
+    CHX_CUDA(cudaMalloc(&md->fs_t, np * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->fs, np * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->refi, np * sizeof(float4)));
     const int ncell = md->g.ncell;
@@ -1239,9 +1292,11 @@ static int md_rebuild(chx_ljmd* md) {
     k_md_cellsort<<<dim3(chx_div_up(g.ncell, 128), R), 128, 0, st>>>(md->xs, g, md->cell_start, md->rep,
                                                                      md->cell_count, md->order);
     CHX_LAUNCHED(ctx);
-    k_md_gather<<<gp, 256, 0, st>>>(md->order, g, md->rep, md->xs, md->vs, md->refu, md->xs_t, md->vs_t, md->ru_t);
+    k_md_gather<<<gp, 256, 0, st>>>(md->order, g, md->rep, md->xs, md->vs, md->refu, md->fs, md->xs_t, md->vs_t,
+                                    md->ru_t, md->fs_t);
     CHX_LAUNCHED(ctx);
-    k_md_adopt<<<gp, 256, 0, st>>>(g, md->rep, md->xs_t, md->vs_t, md->ru_t, md->xs, md->vs, md->refu, md->refi);
+    k_md_adopt<<<gp, 256, 0, st>>>(g, md->rep, md->xs_t, md->vs_t, md->ru_t, md->fs_t, md->xs, md->vs, md->refu,
+                                   md->fs, md->refi);
     CHX_LAUNCHED(ctx);
     const float R_list = md->p.cutoff + md->internal_skin;
     bool regrown = false;
@@ -1392,7 +1447,7 @@ int chx_ljmd_destroy(chx_ljmd* md) {
     if (!md) return CHX_OK;
     cudaStreamSynchronize(md->ctx->stream);
     cudaFree(md->xs); cudaFree(md->vs); cudaFree(md->refu); cudaFree(md->xs_t); cudaFree(md->vs_t);
-    cudaFree(md->ru_t); cudaFree(md->fs); cudaFree(md->refi); cudaFree(md->cell_count);
+    cudaFree(md->ru_t); cudaFree(md->fs_t); cudaFree(md->fs); cudaFree(md->refi); cudaFree(md->cell_count);
     cudaFree(md->cell_start); cudaFree(md->cell_range); cudaFree(md->lin2h); cudaFree(md->h2lin);
     cudaFree(md->cell_of); cudaFree(md->order); cudaFree(md->tiles); cudaFree(md->ntiles);
     cudaFree(md->cand_idx); cudaFree(md->cand_col); cudaFree(md->cand_n); cudaFree(md->memb); cudaFree(md->tmeta);
@@ -1429,6 +1484,7 @@ int chx_ljmd_set_state(chx_ljmd* md, const float* x, const float* v, const float
     rc = md_force(md, FMODE_ALL, -2, false, 0, nullptr);
     if (rc != CHX_OK) return rc;
     md->have_state = true;
+    md->tables_fresh = true;
     return CHX_OK;
 }
 
@@ -1481,7 +1537,8 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     const float hs_int = 0.5f * md->internal_skin;
     const float hs_int2 = hs_int * hs_int;
     const dim3 gb(chx_div_up(g.np, 256), R);
-    const int CH = 32;
+    int CH = 32;   // steps per graph replay / host check (CHX_MD_CHUNK overrides)
+    { const char* e = getenv("CHX_MD_CHUNK"); if (e && atoi(e) > 0) CH = atoi(e); }
 
     auto launch_steps = [&](int s0, int s1, const int* base) -> int {
         for (int s = s0; s < s1; ++s) {
@@ -1498,7 +1555,7 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     // read the chunk's first step from device memory, so the same graph serves every chunk
     const bool use_graph = !report && !md->no_graph;
     auto launch_chunk_graph = [&](int s0) -> int {
-        if (md->chunk_graph && (md->chunk_graph_tcap != md->tcap || md->chunk_graph_lw != md->lw)) {
+        if (md->chunk_graph && (md->chunk_graph_tcap != md->tcap || md->chunk_graph_lw != md->lw || md->chunk_graph_ch != CH)) {
             cudaGraphExecDestroy(md->chunk_graph);
             md->chunk_graph = nullptr;
         }
@@ -1520,6 +1577,7 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
             CHX_CUDA(cudaGraphDestroy(graph));
             md->chunk_graph_tcap = md->tcap;
             md->chunk_graph_lw = md->lw;
+            md->chunk_graph_ch = CH;
         }
         k_md_setbase<<<1, 1, 0, st>>>(md->step_base, s0);
         CHX_LAUNCHED(ctx);
@@ -1528,9 +1586,29 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
         return CHX_OK;
     };
 
+    // Batched replicas go stale at different steps; waiting for each other inside a chunk and then
+    // catching up one by one costs more than the tables themselves.  So with R > 1 every chunk starts
+    // on fresh tables for all replicas (forces are carried through the sort, nothing is re-evaluated),
+    // and a halt inside a chunk becomes the exception.  CHX_MD_PROACTIVE=0 disables it.
+    bool proactive = R > 1;
+    { const char* e = getenv("CHX_MD_PROACTIVE"); if (e) proactive = e[0] == '1'; }
     int t = 0;
     while (t < nsteps) {
         const int te = nsteps - t < CH ? nsteps : t + CH;
+        if (proactive && !(t == 0 && md->tables_fresh)) {
+            for (int r = 0; r < R; ++r) {
+                MdRep& q = md->rep_host[r];
+                q.flag = 1; q.overflow = 0; q.cand_pairs2 = 0; q.trip_slots = 0;
+            }
+            rc = md_upload_rep(md);
+            if (rc != CHX_OK) return rc;
+            rc = md_rebuild(md);
+            if (rc != CHX_OK) return rc;
+            for (int r = 0; r < R; ++r) md->rep_host[r].flag = 0;
+            rc = md_upload_rep(md);
+            if (rc != CHX_OK) return rc;
+        }
+        md->tables_fresh = false;
         rc = (use_graph && te - t == CH) ? launch_chunk_graph(t) : launch_steps(t, te, nullptr);
         if (rc != CHX_OK) return rc;
         rc = md_download_rep(md);

@@ -507,6 +507,8 @@ class _BatchedLJReplicas:
         self.box = box
         self.volume = float(box[0] * box[1] * box[2])
         self._dirty = False
+        self._beta_mol = None
+        self._beta_pv = None
 
     def propagate(self, n_mcmc_iterations: int):
         """`MCMCSampler.run` x n_iterations of the single LangevinDynamicsMove for every local replica:
@@ -535,17 +537,16 @@ class _BatchedLJReplicas:
             self._dirty = True
 
     def reduced_potentials(self) -> np.ndarray:
-        """(n_local, K): u_kl = beta_l (U_k + p_l V) from one batched energy kernel."""
-        ms = self.ms
+        """(n_local, K): u_kl = beta_l (U_k + p_l V) from one batched energy kernel
+        (`states.py:302-325` evaluated for all states at once)."""
         U = self.engine.energy().cpu().numpy()               # kJ/mol per local replica
-        K = ms.number_of_thermodynamic_states
-        rows = np.zeros((self.hi - self.lo, K))
-        for l, ts in enumerate(ms._thermodynamic_states):
-            red = unit.Quantity(U, unit.kilojoule_per_mole) / unit.AVOGADRO_CONSTANT_NA
-            if ts.pressure is not None:
-                red = red + ts.pressure * (self.volume * unit.nanometer ** 3)
-            rows[:, l] = np.asarray(ts.beta * red, dtype=np.float64)
-        return rows
+        if self._beta_mol is None:
+            ms = self.ms
+            one = unit.Quantity(1.0, unit.kilojoule_per_mole) / unit.AVOGADRO_CONSTANT_NA
+            self._beta_mol = np.array([float(ts.beta * one) for ts in ms._thermodynamic_states])
+            self._beta_pv = np.array([float(ts.beta * (ts.pressure * (self.volume * unit.nanometer ** 3)))
+                                      if ts.pressure is not None else 0.0 for ts in ms._thermodynamic_states])
+        return U[:, None] * self._beta_mol[None, :] + self._beta_pv[None, :]
 
     def set_states(self, new_states, velocity_scales: dict):
         kts = [self.kT_of_state[new_states[r]] for r in range(self.lo, self.hi)]

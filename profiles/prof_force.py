@@ -23,8 +23,9 @@ def main(n_side=64, steps=0, repeats=6):
     lj, x, box = bench.make_system(n_side, seed=4)
     n = x.shape[0]
     kT = kT_md(bench.TEMP_K * unit.kelvin)
+    skin_int = float(os.environ["INTERNAL_SKIN"]) if "INTERNAL_SKIN" in os.environ else None
     eng = LJLangevinEngine(n, np.diag(box), bench.SIGMA, bench.EPS, bench.RC, bench.SKIN, bench.DT_PS,
-                           bench.GAMMA, kT, device=dev)
+                           bench.GAMMA, kT, internal_skin=skin_int, device=dev)
     v0 = initialize_velocities(bench.TEMP_K * unit.kelvin, lj.topology, crandom.PRNGKey(11))
     v0 = v0.value_in_unit_system(unit.md_unit_system).cpu().numpy()
     eng.set_state(x, v0, np.full(n, bench.MASS, np.float32), [kT])

@@ -1,0 +1,96 @@
+"""Statistical checks on long runs (BASELINE.json: equipartition, <U> and Metropolis acceptance within
+3 sigma).  Each test states its tolerance; sigma comes from the data (block averages) or from the
+binomial / chi-square law of the estimator."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dynamics as dyn, potentials as pot
+
+pytestmark = pytest.mark.gpu
+R_GAS = 8.314462618e-3     # kJ/mol/K
+
+
+def _setup(n_side, seed, skin=0.4, builder="cell"):
+    from chiron_b200 import unit
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import LennardJonesFluid
+    from chiron_b200.utils import PRNG
+    lj = LennardJonesFluid(nparticles=n_side ** 3, reduced_density=0.8, seed=seed)
+    potential = LJPotential(lj.topology, lj.sigma, lj.epsilon, 1.02 * unit.nanometer)
+    PRNG.set_seed(seed)
+    state = SamplerState(lj.positions, PRNG.get_random_key(), box_vectors=lj.box_vectors)
+    ts = ThermodynamicState(potential, temperature=300 * unit.kelvin)
+    nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.02 * unit.nanometer, skin=skin * unit.nanometer,
+                           n_max_neighbors=200, builder=builder)
+    return lj, potential, state, ts, nl
+
+
+def _sample(integ, state, ts, nl, potential, n_samples, stride):
+    T, U = [], []
+    for _ in range(n_samples):
+        state, nl = integ.run(state, ts, number_of_steps=stride, nbr_list=nl)
+        v = state.velocities.double()
+        n = v.shape[0]
+        T.append(float((39.948 * (v * v).sum()) / (3.0 * n * R_GAS)))
+        nl.build_from_state(state)
+        U.append(float(potential.compute_energy(state.positions, nl)) / n)
+    return np.array(T), np.array(U), state, nl
+
+
+def test_equipartition_and_mean_energy_fused_vs_blocks(cuda_device):
+    """LJ argon N=4096, rho*=0.8, 300 K, dt=2 fs.  (i) kinetic temperature of the fused engine = 300 K within
+    3 sigma (sigma from the chi-square law of 3N velocity components and the number of samples, plus the
+    O(dt^2) BAOAB bias allowance of 0.5 K); (ii) <U>/N of the fused engine and of the building-block path
+    (different kernels, same physics) agree within 3 sigma of their block-average errors."""
+    from chiron_b200 import unit
+    from chiron_b200.integrators import LangevinIntegrator
+    res = {}
+    for fused, n_samples, stride in ((True, 40, 100), (False, 16, 100)):
+        lj, potential, state, ts, nl = _setup(16, seed=5 if fused else 6)
+        integ = LangevinIntegrator(timestep=2.0 * unit.femtosecond, collision_rate=5.0 / unit.picosecond)
+        integ.use_fused_engine = fused
+        state, nl = integ.run(state, ts, number_of_steps=1500, nbr_list=nl)     # melt the lattice, equilibrate
+        T, U, state, nl = _sample(integ, state, ts, nl, potential, n_samples, stride)
+        res[fused] = (T, U)
+    T, U = res[True]
+    n = 4096
+    sigma_T = 300.0 * np.sqrt(2.0 / (3 * n)) / np.sqrt(len(T))      # independent samples (stride >> 1/gamma)
+    assert abs(T.mean() - 300.0) < 3.0 * sigma_T + 0.5, (T.mean(), sigma_T)
+    Tb, Ub = res[False]
+    assert abs(Tb.mean() - 300.0) < 3.0 * 300.0 * np.sqrt(2.0 / (3 * n)) / np.sqrt(len(Tb)) + 0.5
+    err = np.sqrt(U.var(ddof=1) / len(U) + Ub.var(ddof=1) / len(Ub))
+    assert abs(U.mean() - Ub.mean()) < 3.0 * err * 1.5, (U.mean(), Ub.mean(), err)   # 1.5: residual correlation
+    assert -6.5 < U.mean() < -4.0          # kJ/mol per particle: liquid argon at this state point
+
+
+def test_metropolis_acceptance_matches_oracle_statistics(cuda_device):
+    """All-particle displacement moves on LJ N=216: the acceptance ratio of the GPU path (seed A) and of the
+    CPU oracle (seed B) are two estimates of the same probability: |p1 - p2| < 3 sqrt(p(1-p)(1/n1 + 1/n2))."""
+    from chiron_b200 import unit
+    from chiron_b200.mcmc import MonteCarloDisplacementMove
+    from chiron_b200.utils import PRNG
+    lj, potential, state, ts, nl = _setup(6, seed=11, skin=0.5, builder="nsq")
+    nl.build_from_state(state)
+    n_gpu = 400
+    move = MonteCarloDisplacementMove(displacement_sigma=0.0006 * unit.nanometer, number_of_moves=n_gpu)
+    move.update(state, ts, nl)
+    p_gpu = move.statistics["n_accepted"] / n_gpu
+    x = np.asarray(lj.positions.value_in_unit(unit.nanometer), dtype=np.float32)
+    box = np.asarray(lj.box_vectors.value_in_unit(unit.nanometer), dtype=np.float32)
+    sigma, eps, rc = 0.34, 0.238 * 4.184, 1.02
+    nbr = dyn.OracleNeighborList(box, rc, 0.5, 200)
+    nbr.build(x)
+    st = dyn.KeyedState(next(dyn.prng_stream(987)))
+    red = lambda xx, b: dyn.reduced_potential(  # noqa: E731
+        pot.lj_energy_nlist(xx, box, sigma, eps, rc, nbr.neighbor_list, nbr.neighbor_mask), 300.0)
+    xo, u, acc, n_cpu = x, red(x, box), 0, 150
+    for _ in range(n_cpu):
+        xo, u, a = dyn.mc_displacement_step(xo, box, st, 0.0006, u, red, nbr=nbr)
+        acc += a
+    p_cpu = acc / n_cpu
+    p = (move.statistics["n_accepted"] + acc) / (n_gpu + n_cpu)
+    assert 0.1 < p < 0.9, p
+    assert abs(p_gpu - p_cpu) < 3.0 * np.sqrt(p * (1 - p) * (1.0 / n_gpu + 1.0 / n_cpu)), (p_gpu, p_cpu)
