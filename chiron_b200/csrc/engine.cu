@@ -89,6 +89,12 @@ struct chx_ljmd {
     cudaStream_t cap_stream;
     cudaGraphExec_t chunk_graph;     // CH x (BAOAB, force) captured once; re-captured when the table shape changes
     int chunk_graph_tcap, chunk_graph_lw, chunk_graph_ch;
+    // single-system runs: one graph with a device-side WHILE node, body = (BAOAB, force, loop control);
+    // the loop leaves when the run is complete or the tables went stale, no launch is ever wasted
+    cudaGraphExec_t while_graph;
+    int while_graph_tcap, while_graph_lw;
+    int* loop_end;                   // device int: first step the WHILE loop must not execute
+    bool use_while;
     bool no_graph;                   // CHX_MD_NOGRAPH=1: launch every kernel directly
 };
 
@@ -1156,6 +1162,17 @@ k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float
 }
 
 __global__ void k_md_setbase(int* base, int value) { *base = value; }
+__global__ void k_md_setloop(int* base, int* end, int first, int last) { *base = first; *end = last; }
+
+// last kernel of the WHILE body (single replica): advance the step, go on while the run is not
+// complete and the tables are still valid
+__global__ void k_md_loopctl(cudaGraphConditionalHandle handle, int* __restrict__ base,
+                             const int* __restrict__ end, const MdRep* __restrict__ rep) {
+    const int s = *base + 1;
+    *base = s;
+    const bool go = s < *end && *((volatile const int*)&rep[0].halt) == HALT_NONE;
+    cudaGraphSetConditional(handle, go ? 1u : 0u);
+}
 
 __global__ void k_md_scale_v(float4* __restrict__ vs, int np, float sc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1221,6 +1238,8 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->rep, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMalloc(&md->step_base, sizeof(int)));
     md->chunk_graph = nullptr; md->chunk_graph_tcap = -1; md->chunk_graph_lw = -1; md->cap_stream = nullptr;
+    md->while_graph = nullptr; md->while_graph_tcap = -1; md->while_graph_lw = -1;
+    CHX_CUDA(cudaMalloc(&md->loop_end, sizeof(int)));
     CHX_CUDA(cudaMallocHost(&md->rep_host, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMemset(md->rep, 0, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMemset(md->fs, 0, np * sizeof(float4)));
@@ -1436,6 +1455,7 @@ int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
     md->qcap = ((int)(2.5 * cand) + 256 + 31) & ~31;
     md->rebuilds = 0; md->steps = 0; md->have_state = false;
     { const char* e = getenv("CHX_MD_NOGRAPH"); md->no_graph = e && e[0] == '1'; }
+    { const char* e = getenv("CHX_MD_WHILE"); md->use_while = e ? e[0] == '1' : false; }
     md->launches0 = ctx->launches;
     int rc = md_alloc(md);
     if (rc != CHX_OK) { delete md; return rc; }
@@ -1453,6 +1473,8 @@ int chx_ljmd_destroy(chx_ljmd* md) {
     cudaFree(md->cand_idx); cudaFree(md->cand_col); cudaFree(md->cand_n); cudaFree(md->memb); cudaFree(md->tmeta);
     cudaFree(md->generic); cudaFree(md->bcenter); cudaFree(md->rep); cudaFree(md->step_base);
     if (md->chunk_graph) cudaGraphExecDestroy(md->chunk_graph);
+    if (md->while_graph) cudaGraphExecDestroy(md->while_graph);
+    cudaFree(md->loop_end);
     if (md->cap_stream) cudaStreamDestroy(md->cap_stream);
     cudaFreeHost(md->rep_host);
     delete md;
@@ -1585,6 +1607,85 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
         ctx->launches += 2 * CH;
         return CHX_OK;
     };
+
+    // ---- single system, no energy reports: device-side WHILE loop ----
+    if (R == 1 && use_graph && md->use_while) {
+        auto ensure_while_graph = [&]() -> int {
+            if (md->while_graph && (md->while_graph_tcap != md->tcap || md->while_graph_lw != md->lw)) {
+                cudaGraphExecDestroy(md->while_graph);   // the graph bakes the table shape
+                md->while_graph = nullptr;
+            }
+            if (md->while_graph) return CHX_OK;
+            cudaGraph_t graph = nullptr;
+            CHX_CUDA(cudaGraphCreate(&graph, 0));
+            cudaGraphConditionalHandle handle;
+            CHX_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+            cudaGraphNodeParams np_ = {};
+            np_.type = cudaGraphNodeTypeConditional;
+            np_.conditional.handle = handle;
+            np_.conditional.type = cudaGraphCondTypeWhile;
+            np_.conditional.size = 1;
+            cudaGraphNode_t node;
+            CHX_CUDA(cudaGraphAddNode(&node, graph, nullptr, 0, &np_));
+            cudaGraph_t body = np_.conditional.phGraph_out[0];
+            if (!md->cap_stream) CHX_CUDA(cudaStreamCreateWithFlags(&md->cap_stream, cudaStreamNonBlocking));
+            const long long l0 = ctx->launches;
+            CHX_CUDA(cudaStreamBeginCaptureToGraph(md->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+            ctx->stream = md->cap_stream;
+            const int rc2 = launch_steps(0, 1, md->step_base);
+            k_md_loopctl<<<1, 1, 0, md->cap_stream>>>(handle, md->step_base, md->loop_end, md->rep);
+            ctx->stream = st;
+            cudaGraph_t captured = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(md->cap_stream, &captured);
+            ctx->launches = l0;
+            if (rc2 != CHX_OK) { cudaGraphDestroy(graph); return rc2; }
+            CHX_CUDA(ce);
+            CHX_CUDA(cudaGraphInstantiate(&md->while_graph, graph, 0));
+            CHX_CUDA(cudaGraphDestroy(graph));
+            md->while_graph_tcap = md->tcap;
+            md->while_graph_lw = md->lw;
+            return CHX_OK;
+        };
+        int t = 0;
+        while (t < nsteps) {
+            rc = ensure_while_graph();
+            if (rc != CHX_OK) return rc;
+            k_md_setloop<<<1, 1, 0, st>>>(md->step_base, md->loop_end, t, nsteps);
+            CHX_LAUNCHED(ctx);
+            CHX_CUDA(cudaGraphLaunch(md->while_graph, st));
+            rc = md_download_rep(md);
+            if (rc != CHX_OK) return rc;
+            MdRep& q = md->rep_host[0];
+            const int done = q.halt < nsteps ? q.halt + 1 : nsteps;      // steps whose BAOAB update ran
+            ctx->launches += 3ll * (done - t);
+            md->tables_fresh = false;
+            if (q.halt < nsteps) {
+                // tables went stale at step `halt`: rebuild, evaluate that step's forces, go on after it
+                q.flag = 1; q.redo_step = q.halt; q.lo = q.halt + 1; q.halt = HALT_NONE;
+                q.overflow = 0; q.cand_pairs2 = 0; q.trip_slots = 0;
+                rc = md_upload_rep(md);
+                if (rc != CHX_OK) return rc;
+                rc = md_rebuild(md);
+                if (rc != CHX_OK) return rc;
+                rc = md_force(md, FMODE_REDO, -2, false, 0, nullptr);
+                if (rc != CHX_OK) return rc;
+                rc = md_download_rep(md);      // the redo updates the reference-rebuild bookkeeping on the device
+                if (rc != CHX_OK) return rc;
+                md->rep_host[0].flag = 0;
+                rc = md_upload_rep(md);
+                if (rc != CHX_OK) return rc;
+            }
+            t = done;
+        }
+        k_md_kick<<<chx_div_up((long long)R * g.np, 256), 256, 0, st>>>(md->vs, md->fs, g, h, R);
+        CHX_LAUNCHED(ctx);
+        rc = md_download_rep(md);
+        if (rc != CHX_OK) return rc;
+        keys_host[0] = md->rep_host[0].key[nsteps & 1][0];
+        keys_host[1] = md->rep_host[0].key[nsteps & 1][1];
+        md->steps += nsteps;
+        return CHX_OK;
+    }
 
     // Batched replicas go stale at different steps; waiting for each other inside a chunk and then
     // catching up one by one costs more than the tables themselves.  So with R > 1 every chunk starts

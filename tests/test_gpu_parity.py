@@ -602,3 +602,33 @@ def test_mc_displacement_subset_delta_path(cuda_device):
     assert np.array_equal(res[0][1], res[1][1])
     moved = np.nonzero(np.any(res[0][1] != x, axis=1))[0]
     assert moved.tolist() == [5]
+
+
+def test_while_graph_loop_matches_chunked_loop(cuda_device, monkeypatch):
+    """Single-system runs can use one CUDA graph with a device-side WHILE node (body = BAOAB, force,
+    loop control) instead of replaying 32-step chunks: same launches on the same data, so positions,
+    velocities, keys and rebuild bookkeeping are bit-identical."""
+    from chiron_b200 import random as crandom
+    from chiron_b200._engine import LJLangevinEngine
+    lj_sys, x, box = _lj_system(12, 0.8, seed=91)
+    n = x.shape[0]
+    rng = np.random.default_rng(5)
+    v = rng.normal(0, 0.25, (n, 3)).astype(f32)
+    mass = np.full(n, 39.948, f32)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CHX_MD_WHILE", mode)
+        eng = LJLangevinEngine(n, np.diag(box), 0.34, 0.238 * 4.184, 1.02, 0.3, 0.002, 1.0, 2.494,
+                               internal_skin=0.05, device=cuda_device)
+        eng.set_state(x, v, mass, [2.494])
+        keys = crandom.PRNGKey(5).reshape(1, 2)
+        keys, _ = eng.run(75, keys)
+        keys, _ = eng.run(40, keys)
+        xs, vs, _, ref = eng.get_state(want_ref=True)
+        st = eng.stats()
+        out[mode] = (_np(xs), _np(vs), np.array(keys), st["table_rebuilds"], st["reference_rebuilds"], _np(ref))
+        eng.close()
+    a, b = out["0"], out["1"]
+    assert a[3] >= 3 and a[3] == b[3] and a[4] == b[4]
+    assert np.array_equal(a[2], b[2])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[5], b[5])
