@@ -122,6 +122,7 @@ def cpu_reference_steps_per_s(x, box, v0, rebuild_interval=REF_REBUILD_INTERVAL,
     number of pair tests) amortised over the rebuild interval.  The list the timed steps run on is
     built with the oracle's cell-grid accelerator (not timed: it is not part of the reference)."""
     from oracle import cport
+    cport.use_all_cores()
     n = x.shape[0]
     kT = 8.314462618e-3 * TEMP_K
     mass = np.full(n, MASS, np.float32)

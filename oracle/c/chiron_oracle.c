@@ -58,6 +58,15 @@ static inline float disp(const float* a, const float* b, const float* L, int per
     return sqrtf(s);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the baseline legs set the thread count explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -36,6 +36,7 @@ def lib():
         build()
         L = C.CDLL(LIB_PATH)
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_displacement.argtypes = [_fp, _fp, C.c_long, _fp, C.c_int, _fp, _fp]
         L.orc_wrap.argtypes = [_fp, C.c_long, _fp]
         L.orc_nlist_build_rows.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
@@ -71,6 +72,17 @@ def _f(a):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def use_all_cores():
+    """Use every core this process may run on (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(n)
+    return num_threads()
 
 
 def displacement(x1, x2, box, periodic=True):
