@@ -110,7 +110,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU baseline: the C/OpenMP restatement of the reference algorithm (oracle/c) on a bounded sample
 # ---------------------------------------------------------------------------------------------------
-REF_REBUILD_INTERVAL = 150.0   # steps between reference rebuild events (`check()` true) at this state point,
+REF_REBUILD_INTERVAL = 200.0   # steps between reference rebuild events (`check()` true) at this state point,
                                # measured by the engine's exact tracker (bench line: reference_rebuild_interval_steps)
 
 

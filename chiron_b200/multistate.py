@@ -212,36 +212,12 @@ class MultiStateSampler:
         sampler_state = self._sampler_states[replica_id]
         nbr_list = self._nbr_lists[replica_id]
         tol = float(tolerance.value_in_unit_system(unit.md_unit_system)) if isinstance(tolerance, unit.Quantity) else float(tolerance)
-        x = sampler_state.positions.clone()
-        has_ef = hasattr(potential, "compute_energy_and_force")
-
-        def energy_force(xx):
-            if has_ef:
-                try:
-                    e, f = potential.compute_energy_and_force(xx, nbr_list)
-                except TypeError:
-                    e, f = potential.compute_energy_and_force(xx)
-            else:
-                e, f = potential.compute_energy(xx, nbr_list), potential.compute_force(xx, nbr_list)
-            f = f if isinstance(f, torch.Tensor) else torch.zeros_like(xx)
-            return float(e), f
-
-        e, f = energy_force(x)
-        log.debug(f"Replica {replica_id + 1}/{self.number_of_replicas}: initial energy {e:8.3f} kJ/mol")
-        step = 1e-4
-        for _ in range(int(max_iterations)):
-            fmax = float(f.abs().max())
-            if fmax < tol:
-                break
-            x_try = x + step * f
-            e_try, f_try = energy_force(x_try)
-            if e_try <= e:
-                x, e, f = x_try, e_try, f_try
-                step *= 1.5
-            else:
-                step *= 0.25
-                if step < 1e-12:
-                    break
+        from .minimze import minimize_energy
+        e0 = float(potential.compute_energy(sampler_state.positions, nbr_list))
+        log.debug(f"Replica {replica_id + 1}/{self.number_of_replicas}: initial energy {e0:8.3f} kJ/mol")
+        result = minimize_energy(sampler_state.positions, potential.compute_energy, nbr_list,
+                                 maxiter=max_iterations, tolerance=tol)
+        x, e = result.params, result.state.get("value", float("nan"))
         self._sampler_states[replica_id].positions = unit.Quantity(x, unit.nanometer)
         if nbr_list is not None and nbr_list.check(self._sampler_states[replica_id].positions):
             nbr_list.build(self._sampler_states[replica_id].positions, self._sampler_states[replica_id].box_vectors)

@@ -141,3 +141,42 @@ def test_replica_exchange_energy_matrix_and_swaps(cuda_device, tmp_path):
     assert u.shape == (7, 6, 6)
     idx = ms._reporter.get_property("state_index")
     assert idx.shape == (7, 6) and any(not np.array_equal(idx[0], row) for row in idx[1:])   # something swapped
+
+
+def test_minimization_like_reference(cuda_device):
+    """`chiron/tests/test_minization.py`: 0 iterations leave the energy unchanged, 100 iterations lower it;
+    two particles relax to r = 2^(1/6) sigma, E = -epsilon."""
+    from chiron_b200 import unit
+    from chiron_b200.minimze import minimize_energy
+    from chiron_b200.neighbors import OrthogonalPeriodicSpace, PairListNsqrd
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.states import SamplerState
+    from chiron_b200.testsystems import LennardJonesFluid
+    from chiron_b200.utils import PRNG
+    lj = LennardJonesFluid(nparticles=216, reduced_density=0.1)
+    cutoff = unit.Quantity(1.0, unit.nanometer)
+    pot = LJPotential(lj.topology, cutoff=cutoff)
+    PRNG.set_seed(1234)
+    state = SamplerState(lj.positions, current_PRNG_key=PRNG.get_random_key(), box_vectors=lj.box_vectors)
+    nbr = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=cutoff)
+    nbr.build_from_state(state)
+    e0 = float(pot.compute_energy(state.positions, nbr))
+    e0_nolist = float(pot.compute_energy(state.positions))
+    assert not np.isclose(e0, e0_nolist)                      # periodic images matter at this density
+    r0 = minimize_energy(state.positions, pot.compute_energy, nbr, maxiter=0)
+    assert np.isclose(float(pot.compute_energy(r0.params, nbr)), e0)
+    r100 = minimize_energy(state.positions, pot.compute_energy, nbr, maxiter=100)
+    e100 = float(pot.compute_energy(r100.params, nbr))
+    assert e100 < e0 and not np.isnan(e100)
+    # two particles
+    sigma, eps = 1.0 * unit.nanometer, 1.0 * unit.kilojoules_per_mole
+    pot2 = LJPotential(None, sigma=sigma, epsilon=eps, cutoff=3.0 * sigma)
+    xy = np.array([[0.0, 0.0, 0.0], [0.9, 0.0, 0.0]], dtype=np.float32)
+    st2 = SamplerState(positions=xy * unit.nanometer, current_PRNG_key=PRNG.get_random_key(),
+                       box_vectors=np.eye(3, dtype=np.float32) * 10.0 * unit.nanometer)
+    pl = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=3.0 * sigma)
+    pl.build_from_state(st2)
+    res = minimize_energy(st2.positions, pot2.compute_energy, pl, maxiter=10_000)
+    x = res.params.cpu().numpy()
+    assert np.isclose(float(pot2.compute_energy(res.params, pl)), -1.0, atol=1e-3)
+    assert np.isclose(np.linalg.norm(x[1] - x[0]), 2 ** (1.0 / 6.0), atol=1e-3)
