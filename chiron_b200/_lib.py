@@ -58,7 +58,28 @@ SIGNATURES = {
     "chx_init_velocities": [_P, _P, _P, _I, _F, _U, _U],
     "chx_mc_displace": [_P, _P, _I, _U, _U, _F, _P, _F, _F, _F, _I, _P],
     "chx_scale": [_P, _P, _L, _F, _P],
+    "chx_mc_displace_run": [_P, _P, _P, _P, _P, _P, _I],
 }
+
+
+class McDisplaceArgs(C.Structure):
+    """chx_mc_displace_args (include/chiron_b200.h)."""
+    _fields_ = [("n", _I), ("potential", _I), ("periodic", _I), ("lx", _F), ("ly", _F), ("lz", _F),
+                ("sigma", _F), ("epsilon", _F), ("cutoff", _F), ("subset_mask", _P), ("subset_ids", _P),
+                ("n_subset", _I), ("neighbor_list", _P), ("n_neighbors", _P), ("M", _I),
+                ("ref_positions", _P), ("skin", _F), ("x0", _P), ("n0", _I), ("k", _F), ("U0", _F),
+                ("beta", C.c_double), ("pv", C.c_double)]
+
+
+class McState(C.Structure):
+    """chx_mc_state (include/chiron_b200.h), 64 bytes."""
+    _fields_ = [("key", _U * 2), ("sel", C.c_int32), ("have_u", C.c_int32), ("u_current", _F),
+                ("sigma_disp", _F), ("n_accepted", C.c_int32), ("n_proposed", C.c_int32),
+                ("moves_done", C.c_int32), ("halt", C.c_int32), ("nan_seen", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
+
+
+MC_LJ_NLIST, MC_LJ_ALLPAIRS, MC_HO, MC_IDEAL, MC_LJ_SUBSET_DELTA = range(5)
 _RESTYPES = {"chx_launch_count": _L, "chx_last_error_string": C.c_char_p}
 
 

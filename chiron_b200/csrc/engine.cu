@@ -843,24 +843,28 @@ __device__ __forceinline__ int tile_slot(const uint32_t* __restrict__ tp, uint32
 
 // xs: positions of ALL replicas (the tiles hold replica-absolute indices).  LW2: two list words per
 // tile (at most 12 partners per lane and tile), the common case, with the list kept in registers.
-template <bool ENERGY, bool GEN, bool LW2>
+// The loop visits tiles tp, tp + tadv, ... (nt of them): tadv = SPLIT * tstride when SPLIT warps share a
+// block, each taking every SPLIT-th tile.
+template <bool ENERGY, bool GEN, bool LW2, int SPLIT>
 __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, const uint32_t* __restrict__ tp,
-                                             int nt, int tstride, const float4 xi0, const float4 xi,
+                                             int nt, int tstride_arg, const float4 xi0, const float4 xi,
                                              const float4 bc, const MdGeom& g, const LjConst& lj, int lane,
                                              float& fx, float& fy, float& fz, float& e_acc, unsigned& npair) {
     // software pipeline over the tiles: index/list words are fetched two tiles ahead and the j
     // positions one tile ahead, so the L2/HBM latency of a tile hides behind the previous one.
     // The table of a block is padded by TILE_PAD tiles, so the look-ahead never needs clamping.
     if (nt <= 0) return;
+    const int tstride = LW2 ? 96 : tstride_arg;   // two list words: compile-time strides
+    const int tadv = SPLIT * tstride;
     const float INF = __int_as_float(0x7f800000);
     const float FAR = 1.0e18f;
     const bool sentinel = lane == 31;
     const uint32_t* pf = tp + lane;            // this lane's word of the tile being prefetched
     uint32_t code_n = pf[0], la_n = pf[32], lb_n = pf[64];
     float4 xj_n = xs[code_n & 0xffffffu];
-    pf += tstride;
+    pf += tadv;
     uint32_t code_nn = pf[0], la_nn = pf[32], lb_nn = pf[64];
-    pf += tstride;
+    pf += tadv;
 #if CHX_TILE_PREFETCH
     const int nlines = tstride >> 5;            // 128-byte lines per tile
     if (lane < nlines) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 32 * lane));
@@ -875,13 +879,13 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
     const float2 cxy = make_float2(-bc.x * g.inv_lx, -bc.y * g.inv_ly);
     const float czl = -bc.z * g.inv_lz;
     const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
-    for (int t = 0; t < nt; ++t, tp += tstride) {
+    for (int t = 0; t < nt; ++t, tp += tadv) {
         const uint32_t code = code_n, la = la_n, lb = lb_n;
         float4 xj = xj_n;
         code_n = code_nn; la_n = la_nn; lb_n = lb_nn;
         xj_n = xs[code_n & 0xffffffu];
         code_nn = pf[0]; la_nn = pf[32]; lb_nn = pf[64];
-        pf += tstride;
+        pf += tadv;
 #if CHX_TILE_PREFETCH
         // the tables are streamed from HBM once per step: pull the lines of the tile after next into
         // L1 now (no register, no scoreboard), so the register loads above find them on chip
@@ -1012,19 +1016,22 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
     if (ENERGY) e_acc += e2.x + e2.y;
 }
 
-#ifndef CHX_FORCE_MINB
-#define CHX_FORCE_MINB (32 / FW)   // CTAs per SM the register allocation must allow
-#endif
-template <bool ENERGY>
-__global__ void __launch_bounds__(FW * 32, CHX_FORCE_MINB)
+// SPLIT warps of a CTA share one block: warp w takes tiles w, w + SPLIT, ... and the partial forces
+// are summed through shared memory in warp order (deterministic).  SPLIT = 1 is one warp per block;
+// 2 or 4 gives small systems (few blocks per SM) enough warps to hide latency and shortens the tail
+// of the last wave on large ones.
+#define MD_FORCE_MAX_SPLIT 4
+template <bool ENERGY, int SPLIT>
+__global__ void __launch_bounds__(SPLIT * 32, 32 / SPLIT)
 k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
            float4* __restrict__ refu_all, const uint32_t* __restrict__ tiles_all,
            const int* __restrict__ ntiles_all, const uint8_t* __restrict__ generic_all,
            const float4* __restrict__ bcenter_all, MdGeom g, LjConst lj, int tcap, int tstride,
            MdRep* __restrict__ rep, int mode, int step_arg, const int* __restrict__ step_base,
            int report_interval, int n_rep, double* __restrict__ energy_out) {
-    __shared__ double red[FW];
-    __shared__ unsigned long long redn[FW];
+    __shared__ double red[SPLIT];
+    __shared__ unsigned long long redn[SPLIT];
+    __shared__ float4 part[SPLIT > 1 ? SPLIT - 1 : 1][32];
     const int r = blockIdx.y;
     int step = step_arg + (step_base ? *step_base : 0);   // graph replays read the chunk's first step
     if (mode == FMODE_STEP) {
@@ -1035,35 +1042,49 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
         step = rep[r].redo_step;
     }
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * FW + w;
+    const int b = blockIdx.x;
     float e_acc = 0.f;
     unsigned npair = 0;
-    if (b < g.nblk) {
-        const float4* xs = xs_all + (size_t)r * g.np;
-        const int i = b * 32 + lane;
-        const float4 xi0 = xs[i];
-        float4 xi = xi0;
-        if (step >= 0 && rep[r].user_step == step) {  // reference rebuild (neighbors.py:903-905 -> build)
-            refu_all[(size_t)r * g.np + i] = xi0;
-            if (b == 0 && lane == 0) rep[r].user_rebuilds++;
+    const float4* xs = xs_all + (size_t)r * g.np;
+    const int i = b * 32 + lane;
+    const float4 xi0 = xs[i];
+    float4 xi = xi0;
+    if (w == 0 && step >= 0 && rep[r].user_step == step) {  // reference rebuild (neighbors.py:903-905 -> build)
+        refu_all[(size_t)r * g.np + i] = xi0;
+        if (b == 0 && lane == 0) rep[r].user_rebuilds++;
+    }
+    const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * (size_t)(tcap + TILE_PAD) * tstride +
+                         (size_t)w * tstride;
+    const bool lw2 = tstride == 96;
+    const int nt_all = ntiles_all[(size_t)r * g.nblk + b];
+    const int nt = (nt_all - w + SPLIT - 1) / SPLIT;      // tiles w, w + SPLIT, ... < nt_all
+    const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
+    const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (gen) {
+        md_tile_loop<ENERGY, true, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+    } else {
+        xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
+        xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
+        xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
+        if (lw2)
+            md_tile_loop<ENERGY, false, true, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+        else
+            md_tile_loop<ENERGY, false, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+    }
+    if (SPLIT > 1) {
+        if (w > 0) part[w - 1][lane] = make_float4(fx, fy, fz, e_acc);
+        __syncthreads();
+        if (w == 0) {
+            float es = e_acc;
+#pragma unroll
+            for (int k = 0; k < SPLIT - 1; ++k) {
+                const float4 q = part[k][lane];
+                fx += q.x; fy += q.y; fz += q.z; es += q.w;
+            }
+            fs_all[(size_t)r * g.np + i] = make_float4(fx, fy, fz, 0.5f * es);
         }
-        const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * (size_t)(tcap + TILE_PAD) * tstride;
-        const bool lw2 = tstride == 96;
-        const int nt = ntiles_all[(size_t)r * g.nblk + b];
-        const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
-        const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
-        float fx = 0.f, fy = 0.f, fz = 0.f;
-        if (gen) {
-            md_tile_loop<ENERGY, true, false>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
-        } else {
-            xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
-            xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
-            xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
-            if (lw2)
-                md_tile_loop<ENERGY, false, true>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
-            else
-                md_tile_loop<ENERGY, false, false>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
-        }
+    } else {
         fs_all[(size_t)r * g.np + i] = make_float4(fx, fy, fz, 0.5f * e_acc);
     }
     if (ENERGY) {
@@ -1074,7 +1095,7 @@ k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
         if (threadIdx.x == 0) {
             double s = 0.0;
             unsigned long long c = 0;
-            for (int k = 0; k < FW; ++k) { s += red[k]; c += redn[k]; }
+            for (int k = 0; k < SPLIT; ++k) { s += red[k]; c += redn[k]; }
             double* slot = nullptr;
             if (energy_out) {
                 if (mode == FMODE_ALL) slot = energy_out + r;
@@ -1201,7 +1222,9 @@ static inline int md_tstride(const chx_ljmd* md) { return 32 * (1 + md->lw); }
 static inline int md_ccap(const chx_ljmd* md) { return md->tcap * TILE_SLOTS; }
 // tiles of a block: tcap + TILE_PAD (the force kernel's look-ahead reads past the last tile)
 static inline size_t md_tiles_bytes(const chx_ljmd* md) {
-    return (size_t)md->R * md->g.nblk * (md->tcap + TILE_PAD) * md_tstride(md) * sizeof(uint32_t);
+    // + slack after the last block: with SPLIT warps per block the look-ahead reaches 3 * SPLIT tiles on
+    return ((size_t)md->R * md->g.nblk * (md->tcap + TILE_PAD) + 3 * MD_FORCE_MAX_SPLIT + 1) * md_tstride(md) *
+           sizeof(uint32_t);
 }
 
 static int md_alloc(chx_ljmd* md) {
@@ -1390,15 +1413,33 @@ static int md_rebuild(chx_ljmd* md) {
     return CHX_NEIGHBOR_OVERFLOW;
 }
 
+// warps per block in the force kernel: CHX_FORCE_SPLIT (1, 2 or 4) or by the number of blocks in flight
+static int md_force_split(const chx_ljmd* md) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("CHX_FORCE_SPLIT");
+        env = e ? atoi(e) : 0;
+    }
+    if (env == 1 || env == 2 || env == 4) return env;
+    const long long warps = (long long)md->g.nblk * md->R;
+    const long long slots = 32LL * md->ctx->sm_count;       // resident warps at the kernel's register count
+    // measured on B200 (profiles/r01_split_tune.log): splitting costs 7-15 % once every SM is full
+    // (N = 262,144: 46.1 / 49.4 / 53.2 us for 1 / 2 / 4) and gains 14 % on 8 x 8,192 particles
+    return warps >= slots ? 1 : 4;
+}
+
 static int md_force(chx_ljmd* md, int mode, int step, bool energy, int report_interval, double* e_dev,
                     const int* step_base = nullptr) {
     const MdGeom& g = md->g;
-    const dim3 gf(chx_div_up(g.nblk, FW), md->R);
-#define MD_FORCE_LAUNCH(E)                                                                          \
-    k_md_force<E><<<gf, FW * 32, 0, md->ctx->stream>>>(                                              \
+    const dim3 gf(g.nblk, md->R);
+    const int split = md_force_split(md);
+#define MD_FORCE_LAUNCH(E, S)                                                                       \
+    k_md_force<E, S><<<gf, S * 32, 0, md->ctx->stream>>>(                                            \
         md->xs, md->fs, md->refu, md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md),    \
         md->tcap, md_tstride(md), md->rep, mode, step, step_base, report_interval, md->R, e_dev)
-    if (energy) MD_FORCE_LAUNCH(true); else MD_FORCE_LAUNCH(false);
+    if (split == 1) { if (energy) MD_FORCE_LAUNCH(true, 1); else MD_FORCE_LAUNCH(false, 1); }
+    else if (split == 2) { if (energy) MD_FORCE_LAUNCH(true, 2); else MD_FORCE_LAUNCH(false, 2); }
+    else { if (energy) MD_FORCE_LAUNCH(true, 4); else MD_FORCE_LAUNCH(false, 4); }
 #undef MD_FORCE_LAUNCH
     CHX_LAUNCHED(md->ctx);
     return CHX_OK;

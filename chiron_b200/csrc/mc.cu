@@ -1,0 +1,416 @@
+// Device-resident Metropolis loop for MonteCarloDisplacementMove (chiron/mcmc.py:243-306 update,
+// :357-463 _step, :531-548 _accept_or_reject, :733-787 _propose).
+//
+// The reference runs every Monte Carlo step from Python: two PRNG splits, a jitted proposal, a full
+// energy evaluation and a host-side accept/reject.  Here a move is three launches that never leave
+// the device -- propose (+wrap +list check), energy of the proposal, decide (+key advance, counters) --
+// and `n_moves` of them are enqueued (as replays of one cached CUDA graph) before the host looks at
+// the state again.  The PRNG stream, the proposal arithmetic and the acceptance rule are the
+// reference's, so the trajectory is the one the host-driven path (chiron_b200/mcmc.py) produces.
+//
+// A proposal that would make NeighborListNsqrd.check() true (mcmc.py:754-759: rebuild on the
+// proposed positions) stops the loop BEFORE that move (state.halt = 1, key not advanced); the caller
+// performs that one move through the building-block path, which rebuilds the list, and re-enters.
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+
+struct McArgs {
+    chx_mc_displace_args a;
+    float* x0;
+    float* x1;
+    chx_mc_state* st;
+    double* acc;
+};
+
+__device__ __forceinline__ void lj_pair_e(float d, float sigma, float eps, float& e) {
+    const float q = sigma / d;
+    const float q2 = q * q;
+    const float q6 = q2 * q2 * q2;
+    const float q12 = q6 * q6;
+    e = 4.0f * eps * (q12 - q6);
+}
+
+__device__ __forceinline__ void mc_block_add(double v, double* target) {
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        double t = lane < nw ? sh[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0 && t != 0.0) atomicAdd(target, t);
+    }
+}
+
+// ---- propose: x' = wrap(x + sigma * normal(subkey, (n,3)) * mask), list check --------------------
+template <bool WRAP, bool CHECK>
+__global__ void __launch_bounds__(256)
+k_mcl_propose(int n, const float* __restrict__ mask, Box box, const float* __restrict__ ref,
+              float half_skin, float* __restrict__ x0, float* __restrict__ x1,
+              chx_mc_state* __restrict__ st) {
+    if (*((volatile int*)&st->halt)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool moved = false;
+    if (i < n) {
+        uint32_t c0, c1, s0, s1;
+        threefry_split(st->key[0], st->key[1], c0, c1, s0, s1);   // new_PRNG_key (states.py:150-154)
+        const float* xc = st->sel ? x1 : x0;
+        float* xp = st->sel ? x0 : x1;
+        const float sigma = st->sigma_disp;
+        const float m = mask ? mask[i] : 1.0f;
+        const unsigned long long total = 3ull * (unsigned long long)n;
+        float xn[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float d = __fmul_rn(normal_from_bits(random_bits_elem(s0, s1, 3ull * i + c, total)), sigma);
+            if (mask) d = __fmul_rn(d, m);
+            float v = __fadd_rn(xc[3 * i + c], d);
+            if (WRAP) v = ref_wrap(v, c == 0 ? box.lx : (c == 1 ? box.ly : box.lz));
+            xp[3 * i + c] = v;
+            xn[c] = v;
+        }
+        if (CHECK) {
+            float rx, ry, rz, d;
+            ref_displacement<WRAP>(xn[0], xn[1], xn[2], ref[3 * i], ref[3 * i + 1], ref[3 * i + 2], box, rx, ry, rz, d);
+            moved = d >= half_skin;
+        }
+    }
+    if (CHECK) {
+        if (__syncthreads_or(moved) && threadIdx.x == 0) atomicExch(&st->halt, 1);
+    }
+}
+
+// ---- energies of the proposal (which = 1) or of the current state (which = 0) --------------------
+__device__ __forceinline__ const float* mc_buf(const chx_mc_state* st, const float* x0, const float* x1, int which) {
+    return ((st->sel ^ which) & 1) ? x1 : x0;
+}
+
+template <bool PERIODIC>
+__global__ void __launch_bounds__(256)
+k_mcl_lj_nlist(int n, Box box, const uint32_t* __restrict__ list, const int32_t* __restrict__ nn, int M,
+               float sigma, float eps, float cutoff, const float* __restrict__ x0,
+               const float* __restrict__ x1, const chx_mc_state* __restrict__ st, int which,
+               double* __restrict__ acc) {
+    if (st->halt) return;
+    const float* x = mc_buf(st, x0, x1, which);
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    double e_acc = 0.0;
+    if (i < n) {
+        const float xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+        int cnt = nn[i];
+        cnt = cnt < M ? cnt : M;
+        for (int k = lane; k < cnt; k += 32) {
+            const uint32_t j = list[(size_t)i * M + k];
+            float rx, ry, rz, d;
+            ref_displacement<PERIODIC>(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2], box, rx, ry, rz, d);
+            if (d < cutoff) {
+                float e;
+                lj_pair_e(d, sigma, eps, e);
+                e_acc += (double)e;
+            }
+        }
+    }
+    mc_block_add(e_acc, acc);
+}
+
+// all pairs i < j: one block per row, threads over j (PairListNsqrd / nbr_list=None, small N)
+template <bool PERIODIC>
+__global__ void __launch_bounds__(128)
+k_mcl_lj_allpairs(int n, Box box, float sigma, float eps, float cutoff, const float* __restrict__ x0,
+                  const float* __restrict__ x1, const chx_mc_state* __restrict__ st, int which,
+                  double* __restrict__ acc) {
+    if (st->halt) return;
+    const float* x = mc_buf(st, x0, x1, which);
+    const int i = blockIdx.x;
+    const float xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+    double e_acc = 0.0;
+    for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+        float rx, ry, rz, d;
+        ref_displacement<PERIODIC>(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2], box, rx, ry, rz, d);
+        if (cutoff < 0.0f || d < cutoff) {
+            float e;
+            lj_pair_e(d, sigma, eps, e);
+            e_acc += (double)e;
+        }
+    }
+    mc_block_add(e_acc, acc);
+}
+
+__global__ void __launch_bounds__(256)
+k_mcl_ho(int n, const float* __restrict__ xref, int n0, const float* __restrict__ x0,
+         const float* __restrict__ x1, const chx_mc_state* __restrict__ st, int which,
+         double* __restrict__ acc) {
+    if (st->halt) return;
+    const float* x = mc_buf(st, x0, x1, which);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (i < n) {
+        const int r = n0 == 1 ? 0 : i;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float dx = __fsub_rn(x[3 * i + c], xref[3 * r + c]);
+            e += (double)__fmul_rn(dx, dx);
+        }
+    }
+    mc_block_add(e, acc);
+}
+
+// delta energy of the moved subset: one block per moved particle (see k_lj_subset_delta, lj.cu)
+template <bool PERIODIC>
+__global__ void __launch_bounds__(256)
+k_mcl_subset_delta(int n, const uint32_t* __restrict__ moved, const float* __restrict__ mask, Box box,
+                   float sigma, float eps, float cutoff, const float* __restrict__ x0,
+                   const float* __restrict__ x1, const chx_mc_state* __restrict__ st,
+                   double* __restrict__ acc) {
+    if (st->halt) return;
+    const float* xo = mc_buf(st, x0, x1, 0);
+    const float* xn = mc_buf(st, x0, x1, 1);
+    const int m = (int)moved[blockIdx.x];
+    const float ox = xo[3 * m], oy = xo[3 * m + 1], oz = xo[3 * m + 2];
+    const float nx = xn[3 * m], ny = xn[3 * m + 1], nz = xn[3 * m + 2];
+    double a = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        if (j == m) continue;
+        const double w = mask[j] != 0.0f ? 0.5 : 1.0;
+        float rx, ry, rz, d, e;
+        ref_displacement<PERIODIC>(nx, ny, nz, xn[3 * j], xn[3 * j + 1], xn[3 * j + 2], box, rx, ry, rz, d);
+        if (d < cutoff) { lj_pair_e(d, sigma, eps, e); a += w * (double)e; }
+        ref_displacement<PERIODIC>(ox, oy, oz, xo[3 * j], xo[3 * j + 1], xo[3 * j + 2], box, rx, ry, rz, d);
+        if (d < cutoff) { lj_pair_e(d, sigma, eps, e); a -= w * (double)e; }
+    }
+    mc_block_add(a, acc);
+}
+
+// ---- reduced potential and the Metropolis decision ---------------------------------------------------
+struct McThermo {
+    int potential;
+    float k, U0;        // harmonic oscillator
+    double beta, pv;    // u = beta * (U + pv)
+};
+
+__device__ __forceinline__ float mc_reduced(const McThermo& t, double acc) {
+    float U = (float)acc;
+    if (t.potential == CHX_MC_HO) U = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, t.k), U), t.U0);   // potential.py:413-418
+    if (t.potential == CHX_MC_IDEAL) U = 0.0f;
+    return (float)(t.beta * ((double)U + t.pv));
+}
+
+// u of the current state (first entry of a loop, or after the caller changed the state)
+__global__ void k_mcl_init(McThermo t, chx_mc_state* __restrict__ st, double* __restrict__ acc) {
+    const double a = *acc;
+    *acc = 0.0;
+    st->u_current = mc_reduced(t, a);
+    st->have_u = 1;
+}
+
+__global__ void k_mcl_decide(McThermo t, chx_mc_state* __restrict__ st, double* __restrict__ acc) {
+    const double a = *acc;
+    *acc = 0.0;
+    if (st->halt) return;
+    const float u_cur = st->u_current;
+    float u_new;
+    if (t.potential == CHX_MC_LJ_SUBSET_DELTA) u_new = __fadd_rn(u_cur, (float)(a * t.beta));
+    else u_new = mc_reduced(t, a);
+    const float lr = __fadd_rn(-u_new, u_cur);                    // mcmc.py:777
+    uint32_t c0, c1, s0, s1;
+    threefry_split(st->key[0], st->key[1], c0, c1, s0, s1);       // the split _propose made
+    bool accept = false;
+    if (u_new != u_new) {
+        // NaN energy: rejected without drawing the uniform (mcmc.py:417-430)
+        st->nan_seen += 1;
+    } else {
+        uint32_t d0, d1, t0, t1;
+        threefry_split(c0, c1, d0, d1, t0, t1);                   // proposed_sampler_state.new_PRNG_key
+        c0 = d0; c1 = d1;
+        const float uni = uniform_from_bits(random_bits_elem(t0, t1, 0ull, 1ull), 0.0f, 1.0f);
+        accept = (-lr <= 0.0f) || (uni < expf(lr));                // mcmc.py:541-548
+    }
+    st->key[0] = c0; st->key[1] = c1;
+    if (accept) {
+        st->sel ^= 1;
+        st->u_current = u_new;
+        st->n_accepted += 1;
+    }
+    st->n_proposed += 1;
+    st->moves_done += 1;
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+static int mc_launch_energy(chx_ctx* ctx, const McArgs& m, int which) {
+    const chx_mc_displace_args& a = m.a;
+    const Box box = make_box(a.lx, a.ly, a.lz);
+    cudaStream_t st = ctx->stream;
+    switch (a.potential) {
+    case CHX_MC_LJ_NLIST:
+        if (a.periodic)
+            k_mcl_lj_nlist<true><<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, box, a.neighbor_list, a.n_neighbors, a.M, a.sigma, a.epsilon, a.cutoff, m.x0, m.x1, m.st, which, m.acc);
+        else
+            k_mcl_lj_nlist<false><<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, box, a.neighbor_list, a.n_neighbors, a.M, a.sigma, a.epsilon, a.cutoff, m.x0, m.x1, m.st, which, m.acc);
+        break;
+    case CHX_MC_LJ_SUBSET_DELTA:
+        if (which == 0) {
+            // the loop only needs differences; u of the current state is whatever the caller set
+            return CHX_OK;
+        }
+        if (a.periodic)
+            k_mcl_subset_delta<true><<<a.n_subset, 256, 0, st>>>(a.n, a.subset_ids, a.subset_mask, box, a.sigma, a.epsilon, a.cutoff, m.x0, m.x1, m.st, m.acc);
+        else
+            k_mcl_subset_delta<false><<<a.n_subset, 256, 0, st>>>(a.n, a.subset_ids, a.subset_mask, box, a.sigma, a.epsilon, a.cutoff, m.x0, m.x1, m.st, m.acc);
+        break;
+    case CHX_MC_LJ_ALLPAIRS:
+        if (a.periodic)
+            k_mcl_lj_allpairs<true><<<a.n, 128, 0, st>>>(a.n, box, a.sigma, a.epsilon, a.cutoff, m.x0, m.x1, m.st, which, m.acc);
+        else
+            k_mcl_lj_allpairs<false><<<a.n, 128, 0, st>>>(a.n, box, a.sigma, a.epsilon, a.cutoff, m.x0, m.x1, m.st, which, m.acc);
+        break;
+    case CHX_MC_HO:
+        k_mcl_ho<<<chx_div_up(a.n, 256), 256, 0, st>>>(a.n, a.x0, a.n0, m.x0, m.x1, m.st, which, m.acc);
+        break;
+    case CHX_MC_IDEAL:
+        return CHX_OK;   // U = 0 (potential.py:93-127): nothing to launch
+    default:
+        chx_set_error("unknown potential kind %d", a.potential);
+        return CHX_BAD_ARG;
+    }
+    CHX_LAUNCHED(ctx);
+    return CHX_OK;
+}
+
+static McThermo mc_thermo(const chx_mc_displace_args& a) {
+    McThermo t;
+    t.potential = a.potential; t.k = a.k; t.U0 = a.U0; t.beta = a.beta; t.pv = a.pv;
+    return t;
+}
+
+static int mc_launch_move(chx_ctx* ctx, const McArgs& m) {
+    const chx_mc_displace_args& a = m.a;
+    const Box box = make_box(a.lx, a.ly, a.lz);
+    const bool check = a.ref_positions != nullptr;
+    const int blocks = chx_div_up(a.n, 256);
+    const float hs = 0.5f * a.skin;
+#define PROPOSE(W, C)                                                                                   \
+    k_mcl_propose<W, C><<<blocks, 256, 0, ctx->stream>>>(a.n, a.subset_mask, box, a.ref_positions, hs, \
+                                                         m.x0, m.x1, m.st)
+    if (a.periodic) { if (check) PROPOSE(true, true); else PROPOSE(true, false); }
+    else { if (check) PROPOSE(false, true); else PROPOSE(false, false); }
+#undef PROPOSE
+    CHX_LAUNCHED(ctx);
+    int rc = mc_launch_energy(ctx, m, 1);
+    if (rc != CHX_OK) return rc;
+    k_mcl_decide<<<1, 1, 0, ctx->stream>>>(mc_thermo(a), m.st, m.acc);
+    CHX_LAUNCHED(ctx);
+    return CHX_OK;
+}
+
+// launches per move, for the context's launch counter when a graph is replayed
+static int mc_launches_per_move(const chx_mc_displace_args& a) { return a.potential == CHX_MC_IDEAL ? 2 : 3; }
+
+// one cached graph of MC_GRAPH_MOVES moves per distinct argument set (a handful at most)
+#define MC_GRAPH_MOVES 10
+struct McGraph {
+    chx_ctx* ctx;
+    McArgs key;
+    cudaGraphExec_t exec;
+    unsigned long long stamp;
+};
+static std::vector<McGraph> g_mc_graphs;
+static unsigned long long g_mc_stamp = 0;
+
+static int mc_graph_get(chx_ctx* ctx, const McArgs& m, cudaGraphExec_t* out) {
+    for (auto& g : g_mc_graphs)
+        if (g.ctx == ctx && memcmp(&g.key, &m, sizeof(McArgs)) == 0) {
+            g.stamp = ++g_mc_stamp;
+            *out = g.exec;
+            return CHX_OK;
+        }
+    cudaStream_t user = ctx->stream, cap = nullptr;
+    CHX_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    ctx->stream = cap;
+    const long long launches_before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t err = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    int rc = CHX_OK;
+    if (err == cudaSuccess) {
+        for (int k = 0; k < MC_GRAPH_MOVES && rc == CHX_OK; ++k) rc = mc_launch_move(ctx, m);
+        err = cudaStreamEndCapture(cap, &graph);
+    }
+    ctx->stream = user;
+    ctx->launches = launches_before;
+    cudaGraphExec_t exec = nullptr;
+    if (err == cudaSuccess && rc == CHX_OK) err = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    cudaStreamDestroy(cap);
+    if (rc != CHX_OK) return rc;
+    if (err != cudaSuccess) {
+        chx_set_error("Monte Carlo graph capture failed: %s", cudaGetErrorString(err));
+        return CHX_CUDA_ERROR;
+    }
+    if (g_mc_graphs.size() >= 16) {   // drop the least recently used
+        size_t lru = 0;
+        for (size_t k = 1; k < g_mc_graphs.size(); ++k)
+            if (g_mc_graphs[k].stamp < g_mc_graphs[lru].stamp) lru = k;
+        cudaGraphExecDestroy(g_mc_graphs[lru].exec);
+        g_mc_graphs.erase(g_mc_graphs.begin() + lru);
+    }
+    McGraph g;
+    g.ctx = ctx; g.exec = exec; g.stamp = ++g_mc_stamp;
+    memcpy(&g.key, &m, sizeof(McArgs));
+    g_mc_graphs.push_back(g);
+    *out = exec;
+    return CHX_OK;
+}
+
+extern "C" {
+
+int chx_mc_displace_run(chx_ctx* ctx, const chx_mc_displace_args* args, float* x0, float* x1,
+                        chx_mc_state* state_dev, chx_mc_state* state_host, int n_moves) {
+    CHX_REQUIRE(ctx && args && x0 && x1 && state_dev && state_host, "NULL argument");
+    CHX_REQUIRE(args->n > 0 && n_moves >= 0, "n must be positive, n_moves non-negative");
+    const chx_mc_displace_args& a = *args;
+    if (a.potential == CHX_MC_LJ_NLIST)
+        CHX_REQUIRE(a.neighbor_list && a.n_neighbors && a.ref_positions && a.M > 0, "neighbour list arrays missing");
+    if (a.potential == CHX_MC_LJ_SUBSET_DELTA)
+        CHX_REQUIRE(a.subset_ids && a.subset_mask && a.n_subset > 0, "subset ids / mask missing");
+    if (a.potential == CHX_MC_HO) CHX_REQUIRE(a.x0 && (a.n0 == 1 || a.n0 == a.n), "x0 must have 1 or n rows");
+    McArgs m;
+    memset(&m, 0, sizeof(m));   // padding bytes too: the struct is the graph cache key
+    m.a = a; m.x0 = x0; m.x1 = x1; m.st = state_dev;
+    m.acc = (double*)chx_scratch(ctx, 256);
+    if (!m.acc) return CHX_CUDA_ERROR;
+    cudaStream_t st = ctx->stream;
+    state_host->halt = 0;
+    state_host->moves_done = 0;
+    CHX_CUDA(cudaMemcpyAsync(state_dev, state_host, sizeof(chx_mc_state), cudaMemcpyHostToDevice, st));
+    CHX_CUDA(cudaMemsetAsync(m.acc, 0, sizeof(double), st));
+    int rc = CHX_OK;
+    if (!state_host->have_u) {
+        rc = mc_launch_energy(ctx, m, 0);
+        if (rc != CHX_OK) return rc;
+        k_mcl_init<<<1, 1, 0, st>>>(mc_thermo(a), state_dev, m.acc);
+        CHX_LAUNCHED(ctx);
+    }
+    int left = n_moves;
+    static int use_graph = -1;
+    if (use_graph < 0) { const char* e = getenv("CHX_MC_NOGRAPH"); use_graph = (e && e[0] == '1') ? 0 : 1; }
+    if (use_graph && left >= MC_GRAPH_MOVES) {
+        cudaGraphExec_t exec = nullptr;
+        rc = mc_graph_get(ctx, m, &exec);
+        if (rc != CHX_OK) return rc;
+        while (left >= MC_GRAPH_MOVES) {
+            CHX_CUDA(cudaGraphLaunch(exec, st));
+            ctx->launches += MC_GRAPH_MOVES * mc_launches_per_move(a);
+            left -= MC_GRAPH_MOVES;
+        }
+    }
+    for (; left > 0 && rc == CHX_OK; --left) rc = mc_launch_move(ctx, m);
+    if (rc != CHX_OK) return rc;
+    CHX_CUDA(cudaMemcpyAsync(state_host, state_dev, sizeof(chx_mc_state), cudaMemcpyDeviceToHost, st));
+    CHX_CUDA(cudaStreamSynchronize(st));
+    return CHX_OK;
+}
+
+}  // extern "C"

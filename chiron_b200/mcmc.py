@@ -7,6 +7,7 @@ with `copy.deepcopy` are replaced by tensor clones of what actually changes.
 """
 import copy
 import math
+import os
 from abc import abstractmethod
 from typing import List, Optional, Tuple
 
@@ -96,8 +97,21 @@ class MCMove(MCMCMove):
         self.autotune = autotune
         self.autotune_interval = autotune_interval
 
+    # Run whole `update()` calls as a device-resident loop (csrc/mc.cu) when the move supports it and
+    # nothing has to be reported per step.  False keeps the reference's step-by-step control flow.
+    device_loop = os.environ.get("CHX_MC_DEVICE_LOOP", "1") != "0"
+
+    def _device_plan(self, sampler_state, thermodynamic_state, nbr_list):
+        """Arguments of the device loop for this move, or None to use the step-by-step path."""
+        return None
+
     def update(self, sampler_state, thermodynamic_state, nbr_list=None):
         self._current_reduced_potential = None
+        if self.device_loop and getattr(self, "reporter", None) is None \
+                and self.acceptance_method == "Metropolis-Hastings" and self.number_of_moves > 0:
+            plan = self._device_plan(sampler_state, thermodynamic_state, nbr_list)
+            if plan is not None:
+                return self._update_device(plan, sampler_state, thermodynamic_state, nbr_list)
         for i in range(self.number_of_moves):
             sampler_state, thermodynamic_state, nbr_list = self._step(sampler_state, thermodynamic_state, nbr_list)
             self._number_of_attempts_made += 1
@@ -108,6 +122,65 @@ class MCMove(MCMCMove):
             if self.autotune:
                 if self._number_of_attempts_made % self.autotune_interval == 0 and self._number_of_attempts_made > 0:
                     self._autotune()
+        self._move_iteration += 1
+        return sampler_state, thermodynamic_state, nbr_list
+
+    def _update_device(self, plan, sampler_state, thermodynamic_state, nbr_list):
+        """`update()` on the device loop `chx_mc_displace_run` (include/chiron_b200.h): segments end at
+        autotune boundaries; a proposal that needs a neighbour-list rebuild is made by `_step`."""
+        import ctypes as C
+        remaining = self.number_of_moves
+        while remaining > 0:
+            args, keep = plan
+            x = _lib.as_device_f32(sampler_state.positions)
+            dev = x.device
+            ctx = _lib.get_context(dev)
+            bufs = [x.clone(), torch.empty_like(x)]
+            st_dev = torch.zeros(16, dtype=torch.int32, device=dev)
+            st = _lib.McState()
+            key = sampler_state._current_PRNG_key
+            st.key[0], st.key[1] = int(key[0]), int(key[1])
+            st.n_accepted, st.n_proposed = int(self.n_accepted), int(self.n_proposed)
+            accepted_before = int(self.n_accepted)
+            halted = False
+            while remaining > 0 and not halted:
+                seg = remaining
+                if self.autotune:
+                    seg = min(seg, self.autotune_interval - self._number_of_attempts_made % self.autotune_interval)
+                st.sigma_disp = float(self.displacement_sigma.value_in_unit_system(unit.md_unit_system))
+                ctx.call("chx_mc_displace_run", C.byref(args), _lib.ptr(bufs[0]), _lib.ptr(bufs[1]),
+                         _lib.ptr(st_dev), C.byref(st), int(seg))
+                done = int(st.moves_done)
+                remaining -= done
+                self._number_of_attempts_made += done
+                self.n_accepted, self.n_proposed = int(st.n_accepted), int(st.n_proposed)
+                halted = bool(st.halt)
+                if self.autotune and done > 0 and self._number_of_attempts_made % self.autotune_interval == 0:
+                    self._autotune()
+            new_key = np.array([st.key[0], st.key[1]], dtype=np.uint32)
+            if self.n_accepted != accepted_before:
+                # accept returns a new state object, reject the same one with the advanced key (mcmc.py:441-463)
+                out = _shallow_state_copy(sampler_state)
+                out.positions = bufs[int(st.sel)]
+                sampler_state = out
+            sampler_state._current_PRNG_key = new_key
+            if halted:
+                # this proposal rebuilds the neighbour list (mcmc.py:754-759): one reference-shaped step
+                self._current_reduced_potential = None
+                sampler_state, thermodynamic_state, nbr_list = self._step(sampler_state, thermodynamic_state, nbr_list)
+                self._number_of_attempts_made += 1
+                remaining -= 1
+                if self.autotune and self._number_of_attempts_made % self.autotune_interval == 0:
+                    self._autotune()
+                if remaining > 0:
+                    plan = self._device_plan(sampler_state, thermodynamic_state, nbr_list)
+                    if plan is None:
+                        for _ in range(remaining):
+                            sampler_state, thermodynamic_state, nbr_list = self._step(
+                                sampler_state, thermodynamic_state, nbr_list)
+                            self._number_of_attempts_made += 1
+                        remaining = 0
+        self._current_reduced_potential = None
         self._move_iteration += 1
         return sampler_state, thermodynamic_state, nbr_list
 
@@ -219,6 +292,96 @@ class MonteCarloDisplacementMove(MCMove):
             self.displacement_sigma *= 1.1
         elif acceptance_ratio < 0.4:
             self.displacement_sigma /= 1.1
+
+    def _ensure_subset(self, n, dev):
+        if self.atom_subset is not None and self.atom_subset_mask is None:
+            m = torch.zeros(n, dtype=torch.float32, device=dev)
+            ids = torch.as_tensor(list(self.atom_subset), dtype=torch.long, device=dev)
+            m[ids] = 1.0
+            self.atom_subset_mask = m
+            self._subset_ids = ids.to(torch.int32).contiguous()
+
+    def _device_plan(self, sampler_state, thermodynamic_state, nbr_list):
+        """chx_mc_displace_args for (potential, list) combinations the device loop covers."""
+        from .neighbors import NeighborListNsqrd, PairListNsqrd
+        from .potential import HarmonicOscillatorPotential, IdealGasPotential, LJPotential
+        from .utils import kT_md
+        ts = thermodynamic_state
+        if ts.temperature is None or not torch.cuda.is_available():
+            return None
+        x = sampler_state.positions
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and x.shape[1] == 3):
+            return None
+        pot = ts.potential
+        n, dev = x.shape[0], x.device
+        a = _lib.McDisplaceArgs()
+        keep = []
+        a.n = n
+        a.lx = a.ly = a.lz = 1.0
+        if nbr_list is not None:
+            if not isinstance(nbr_list, (NeighborListNsqrd, PairListNsqrd)) or not nbr_list.is_built:
+                return None
+            if nbr_list.ref_positions.shape[0] != n:
+                return None
+            a.periodic = int(nbr_list.space.periodic)
+            if a.periodic:
+                if sampler_state.box_vectors is None:
+                    return None
+                a.lx, a.ly, a.lz = sampler_state.box_lengths_host()
+                if tuple(np.float32(v) for v in nbr_list._box_args()[:3]) != \
+                        tuple(np.float32(v) for v in (a.lx, a.ly, a.lz)):
+                    return None
+        self._ensure_subset(n, dev)
+        if self.atom_subset is not None:
+            a.subset_mask = _lib.ptr(self.atom_subset_mask)
+            keep.append(self.atom_subset_mask)
+        if isinstance(nbr_list, NeighborListNsqrd):
+            ref = _lib.as_device_f32(nbr_list.ref_positions)
+            a.ref_positions, a.skin = _lib.ptr(ref), nbr_list._skin_md()
+            keep.append(ref)
+        if type(pot) is LJPotential:
+            a.sigma, a.epsilon, a.cutoff = pot.sigma, pot.epsilon, pot.cutoff
+            if isinstance(nbr_list, NeighborListNsqrd):
+                if nbr_list._cutoff_md() != pot.cutoff:
+                    return None   # the step-by-step path raises the reference's ValueError
+                if self.use_delta_energy and self.atom_subset is not None and a.periodic \
+                        and len(self.atom_subset) * 8 <= n:
+                    a.potential = _lib.MC_LJ_SUBSET_DELTA
+                    a.subset_ids, a.n_subset = _lib.ptr(self._subset_ids), int(self._subset_ids.shape[0])
+                    keep.append(self._subset_ids)
+                else:
+                    a.potential = _lib.MC_LJ_NLIST
+                    nl, nn = nbr_list.neighbor_list, nbr_list.n_neighbors
+                    a.neighbor_list, a.n_neighbors, a.M = _lib.ptr(nl), _lib.ptr(nn), int(nl.shape[1])
+                    keep += [nl, nn]
+            elif isinstance(nbr_list, PairListNsqrd):
+                if nbr_list.cutoff is not None and nbr_list._cutoff_md() != pot.cutoff:
+                    return None
+                a.potential = _lib.MC_LJ_ALLPAIRS
+                a.cutoff = nbr_list._cutoff_md()
+            else:
+                a.potential = _lib.MC_LJ_ALLPAIRS   # potential.py:235-258: non-periodic N^2 pairs, d < cutoff
+            if a.potential == _lib.MC_LJ_ALLPAIRS and n > 8192:
+                return None
+        elif type(pot) is HarmonicOscillatorPotential:
+            x0 = pot.x0
+            if x0.shape[0] not in (1, n):
+                return None
+            a.potential, a.x0, a.n0, a.k, a.U0 = _lib.MC_HO, _lib.ptr(x0), int(x0.shape[0]), pot.k, pot.U0
+            keep.append(x0)
+        elif type(pot) is IdealGasPotential:
+            a.potential = _lib.MC_IDEAL
+        else:
+            return None
+        a.beta = 1.0 / kT_md(ts.temperature)
+        a.pv = 0.0
+        if ts.pressure is not None:
+            if sampler_state.box_vectors is None:
+                return None
+            lx, ly, lz = sampler_state.box_lengths_host()
+            volume = (lx * ly * lz) * unit.nanometer ** 3
+            a.pv = float((ts.pressure * volume * unit.AVOGADRO_CONSTANT_NA).value_in_unit_system(unit.md_unit_system))
+        return a, keep
 
     def _propose(self, current_sampler_state, current_thermodynamic_state, current_reduced_potential,
                  current_nbr_list=None):

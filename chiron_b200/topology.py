@@ -59,6 +59,13 @@ except Exception:  # noqa: BLE001
             self._atoms.append(a)
             return a
 
+        def __deepcopy__(self, memo):
+            # atoms are immutable records: MCMCSampler.run deep-copies its inputs (mcmc.py:1134-1136) and
+            # must not spend 100 ms per call cloning 10^5 Python objects
+            t = Topology()
+            t._atoms = list(self._atoms)
+            return t
+
         def atoms(self):
             return iter(self._atoms)
 

@@ -158,6 +158,58 @@ int chx_mc_displace(chx_ctx* ctx, const float* x, int n, uint32_t key0, uint32_t
 /* x_out = x * s (barostat coordinate scaling). */
 int chx_scale(chx_ctx* ctx, const float* x, long long n_elems, float s, float* x_out);
 
+/* ---- Device-resident Metropolis loop (chiron/mcmc.py:243-306 MCMove.update, :357-463 _step,
+ *      :531-548 _accept_or_reject, :733-787 MonteCarloDisplacementMove._propose) --------------------- */
+/* n_moves Monte Carlo displacement steps without a host round trip per step.  Per move: split the
+ * state's key (states.py:150-154), x' = wrap(x + sigma * normal(subkey,(n,3)) * subset_mask[:,None]),
+ * NeighborListNsqrd.check(x') (neighbors.py:828-907), reduced potential u' = beta (U(x') + pv), split
+ * again, accept iff -(u - u') <= 0 or uniform(subkey) < exp(u - u') (fp32).  The two position
+ * buffers alternate roles: x[state.sel] is the current configuration.
+ * Potential kinds: what `U` is evaluated with. */
+enum {
+    CHX_MC_LJ_NLIST = 0,        /* LJPotential over a built NeighborListNsqrd (potential.py:193-279) */
+    CHX_MC_LJ_ALLPAIRS = 1,     /* LJPotential over all pairs i<j (PairListNsqrd / nbr_list=None); cutoff<0: none */
+    CHX_MC_HO = 2,              /* HarmonicOscillatorPotential (potential.py:413-418) */
+    CHX_MC_IDEAL = 3,           /* IdealGasPotential: U = 0 (potential.py:93-127) */
+    CHX_MC_LJ_SUBSET_DELTA = 4  /* LJ, only the rows of the moved subset: u' = u + beta dU (new fast path) */
+};
+typedef struct {
+    int n;                         /* particles */
+    int potential;                 /* CHX_MC_* */
+    int periodic;                  /* 1: wrap proposals and use minimum images (OrthogonalPeriodicSpace) */
+    float lx, ly, lz;
+    float sigma, epsilon, cutoff;  /* LJ, md units */
+    const float* subset_mask;      /* device (n) 0/1 floats, NULL = all particles move (mcmc.py:742-745) */
+    const uint32_t* subset_ids;    /* device ids of the moved particles (CHX_MC_LJ_SUBSET_DELTA) */
+    int n_subset;
+    const uint32_t* neighbor_list; /* device (n,M), CHX_MC_LJ_NLIST */
+    const int32_t* n_neighbors;    /* device (n) */
+    int M;
+    const float* ref_positions;    /* device (n,3): positions at the last list build; NULL = no check */
+    float skin;                    /* the loop halts before a proposal with a displacement >= skin/2 */
+    const float* x0;               /* device (n0,3) harmonic-oscillator centres, n0 = 1 or n */
+    int n0;
+    float k, U0;
+    double beta;                   /* mol/kJ */
+    double pv;                     /* P V N_A in kJ/mol (0 without a pressure), states.py:313-323 */
+} chx_mc_displace_args;
+typedef struct {
+    uint32_t key[2];               /* SamplerState.current_PRNG_key, advanced by the loop */
+    int32_t sel;                   /* which position buffer holds the current configuration */
+    int32_t have_u;                /* 0: evaluate u of the current configuration first */
+    float u_current;               /* reduced potential of the current configuration */
+    float sigma_disp;              /* displacement_sigma, nm */
+    int32_t n_accepted, n_proposed;/* running counters (MCMove.statistics) */
+    int32_t moves_done;            /* moves completed by this call */
+    int32_t halt;                  /* 1: move number `moves_done` needs a neighbour-list rebuild and was not started */
+    int32_t nan_seen;              /* proposals rejected because u' was NaN (mcmc.py:417-430) */
+    int32_t reserved[5];
+} chx_mc_state;
+/* x0/x1: device (n,3) buffers; state_dev: device scratch of sizeof(chx_mc_state); state_host is
+ * uploaded first and holds the final state on return.  Synchronises once, at the end. */
+int chx_mc_displace_run(chx_ctx* ctx, const chx_mc_displace_args* args, float* x0, float* x1,
+                        chx_mc_state* state_dev, chx_mc_state* state_host, int n_moves);
+
 /* ---- Fused LJ Langevin engine (integrators.py:110-218 + neighbors.py + potential.py) -------------- */
 /* Runs whole trajectories on the device: cell-sorted particles, counting-sort cell list,
  * tiled neighbour structure, fused BAOAB(+wrap+check) kernel, device-side rebuild decision.

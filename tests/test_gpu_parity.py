@@ -2,6 +2,8 @@
 chiron's classes) against the CPU oracle on identical seeded inputs, and against the reference's
 golden vectors.  Bar: bit-exact for lists / masks / counts / PRNG bits; energies, forces and
 trajectories within rel 1e-5 (the tolerance BASELINE.json states for fp32), written in each test."""
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -632,3 +634,98 @@ def test_while_graph_loop_matches_chunked_loop(cuda_device, monkeypatch):
     assert a[3] >= 3 and a[3] == b[3] and a[4] == b[4]
     assert np.array_equal(a[2], b[2])
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[5], b[5])
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident Metropolis loop (csrc/mc.cu) == the reference-shaped step-by-step path
+# ---------------------------------------------------------------------------------------------------
+def _run_move_both_ways(make, n_moves, **move_kw):
+    """Run the same MonteCarloDisplacementMove through the device loop and step by step."""
+    from chiron_b200.mcmc import MonteCarloDisplacementMove
+    out = {}
+    for loop in (True, False):
+        state, ts, nl = make()
+        move = MonteCarloDisplacementMove(number_of_moves=n_moves, **copy.deepcopy(move_kw))  # autotune mutates sigma
+        move.device_loop = loop
+        s, _, nl_out = move.update(state, ts, nl)
+        out[loop] = (move.statistics, _np(s.positions), np.asarray(s._current_PRNG_key).copy(),
+                     move.number_of_attemps_made, move.displacement_sigma, nl_out)
+    return out
+
+
+@pytest.mark.parametrize("subset", [None, [5]])
+def test_mc_device_loop_matches_stepwise_lj(cuda_device, subset):
+    """LJ + NeighborListNsqrd: identical decisions, positions and key (the two paths share the proposal
+    arithmetic bit for bit; the reduced potentials differ by fp32 rounding only)."""
+    from chiron_b200 import unit
+
+    def make():
+        lj_sys, x, box, potential, state, ts, nl = _lj_langevin_setup(6, 0.8, seed=71, builder="nsq")
+        nl.build_from_state(state)
+        return state, ts, nl
+    sig = 0.0005 if subset is None else 0.02
+    out = _run_move_both_ways(make, 60, displacement_sigma=sig * unit.nanometer, atom_subset=subset)
+    a, b = out[True], out[False]
+    assert a[0] == b[0] and 0 < a[0]["n_accepted"] < 60 and a[0]["n_proposed"] == 60
+    assert np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2])
+    assert a[3] == b[3] == 60
+
+
+def test_mc_device_loop_halts_for_list_rebuilds_and_autotunes(cuda_device):
+    """A skin small enough that proposals trigger NeighborListNsqrd.check(): the loop stops before
+    those moves, they run through the building-block path (rebuild), and the sequence still equals the
+    step-by-step one; autotune fires at the same attempts."""
+    from chiron_b200 import unit
+
+    def make():
+        lj_sys, x, box, potential, state, ts, nl = _lj_langevin_setup(6, 0.8, seed=72, skin=0.004, builder="cell")
+        nl.build_from_state(state)
+        return state, ts, nl
+    out = _run_move_both_ways(make, 45, displacement_sigma=0.0005 * unit.nanometer, autotune=True,
+                              autotune_interval=10)
+    a, b = out[True], out[False]
+    assert a[0] == b[0] and 0 < a[0]["n_accepted"] < 45
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert float(a[4].value_in_unit(unit.nanometer)) == float(b[4].value_in_unit(unit.nanometer))
+    assert a[5].n_builds == b[5].n_builds and a[5].n_builds > 1
+    assert np.array_equal(_np(a[5].ref_positions), _np(b[5].ref_positions))
+
+
+def test_mc_device_loop_ho_and_ideal_gas(cuda_device):
+    """Harmonic oscillator (no list) and ideal gas (pair list, NPT reduced potential) displacement moves."""
+    from chiron_b200 import unit
+    from chiron_b200.neighbors import OrthogonalPeriodicSpace, PairListNsqrd
+    from chiron_b200.potential import HarmonicOscillatorPotential, IdealGasPotential
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import _topology
+    from chiron_b200.utils import PRNG
+
+    def make_ho():
+        PRNG.set_seed(1234)
+        pot_ho = HarmonicOscillatorPotential(_topology(5), k=100.0 * unit.kilocalories_per_mole / unit.angstrom ** 2,
+                                             x0=np.zeros((5, 3)) * unit.angstrom)
+        x = np.linspace(-0.01, 0.01, 15).reshape(5, 3).astype(f32)
+        state = SamplerState(positions=x * unit.nanometer, current_PRNG_key=PRNG.get_random_key())
+        return state, ThermodynamicState(pot_ho, temperature=300 * unit.kelvin), None
+    out = _run_move_both_ways(make_ho, 80, displacement_sigma=0.01 * unit.angstrom)
+    a, b = out[True], out[False]
+    assert a[0] == b[0] and 0 < a[0]["n_accepted"] < 80
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+    def make_ig():
+        PRNG.set_seed(1234)
+        rng = np.random.default_rng(3)
+        x = (rng.random((216, 3)) * 10).astype(f32)
+        state = SamplerState(positions=x * unit.nanometer, box_vectors=BOX10 * unit.nanometer,
+                             current_PRNG_key=PRNG.get_random_key())
+        ts = ThermodynamicState(IdealGasPotential(_topology(216)), temperature=298 * unit.kelvin,
+                                pressure=1.0 * unit.atmosphere)
+        nl = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=0 * unit.nanometer)
+        nl.build_from_state(state)
+        return state, ts, nl
+    out = _run_move_both_ways(make_ig, 25, displacement_sigma=0.1 * unit.nanometer)
+    a, b = out[True], out[False]
+    assert a[0] == b[0] == dict(n_accepted=25, n_proposed=25)     # U = 0: every proposal is accepted
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[1].min() >= 0 and a[1].max() < 10                      # wrapped into the box
