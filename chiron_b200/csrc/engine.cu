@@ -38,13 +38,13 @@
 struct MdRep {            // per replica control block
     uint32_t key[2][2];   // loop key of step s in key[s & 1] (integrators.py:179), written two steps ahead
     uint32_t sub[2][2];   // subkey of step s (the noise key) in sub[s & 1], written one step ahead
-    int user_step;        // last step at which the reference rebuild condition fired
+    int user_step[2];     // user_step[s & 1] = s: the reference rebuild condition fired in the BAOAB update of step s
     int user_rebuilds;
     float kT;
     int lo;               // first step this replica executes in the current pass
     int halt;             // first step whose BAOAB update invalidated the tables (HALT_NONE = none)
     int flag;             // 1 = takes part in the current rebuild / force-redo pass
-    int redo_step;        // step whose forces the redo pass evaluates
+    int fs_valid;         // run start: fs holds the forces of the current positions (step 0 skips the tile loop)
     int overflow;         // table or queue capacity exceeded during the last build
     unsigned long long cand_pairs2;  // mask bits set by the last build (= 2 * candidate pairs)
     unsigned long long int_pairs2;   // directed interacting pairs seen by the last energy kernel
@@ -66,6 +66,7 @@ struct chx_ljmd {
     MdGeom g;
     int R;
     float4 *xs, *vs, *refu, *fs, *refi;
+    float4* xs_b;                    // positions after odd steps inside a run (step s reads buffer s & 1)
     float4 *xs_t, *vs_t, *ru_t, *fs_t;   // gather targets of the sort
     int *lin2h, *h2lin;              // Hilbert rank of a cell / its inverse
     int *cell_count, *cell_start, *cell_of, *order;
@@ -87,14 +88,9 @@ struct chx_ljmd {
     bool tables_fresh;               // the tables were built and no step has run since
     int* step_base;                  // device int: first step of the chunk a graph replay runs
     cudaStream_t cap_stream;
-    cudaGraphExec_t chunk_graph;     // CH x (BAOAB, force) captured once; re-captured when the table shape changes
+    cudaGraphExec_t chunk_graph;     // CH fused steps captured once; re-captured when the table shape changes
     int chunk_graph_tcap, chunk_graph_lw, chunk_graph_ch;
-    // single-system runs: one graph with a device-side WHILE node, body = (BAOAB, force, loop control);
-    // the loop leaves when the run is complete or the tables went stale, no launch is ever wasted
-    cudaGraphExec_t while_graph;
-    int while_graph_tcap, while_graph_lw;
-    int* loop_end;                   // device int: first step the WHILE loop must not execute
-    bool use_while;
+    bool forces_valid;               // fs = F(current positions): set_state and the end of every run
     bool no_graph;                   // CHX_MD_NOGRAPH=1: launch every kernel directly
 };
 
@@ -818,18 +814,24 @@ struct LjConst {
 };
 
 // which replicas / which step a force launch serves
-#define FMODE_STEP 0   // step s of the loop: replicas with lo <= s < halt
-#define FMODE_REDO 1   // after a rebuild: replicas with flag set, step = rep.redo_step
-#define FMODE_ALL  2   // every replica, no step (set_state, energy(), force_only)
+#define FMODE_STEP  0  // fused step s: forces of x_s, then the BAOAB update to x_{s+1}; replicas with lo <= s < halt
+#define FMODE_FINAL 1  // forces of x_n after the last step (every replica), with step n's bookkeeping, no update
+#define FMODE_ALL   2  // every replica, no step (set_state, energy(), force_only)
 
 #ifndef CHX_FW
 #define CHX_FW 1
 #endif
 #ifndef CHX_TILE_PREFETCH
-#define CHX_TILE_PREFETCH 1
+#define CHX_TILE_PREFETCH 0   // L1 prefetch of the tile after next: measured neutral (profiles/r01_flag_tune.log)
 #endif
 #ifndef CHX_TRIP_UNROLL
 #define CHX_TRIP_UNROLL 1
+#endif
+#ifndef CHX_NEAR3
+#define CHX_NEAR3 1           // one FMNMX3 instead of two FMNMX for the cutoff-band tracker
+#endif
+#ifndef CHX_FSET_MASK
+#define CHX_FSET_MASK 1       // FSET + packed multiply instead of FSETP + FSEL: 34 instead of 37 instructions per packed trip
 #endif
 constexpr int kTripUnroll = CHX_TRIP_UNROLL;   // unroll factor of the packed trip loop
 #define FW CHX_FW  // warps per CTA in the force kernel
@@ -957,15 +959,27 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
                     r2 = __ffma2_rn(dy, dy, r2);
                     r2 = __ffma2_rn(dz, dz, r2);
                     const float2 off = __fadd2_rn(r2, negmid);
+#if CHX_NEAR3
+                    near2.x = fminf(fminf(near2.x, fabsf(off.x)), fabsf(off.y));   // FMNMX3 on sm_100
+#else
                     near2.x = fminf(near2.x, fabsf(off.x));
                     near2.y = fminf(near2.y, fabsf(off.y));
+#endif
                     const bool in0 = r2.x < lj.rc2_lo, in1 = r2.y < lj.rc2_lo;
                     float2 inv;
                     inv.x = rcp_approx(r2.x); inv.y = rcp_approx(r2.y);
                     const float2 inv3 = __fmul2_rn(__fmul2_rn(inv, inv), inv);
+#if CHX_FSET_MASK
+                    // cutoff as a 1.0 / 0.0 factor (FSET) folded into the packed multiply chain:
+                    // one instruction less than two FSETP + two FSEL
+                    float2 msk;
+                    msk.x = in0 ? 1.0f : 0.0f; msk.y = in1 ? 1.0f : 0.0f;
+                    const float2 f = __fmul2_rn(__fmul2_rn(__fmul2_rn(inv, msk), inv3), __ffma2_rn(c12f, inv3, c6f));
+#else
                     float2 f = __fmul2_rn(__fmul2_rn(inv, inv3), __ffma2_rn(c12f, inv3, c6f));
                     f.x = in0 ? f.x : 0.f;
                     f.y = in1 ? f.y : 0.f;
+#endif
                     fx2 = __ffma2_rn(f, dx, fx2); fy2 = __ffma2_rn(f, dy, fy2); fz2 = __ffma2_rn(f, dz, fz2);
                     if (ENERGY) {
                         const float2 c12e = make_float2(lj.c12e, lj.c12e), c6e = make_float2(-lj.c6e, -lj.c6e);
@@ -1016,183 +1030,194 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
     if (ENERGY) e_acc += e2.x + e2.y;
 }
 
+// The step kernel.  One launch = one Langevin step: forces of the current positions x_s over the
+// tiles, then -- for the warp's own 32 particles, with the forces still in registers -- the trailing
+// B of step s-1, B-A-O-A of step s (integrators.py:174-195), wrap, and both rebuild checks.  The new
+// positions go to the OTHER position buffer (step s reads buffer s & 1, writes buffer (s+1) & 1),
+// because the other warps of this launch are still reading x_s.  Nothing round-trips HBM between
+// the force evaluation and the sub-steps, and there is no separate integrator launch.
+//
 // SPLIT warps of a CTA share one block: warp w takes tiles w, w + SPLIT, ... and the partial forces
 // are summed through shared memory in warp order (deterministic).  SPLIT = 1 is one warp per block;
-// 2 or 4 gives small systems (few blocks per SM) enough warps to hide latency and shortens the tail
-// of the last wave on large ones.
+// 4 gives small systems (few blocks per SM) enough warps to hide latency.
+struct MdStepConst {
+    float h, a, b;               // dt/2, exp(-gamma dt), sqrt(1 - exp(-2 gamma dt))
+    float half_skin_user;        // reference rebuild condition d >= skin/2 (exact predicate)
+    float half_skin_int2;        // (internal skin / 2)^2
+};
+
 #define MD_FORCE_MAX_SPLIT 4
-template <bool ENERGY, int SPLIT>
+template <bool ENERGY, int SPLIT, bool UPDATE>
 __global__ void __launch_bounds__(SPLIT * 32, 32 / SPLIT)
-k_md_force(const float4* __restrict__ xs_all, float4* __restrict__ fs_all,
-           float4* __restrict__ refu_all, const uint32_t* __restrict__ tiles_all,
-           const int* __restrict__ ntiles_all, const uint8_t* __restrict__ generic_all,
-           const float4* __restrict__ bcenter_all, MdGeom g, LjConst lj, int tcap, int tstride,
-           MdRep* __restrict__ rep, int mode, int step_arg, const int* __restrict__ step_base,
-           int report_interval, int n_rep, double* __restrict__ energy_out) {
+k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, float4* __restrict__ fs_all,
+           float4* __restrict__ vs_all, float4* __restrict__ refu_all, const float4* __restrict__ refi_all,
+           const uint32_t* __restrict__ tiles_all, const int* __restrict__ ntiles_all,
+           const uint8_t* __restrict__ generic_all, const float4* __restrict__ bcenter_all, MdGeom g,
+           LjConst lj, MdStepConst sc, int tcap, int tstride, MdRep* __restrict__ rep, int mode, int step_arg,
+           const int* __restrict__ step_base, int report_interval, int n_rep, double* __restrict__ energy_out) {
     __shared__ double red[SPLIT];
     __shared__ unsigned long long redn[SPLIT];
     __shared__ float4 part[SPLIT > 1 ? SPLIT - 1 : 1][32];
     const int r = blockIdx.y;
-    int step = step_arg + (step_base ? *step_base : 0);   // graph replays read the chunk's first step
+    const int step = step_arg + (step_base ? *step_base : 0);   // graph replays read the chunk's first step
     if (mode == FMODE_STEP) {
-        // the tables are stale from step `halt` on: that step's forces are evaluated after the rebuild
+        // tables valid for x_lo .. x_{halt-1}; a halt raised by another warp of THIS launch is step + 1
         if (!(rep[r].lo <= step && step < *((volatile int*)&rep[r].halt))) return;
-    } else if (mode == FMODE_REDO) {
-        if (!rep[r].flag) return;
-        step = rep[r].redo_step;
     }
+    const bool odd = mode != FMODE_ALL && (step & 1);
+    const float4* xs_all = odd ? xs_b : xs_a;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x;
     float e_acc = 0.f;
     unsigned npair = 0;
     const float4* xs = xs_all + (size_t)r * g.np;
     const int i = b * 32 + lane;
+    const size_t o = (size_t)r * g.np + i;
     const float4 xi0 = xs[i];
     float4 xi = xi0;
-    if (w == 0 && step >= 0 && rep[r].user_step == step) {  // reference rebuild (neighbors.py:903-905 -> build)
-        refu_all[(size_t)r * g.np + i] = xi0;
-        if (b == 0 && lane == 0) rep[r].user_rebuilds++;
-    }
-    const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * (size_t)(tcap + TILE_PAD) * tstride +
-                         (size_t)w * tstride;
-    const bool lw2 = tstride == 96;
-    const int nt_all = ntiles_all[(size_t)r * g.nblk + b];
-    const int nt = (nt_all - w + SPLIT - 1) / SPLIT;      // tiles w, w + SPLIT, ... < nt_all
-    const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
-    const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
-    float fx = 0.f, fy = 0.f, fz = 0.f;
-    if (gen) {
-        md_tile_loop<ENERGY, true, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
-    } else {
-        xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
-        xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
-        xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
-        if (lw2)
-            md_tile_loop<ENERGY, false, true, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
-        else
-            md_tile_loop<ENERGY, false, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
-    }
-    if (SPLIT > 1) {
-        if (w > 0) part[w - 1][lane] = make_float4(fx, fy, fz, e_acc);
-        __syncthreads();
+    // reference rebuild (neighbors.py:903-905 -> build): the update of step - 1 found a particle
+    // skin/2 away from the reference positions, so x_step becomes the new reference
+    bool took_ref = false;
+    if (mode != FMODE_ALL && step >= 1 && rep[r].user_step[(step - 1) & 1] == step - 1) {
+        took_ref = true;
         if (w == 0) {
-            float es = e_acc;
-#pragma unroll
-            for (int k = 0; k < SPLIT - 1; ++k) {
-                const float4 q = part[k][lane];
-                fx += q.x; fy += q.y; fz += q.z; es += q.w;
-            }
-            fs_all[(size_t)r * g.np + i] = make_float4(fx, fy, fz, 0.5f * es);
+            refu_all[o] = xi0;
+            if (b == 0 && lane == 0) rep[r].user_rebuilds++;
         }
+    }
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (UPDATE && step == 0 && rep[r].fs_valid) {
+        // first step of a run: set_state / the previous run left F(x_0) in fs
+        if (w == 0) { const float4 f0 = fs_all[o]; fx = f0.x; fy = f0.y; fz = f0.z; }
     } else {
-        fs_all[(size_t)r * g.np + i] = make_float4(fx, fy, fz, 0.5f * e_acc);
-    }
-    if (ENERGY) {
-        double e = warp_sum((double)e_acc * 0.5);
-        int np = warp_sum((int)npair);
-        if (lane == 0) { red[w] = e; redn[w] = (unsigned long long)np; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double s = 0.0;
-            unsigned long long c = 0;
-            for (int k = 0; k < SPLIT; ++k) { s += red[k]; c += redn[k]; }
-            double* slot = nullptr;
-            if (energy_out) {
-                if (mode == FMODE_ALL) slot = energy_out + r;
-                else if (report_interval > 0 && step >= 0 && step % report_interval == 0)
-                    slot = energy_out + (size_t)(step / report_interval) * n_rep + r;
+        const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * (size_t)(tcap + TILE_PAD) * tstride +
+                             (size_t)w * tstride;
+        const bool lw2 = tstride == 96;
+        const int nt_all = ntiles_all[(size_t)r * g.nblk + b];
+        const int nt = (nt_all - w + SPLIT - 1) / SPLIT;      // tiles w, w + SPLIT, ... < nt_all
+        const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
+        const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
+        if (gen) {
+            md_tile_loop<ENERGY, true, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+        } else {
+            xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
+            xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
+            xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
+            if (lw2)
+                md_tile_loop<ENERGY, false, true, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+            else
+                md_tile_loop<ENERGY, false, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+        }
+        if (SPLIT > 1) {
+            if (w > 0) part[w - 1][lane] = make_float4(fx, fy, fz, e_acc);
+            __syncthreads();
+            if (w == 0) {
+                float es = e_acc;
+#pragma unroll
+                for (int k = 0; k < SPLIT - 1; ++k) {
+                    const float4 q = part[k][lane];
+                    fx += q.x; fy += q.y; fz += q.z; es += q.w;
+                }
+                fs_all[o] = make_float4(fx, fy, fz, 0.5f * es);
             }
-            if (slot && s != 0.0) atomicAdd(slot, s);
-            if (c) atomicAdd(&rep[r].int_pairs2, c);
+        } else {
+            fs_all[o] = make_float4(fx, fy, fz, 0.5f * e_acc);
+        }
+        if (ENERGY) {
+            double e = warp_sum((double)e_acc * 0.5);
+            int np = warp_sum((int)npair);
+            if (lane == 0) { red[w] = e; redn[w] = (unsigned long long)np; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double s = 0.0;
+                unsigned long long c = 0;
+                for (int k = 0; k < SPLIT; ++k) { s += red[k]; c += redn[k]; }
+                double* slot = nullptr;
+                if (energy_out) {
+                    // the energy after step s - 1 (integrators.py:197-205) is the energy of x_s
+                    if (mode == FMODE_ALL) slot = energy_out + r;
+                    else if (report_interval > 0 && step >= 1 && (step - 1) % report_interval == 0)
+                        slot = energy_out + (size_t)((step - 1) / report_interval) * n_rep + r;
+                }
+                if (slot && s != 0.0) atomicAdd(slot, s);
+                if (c) atomicAdd(&rep[r].int_pairs2, c);
+            }
         }
     }
-}
+    if (!UPDATE || w != 0) return;
 
-// ---------------------------------------------------------------------------------------------
-// fused BAOAB (+ trailing B of the previous step) + wrap + both rebuild checks
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_md_baoab(float4* __restrict__ xs_all, float4* __restrict__ vs_all, const float4* __restrict__ fs_all,
-           const float4* __restrict__ refi_all, const float4* __restrict__ refu_all, MdGeom g,
-           float h, float a, float b, float half_skin_user, float half_skin_int2, int step_arg,
-           const int* __restrict__ step_base, MdRep* __restrict__ rep) {
-    const int r = blockIdx.y;
-    const int step = step_arg + (step_base ? *step_base : 0);
-    // a halt raised by ANOTHER block of this same launch (halt == step) must not stop us
-    if (!(rep[r].lo <= step && step <= *((volatile int*)&rep[r].halt))) return;
+    // ---- BAOAB update of the warp's own particles: x_step -> x_{step+1} (other buffer) ----
     // the noise key of this step was prepared by the previous launch; one thread prepares the next:
     // (key(s+2), subkey(s+1)) = split(key(s+1)) -- nobody in this launch reads the slots it writes
     const uint32_t sk0 = rep[r].sub[step & 1][0], sk1 = rep[r].sub[step & 1][1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (b == 0 && lane == 0) {
         uint32_t c0, c1, s0, s1;
         threefry_split(rep[r].key[(step + 1) & 1][0], rep[r].key[(step + 1) & 1][1], c0, c1, s0, s1);
         rep[r].key[step & 1][0] = c0; rep[r].key[step & 1][1] = c1;
         rep[r].sub[(step + 1) & 1][0] = s0; rep[r].sub[(step + 1) & 1][1] = s1;
     }
-    const int trailing = step > 0;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float4* xn_all = const_cast<float4*>(odd ? xs_a : xs_b);
+    const int id = __float_as_int(xi0.w);
     bool moved_int = false, moved_user = false;
-    if (i < g.np) {
-        const size_t o = (size_t)r * g.np + i;
-        float4 x = xs_all[o];
-        const int id = __float_as_int(x.w);
-        if (id >= 0) {
-            float4 v = vs_all[o];
-            const float4 f = fs_all[o];
-            const float m = v.w;
-            const float kT = rep[r].kT;
-            const float bs = __fmul_rn(b, __fsqrt_rn(__fdiv_rn(kT, m)));
-            const unsigned long long total = 3ull * (unsigned long long)g.n;
-            const uint32_t k0 = sk0, k1 = sk1;
-            float xc[3] = {x.x, x.y, x.z}, vc[3] = {v.x, v.y, v.z};
-            const float fc[3] = {f.x, f.y, f.z};
-            const float L[3] = {g.box.lx, g.box.ly, g.box.lz};
+    if (id < 0) {
+        xn_all[o] = xi0;                      // padding slot: present in both buffers
+    } else {
+        float4 v = vs_all[o];
+        const float m = v.w;
+        const float kT = rep[r].kT;
+        const float bs = __fmul_rn(sc.b, __fsqrt_rn(__fdiv_rn(kT, m)));
+        const unsigned long long total = 3ull * (unsigned long long)g.n;
+        const bool trailing = step > 0;
+        float xc[3] = {xi0.x, xi0.y, xi0.z}, vc[3] = {v.x, v.y, v.z};
+        const float fc[3] = {fx, fy, fz};
+        const float L[3] = {g.box.lx, g.box.ly, g.box.lz};
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float kick = __fdiv_rn(__fmul_rn(h, fc[c]), m);
-                if (trailing) vc[c] = __fadd_rn(vc[c], kick);
-                vc[c] = __fadd_rn(vc[c], kick);
-                xc[c] = __fadd_rn(xc[c], __fmul_rn(h, vc[c]));
-                const float xi = normal_from_bits(random_bits_elem(k0, k1, 3ull * id + c, total));
-                vc[c] = __fadd_rn(__fmul_rn(a, vc[c]), __fmul_rn(bs, xi));
-                xc[c] = __fadd_rn(xc[c], __fmul_rn(h, vc[c]));
-                xc[c] = ref_wrap(xc[c], L[c]);
-            }
-            xs_all[o] = make_float4(xc[0], xc[1], xc[2], x.w);
-            vs_all[o] = make_float4(vc[0], vc[1], vc[2], m);
-            // reference rebuild condition (exact, neighbors.py:864-868)
-            const float4 ru = refu_all[o];
-            float rx, ry, rz, d;
-            ref_displacement<true>(xc[0], xc[1], xc[2], ru.x, ru.y, ru.z, g.box, rx, ry, rz, d);
-            moved_user = d >= half_skin_user;
-            // engine's own list validity (fast min-image)
-            const float4 ri = refi_all[o];
-            float dx = xc[0] - ri.x, dy = xc[1] - ri.y, dz = xc[2] - ri.z;
-            dx -= g.box.lx * rintf(dx * g.inv_lx);
-            dy -= g.box.ly * rintf(dy * g.inv_ly);
-            dz -= g.box.lz * rintf(dz * g.inv_lz);
-            moved_int = dx * dx + dy * dy + dz * dz >= half_skin_int2;
+        for (int c = 0; c < 3; ++c) {
+            const float kick = __fdiv_rn(__fmul_rn(sc.h, fc[c]), m);
+            if (trailing) vc[c] = __fadd_rn(vc[c], kick);                      // B of step - 1
+            vc[c] = __fadd_rn(vc[c], kick);                                    // B
+            xc[c] = __fadd_rn(xc[c], __fmul_rn(sc.h, vc[c]));                  // A
+            const float xi_n = normal_from_bits(random_bits_elem(sk0, sk1, 3ull * id + c, total));
+            vc[c] = __fadd_rn(__fmul_rn(sc.a, vc[c]), __fmul_rn(bs, xi_n));    // O
+            xc[c] = __fadd_rn(xc[c], __fmul_rn(sc.h, vc[c]));                  // A
+            xc[c] = ref_wrap(xc[c], L[c]);
         }
+        xn_all[o] = make_float4(xc[0], xc[1], xc[2], xi0.w);
+        vs_all[o] = make_float4(vc[0], vc[1], vc[2], m);
+        // reference rebuild condition (exact, neighbors.py:864-868)
+        const float4 ru = took_ref ? xi0 : refu_all[o];
+        float rx, ry, rz, d;
+        ref_displacement<true>(xc[0], xc[1], xc[2], ru.x, ru.y, ru.z, g.box, rx, ry, rz, d);
+        moved_user = d >= sc.half_skin_user;
+        // engine's own list validity (fast min-image)
+        const float4 ri = refi_all[o];
+        float dx = xc[0] - ri.x, dy = xc[1] - ri.y, dz = xc[2] - ri.z;
+        dx -= g.box.lx * rintf(dx * g.inv_lx);
+        dy -= g.box.ly * rintf(dy * g.inv_ly);
+        dz -= g.box.lz * rintf(dz * g.inv_lz);
+        moved_int = dx * dx + dy * dy + dz * dz >= sc.half_skin_int2;
     }
-    // rare events (a rebuild every few dozen steps): warp vote, then straight to the control block
+    // rare events (a rebuild every few dozen steps): warp vote, then straight to the control block.
+    // halt = first step that must not run on these tables; user_step[] is read by the NEXT launch
     const unsigned ev = __reduce_or_sync(FULL, (moved_int ? 1u : 0u) | (moved_user ? 2u : 0u));
-    if ((threadIdx.x & 31) == 0 && ev) {
-        if (ev & 1u) atomicMin(&rep[r].halt, step);
-        if (ev & 2u) rep[r].user_step = step;
+    if (lane == 0 && ev) {
+        if (ev & 1u) atomicMin(&rep[r].halt, step + 1);
+        if (ev & 2u) rep[r].user_step[step & 1] = step;
     }
 }
 
 __global__ void k_md_setbase(int* base, int value) { *base = value; }
-__global__ void k_md_setloop(int* base, int* end, int first, int last) { *base = first; *end = last; }
 
-// last kernel of the WHILE body (single replica): advance the step, go on while the run is not
-// complete and the tables are still valid
-__global__ void k_md_loopctl(cudaGraphConditionalHandle handle, int* __restrict__ base,
-                             const int* __restrict__ end, const MdRep* __restrict__ rep) {
-    const int s = *base + 1;
-    *base = s;
-    const bool go = s < *end && *((volatile const int*)&rep[0].halt) == HALT_NONE;
-    cudaGraphSetConditional(handle, go ? 1u : 0u);
+// flagged replicas that resume at an odd step keep their current positions in buffer B: the rebuild
+// kernels work on buffer A, so copy B -> A before the sort and A -> B after it
+__global__ void k_md_sync_odd(MdGeom g, const MdRep* __restrict__ rep, const float4* __restrict__ src,
+                              float4* __restrict__ dst) {
+    const int r = blockIdx.y;
+    if (!rep[r].flag || !(rep[r].lo & 1)) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.np) return;
+    const size_t o = (size_t)r * g.np + p;
+    dst[o] = src[o];
 }
 
 __global__ void k_md_scale_v(float4* __restrict__ vs, int np, float sc) {
@@ -1230,6 +1255,8 @@ static inline size_t md_tiles_bytes(const chx_ljmd* md) {
 static int md_alloc(chx_ljmd* md) {
     const size_t np = (size_t)md->R * md->g.np;
     CHX_CUDA(cudaMalloc(&md->xs, np * sizeof(float4)));
+    CHX_CUDA(cudaMalloc(&md->xs_b, np * sizeof(float4)));
+    CHX_CUDA(cudaMemset(md->xs_b, 0, np * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->vs, np * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->refu, np * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->xs_t, np * sizeof(float4)));
@@ -1261,8 +1288,6 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->rep, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMalloc(&md->step_base, sizeof(int)));
     md->chunk_graph = nullptr; md->chunk_graph_tcap = -1; md->chunk_graph_lw = -1; md->cap_stream = nullptr;
-    md->while_graph = nullptr; md->while_graph_tcap = -1; md->while_graph_lw = -1;
-    CHX_CUDA(cudaMalloc(&md->loop_end, sizeof(int)));
     CHX_CUDA(cudaMallocHost(&md->rep_host, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMemset(md->rep, 0, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMemset(md->fs, 0, np * sizeof(float4)));
@@ -1319,12 +1344,16 @@ static size_t md_build_smem(int nw, int qcap) { return (size_t)nw * (512 + 8 * (
 
 // sort + table build for the replicas whose rep_host[r].flag is set (rep_host must already be
 // uploaded); grows the table capacity on overflow.  Leaves rep_host refreshed.
-static int md_rebuild(chx_ljmd* md) {
+static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
     chx_ctx* ctx = md->ctx;
     const MdGeom& g = md->g;
     cudaStream_t st = ctx->stream;
     const int R = md->R;
     const dim3 gp(chx_div_up(g.np, 256), R);
+    if (odd_possible) {
+        k_md_sync_odd<<<gp, 256, 0, st>>>(g, md->rep, md->xs_b, md->xs);
+        CHX_LAUNCHED(ctx);
+    }
     k_md_cellcount<<<gp, 256, 0, st>>>(md->xs, g, md->lin2h, md->rep, md->cell_of, md->cell_count);
     CHX_LAUNCHED(ctx);
     k_md_scan<<<R, 1024, 0, st>>>(md->cell_count, md->cell_start, md->cell_range, md->h2lin, g.ncell, md->rep);
@@ -1340,6 +1369,10 @@ static int md_rebuild(chx_ljmd* md) {
     k_md_adopt<<<gp, 256, 0, st>>>(g, md->rep, md->xs_t, md->vs_t, md->ru_t, md->fs_t, md->xs, md->vs, md->refu,
                                    md->fs, md->refi);
     CHX_LAUNCHED(ctx);
+    if (odd_possible) {
+        k_md_sync_odd<<<gp, 256, 0, st>>>(g, md->rep, md->xs, md->xs_b);
+        CHX_LAUNCHED(ctx);
+    }
     const float R_list = md->p.cutoff + md->internal_skin;
     bool regrown = false;
     for (int attempt = 0; attempt < 10; ++attempt) {
@@ -1428,18 +1461,40 @@ static int md_force_split(const chx_ljmd* md) {
     return warps >= slots ? 1 : 4;
 }
 
+static MdStepConst md_step_const(const chx_ljmd* md) {
+    MdStepConst c;
+    const float dt = md->p.dt, gamma = md->p.gamma;
+    c.h = dt * 0.5f;
+    c.a = (float)exp((double)(float)(-gamma * dt));
+    const float e2 = (float)exp((double)(float)(-2.0f * gamma * dt));
+    c.b = sqrtf(1.0f - e2);
+    c.half_skin_user = (float)((double)md->p.skin / 2.0);
+    const float hs_int = 0.5f * md->internal_skin;
+    c.half_skin_int2 = hs_int * hs_int;
+    return c;
+}
+
+// FMODE_STEP launches the fused step (forces + BAOAB update); the other modes evaluate forces only
 static int md_force(chx_ljmd* md, int mode, int step, bool energy, int report_interval, double* e_dev,
                     const int* step_base = nullptr) {
     const MdGeom& g = md->g;
     const dim3 gf(g.nblk, md->R);
     const int split = md_force_split(md);
-#define MD_FORCE_LAUNCH(E, S)                                                                       \
-    k_md_force<E, S><<<gf, S * 32, 0, md->ctx->stream>>>(                                            \
-        md->xs, md->fs, md->refu, md->tiles, md->ntiles, md->generic, md->bcenter, g, md_lj(md),    \
-        md->tcap, md_tstride(md), md->rep, mode, step, step_base, report_interval, md->R, e_dev)
-    if (split == 1) { if (energy) MD_FORCE_LAUNCH(true, 1); else MD_FORCE_LAUNCH(false, 1); }
-    else if (split == 2) { if (energy) MD_FORCE_LAUNCH(true, 2); else MD_FORCE_LAUNCH(false, 2); }
-    else { if (energy) MD_FORCE_LAUNCH(true, 4); else MD_FORCE_LAUNCH(false, 4); }
+    const bool upd = mode == FMODE_STEP;
+#define MD_FORCE_LAUNCH(E, S, U)                                                                    \
+    k_md_force<E, S, U><<<gf, S * 32, 0, md->ctx->stream>>>(                                         \
+        md->xs, md->xs_b, md->fs, md->vs, md->refu, md->refi, md->tiles, md->ntiles, md->generic,   \
+        md->bcenter, g, md_lj(md), md_step_const(md), md->tcap, md_tstride(md), md->rep, mode, step, \
+        step_base, report_interval, md->R, e_dev)
+#define MD_FORCE_SPLIT(S)                                                                           \
+    do {                                                                                            \
+        if (upd) { if (energy) MD_FORCE_LAUNCH(true, S, true); else MD_FORCE_LAUNCH(false, S, true); } \
+        else { if (energy) MD_FORCE_LAUNCH(true, S, false); else MD_FORCE_LAUNCH(false, S, false); } \
+    } while (0)
+    if (split == 1) MD_FORCE_SPLIT(1);
+    else if (split == 2) MD_FORCE_SPLIT(2);
+    else MD_FORCE_SPLIT(4);
+#undef MD_FORCE_SPLIT
 #undef MD_FORCE_LAUNCH
     CHX_LAUNCHED(md->ctx);
     return CHX_OK;
@@ -1498,9 +1553,8 @@ int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
         md->lw = lw <= 2 ? 2 : (lw <= 4 ? 4 : 6);   // even: the force loop reads list words in pairs
     }
     md->qcap = ((int)(2.5 * cand) + 256 + 31) & ~31;
-    md->rebuilds = 0; md->steps = 0; md->have_state = false;
+    md->rebuilds = 0; md->steps = 0; md->have_state = false; md->forces_valid = false;
     { const char* e = getenv("CHX_MD_NOGRAPH"); md->no_graph = e && e[0] == '1'; }
-    { const char* e = getenv("CHX_MD_WHILE"); md->use_while = e ? e[0] == '1' : false; }
     md->launches0 = ctx->launches;
     int rc = md_alloc(md);
     if (rc != CHX_OK) { delete md; return rc; }
@@ -1518,8 +1572,7 @@ int chx_ljmd_destroy(chx_ljmd* md) {
     cudaFree(md->cand_idx); cudaFree(md->cand_col); cudaFree(md->cand_n); cudaFree(md->memb); cudaFree(md->tmeta);
     cudaFree(md->generic); cudaFree(md->bcenter); cudaFree(md->rep); cudaFree(md->step_base);
     if (md->chunk_graph) cudaGraphExecDestroy(md->chunk_graph);
-    if (md->while_graph) cudaGraphExecDestroy(md->while_graph);
-    cudaFree(md->loop_end);
+    cudaFree(md->xs_b);
     if (md->cap_stream) cudaStreamDestroy(md->cap_stream);
     cudaFreeHost(md->rep_host);
     delete md;
@@ -1535,11 +1588,10 @@ int chx_ljmd_set_state(chx_ljmd* md, const float* x, const float* v, const float
     for (int r = 0; r < md->R; ++r) {
         md->rep_host[r] = MdRep();
         md->rep_host[r].kT = kT_per_replica_host ? kT_per_replica_host[r] : md->p.kT;
-        md->rep_host[r].user_step = -1;
+        md->rep_host[r].user_step[0] = md->rep_host[r].user_step[1] = -1;
         md->rep_host[r].lo = 0;
         md->rep_host[r].halt = HALT_NONE;
         md->rep_host[r].flag = 1;
-        md->rep_host[r].redo_step = -2;
     }
     int rc = md_upload_rep(md);
     if (rc != CHX_OK) return rc;
@@ -1552,6 +1604,7 @@ int chx_ljmd_set_state(chx_ljmd* md, const float* x, const float* v, const float
     if (rc != CHX_OK) return rc;
     md->have_state = true;
     md->tables_fresh = true;
+    md->forces_valid = true;
     return CHX_OK;
 }
 
@@ -1580,7 +1633,8 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     const int n_reports = report ? (nsteps + report_interval - 1) / report_interval : 0;
     CHX_REQUIRE(!report || n_reports <= n_reports_capacity, "energy buffer too small");
     const int rint = report ? report_interval : 0;
-    // upload loop keys (parity 0), reset per-run control
+    // upload loop keys (parity 0), reset per-run control.  Step s of this run reads the positions
+    // from buffer s & 1 (x_0 is in md->xs) and writes x_{s+1} to the other one.
     int rc = md_download_rep(md);
     if (rc != CHX_OK) return rc;
     for (int r = 0; r < R; ++r) {
@@ -1588,38 +1642,30 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
         q.key[0][0] = keys_host[2 * r];
         q.key[0][1] = keys_host[2 * r + 1];
         threefry_split(q.key[0][0], q.key[0][1], q.key[1][0], q.key[1][1], q.sub[0][0], q.sub[0][1]);
-        q.user_step = -1;
-        q.lo = 0; q.halt = HALT_NONE; q.flag = 0; q.redo_step = -2;
+        q.user_step[0] = q.user_step[1] = -1;
+        q.lo = 0; q.halt = HALT_NONE; q.flag = 0;
+        q.fs_valid = md->forces_valid ? 1 : 0;
     }
     rc = md_upload_rep(md);
     if (rc != CHX_OK) return rc;
     if (report) CHX_CUDA(cudaMemsetAsync(energies_dev, 0, sizeof(double) * R * n_reports, st));
+    md->forces_valid = false;
 
-    const float dt = md->p.dt, gamma = md->p.gamma;
-    const float h = dt * 0.5f;
-    const float a = (float)exp((double)(float)(-gamma * dt));
-    const float e2 = (float)exp((double)(float)(-2.0f * gamma * dt));
-    const float bcoef = sqrtf(1.0f - e2);
-    const float hs_user = (float)((double)md->p.skin / 2.0);
-    const float hs_int = 0.5f * md->internal_skin;
-    const float hs_int2 = hs_int * hs_int;
-    const dim3 gb(chx_div_up(g.np, 256), R);
-    int CH = R > 1 ? 50 : 32;   // steps per graph replay / host check (CHX_MD_CHUNK overrides)
+    int CH = R > 1 ? 50 : 32;   // steps per graph replay / host check (CHX_MD_CHUNK overrides; even)
     { const char* e = getenv("CHX_MD_CHUNK"); if (e && atoi(e) > 0) CH = atoi(e); }
+    CH += CH & 1;
 
+    // the energy after step s - 1 is evaluated by the launch of step s (forces of x_s)
+    auto wants_energy = [&](int s) { return report && s >= 1 && (s - 1) % report_interval == 0; };
     auto launch_steps = [&](int s0, int s1, const int* base) -> int {
         for (int s = s0; s < s1; ++s) {
-            k_md_baoab<<<gb, 256, 0, ctx->stream>>>(md->xs, md->vs, md->fs, md->refi, md->refu, g, h, a,
-                                                    bcoef, hs_user, hs_int2, s, base, md->rep);
-            CHX_LAUNCHED(ctx);
-            const bool en = report && (s % report_interval == 0);
-            int rc2 = md_force(md, FMODE_STEP, s, en, rint, energies_dev, base);
+            int rc2 = md_force(md, FMODE_STEP, s, wants_energy(s), rint, energies_dev, base);
             if (rc2 != CHX_OK) return rc2;
         }
         return CHX_OK;
     };
-    // full chunks without energy reports replay one CUDA graph of CH x (BAOAB, force): the kernels
-    // read the chunk's first step from device memory, so the same graph serves every chunk
+    // full chunks without energy reports replay one CUDA graph of CH fused steps: the kernels read
+    // the chunk's first step (even, so the buffer roles are the captured ones) from device memory
     const bool use_graph = !report && !md->no_graph;
     auto launch_chunk_graph = [&](int s0) -> int {
         if (md->chunk_graph && (md->chunk_graph_tcap != md->tcap || md->chunk_graph_lw != md->lw || md->chunk_graph_ch != CH)) {
@@ -1649,155 +1695,84 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
         k_md_setbase<<<1, 1, 0, st>>>(md->step_base, s0);
         CHX_LAUNCHED(ctx);
         CHX_CUDA(cudaGraphLaunch(md->chunk_graph, st));
-        ctx->launches += 2 * CH;
+        ctx->launches += CH;
         return CHX_OK;
     };
-
-    // ---- single system, no energy reports: device-side WHILE loop ----
-    if (R == 1 && use_graph && md->use_while) {
-        auto ensure_while_graph = [&]() -> int {
-            if (md->while_graph && (md->while_graph_tcap != md->tcap || md->while_graph_lw != md->lw)) {
-                cudaGraphExecDestroy(md->while_graph);   // the graph bakes the table shape
-                md->while_graph = nullptr;
-            }
-            if (md->while_graph) return CHX_OK;
-            cudaGraph_t graph = nullptr;
-            CHX_CUDA(cudaGraphCreate(&graph, 0));
-            cudaGraphConditionalHandle handle;
-            CHX_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
-            cudaGraphNodeParams np_ = {};
-            np_.type = cudaGraphNodeTypeConditional;
-            np_.conditional.handle = handle;
-            np_.conditional.type = cudaGraphCondTypeWhile;
-            np_.conditional.size = 1;
-            cudaGraphNode_t node;
-            CHX_CUDA(cudaGraphAddNode(&node, graph, nullptr, 0, &np_));
-            cudaGraph_t body = np_.conditional.phGraph_out[0];
-            if (!md->cap_stream) CHX_CUDA(cudaStreamCreateWithFlags(&md->cap_stream, cudaStreamNonBlocking));
-            const long long l0 = ctx->launches;
-            CHX_CUDA(cudaStreamBeginCaptureToGraph(md->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-            ctx->stream = md->cap_stream;
-            const int rc2 = launch_steps(0, 1, md->step_base);
-            k_md_loopctl<<<1, 1, 0, md->cap_stream>>>(handle, md->step_base, md->loop_end, md->rep);
-            ctx->stream = st;
-            cudaGraph_t captured = nullptr;
-            const cudaError_t ce = cudaStreamEndCapture(md->cap_stream, &captured);
-            ctx->launches = l0;
-            if (rc2 != CHX_OK) { cudaGraphDestroy(graph); return rc2; }
-            CHX_CUDA(ce);
-            CHX_CUDA(cudaGraphInstantiate(&md->while_graph, graph, 0));
-            CHX_CUDA(cudaGraphDestroy(graph));
-            md->while_graph_tcap = md->tcap;
-            md->while_graph_lw = md->lw;
-            return CHX_OK;
-        };
-        int t = 0;
-        while (t < nsteps) {
-            rc = ensure_while_graph();
-            if (rc != CHX_OK) return rc;
-            k_md_setloop<<<1, 1, 0, st>>>(md->step_base, md->loop_end, t, nsteps);
-            CHX_LAUNCHED(ctx);
-            CHX_CUDA(cudaGraphLaunch(md->while_graph, st));
-            rc = md_download_rep(md);
-            if (rc != CHX_OK) return rc;
-            MdRep& q = md->rep_host[0];
-            const int done = q.halt < nsteps ? q.halt + 1 : nsteps;      // steps whose BAOAB update ran
-            ctx->launches += 3ll * (done - t);
-            md->tables_fresh = false;
-            if (q.halt < nsteps) {
-                // tables went stale at step `halt`: rebuild, evaluate that step's forces, go on after it
-                q.flag = 1; q.redo_step = q.halt; q.lo = q.halt + 1; q.halt = HALT_NONE;
-                q.overflow = 0; q.cand_pairs2 = 0; q.trip_slots = 0;
-                rc = md_upload_rep(md);
-                if (rc != CHX_OK) return rc;
-                rc = md_rebuild(md);
-                if (rc != CHX_OK) return rc;
-                rc = md_force(md, FMODE_REDO, -2, false, 0, nullptr);
-                if (rc != CHX_OK) return rc;
-                rc = md_download_rep(md);      // the redo updates the reference-rebuild bookkeeping on the device
-                if (rc != CHX_OK) return rc;
-                md->rep_host[0].flag = 0;
-                rc = md_upload_rep(md);
-                if (rc != CHX_OK) return rc;
-            }
-            t = done;
-        }
-        k_md_kick<<<chx_div_up((long long)R * g.np, 256), 256, 0, st>>>(md->vs, md->fs, g, h, R);
-        CHX_LAUNCHED(ctx);
-        rc = md_download_rep(md);
-        if (rc != CHX_OK) return rc;
-        keys_host[0] = md->rep_host[0].key[nsteps & 1][0];
-        keys_host[1] = md->rep_host[0].key[nsteps & 1][1];
-        md->steps += nsteps;
-        return CHX_OK;
-    }
+    auto clear_build_stats = [](MdRep& q) { q.overflow = 0; q.cand_pairs2 = 0; q.trip_slots = 0; };
 
     // Batched replicas go stale at different steps; waiting for each other inside a chunk and then
     // catching up one by one costs more than the tables themselves.  So with R > 1 every chunk starts
-    // on fresh tables for all replicas (forces are carried through the sort, nothing is re-evaluated),
-    // and a halt inside a chunk becomes the exception.  CHX_MD_PROACTIVE=0 disables it.
+    // on fresh tables for all replicas and a halt inside a chunk becomes the exception.
+    // CHX_MD_PROACTIVE=0 disables it.
     bool proactive = R > 1;
     { const char* e = getenv("CHX_MD_PROACTIVE"); if (e) proactive = e[0] == '1'; }
     int t = 0;
     while (t < nsteps) {
         const int te = nsteps - t < CH ? nsteps : t + CH;
         if (proactive && !(t == 0 && md->tables_fresh)) {
-            for (int r = 0; r < R; ++r) {
-                MdRep& q = md->rep_host[r];
-                q.flag = 1; q.overflow = 0; q.cand_pairs2 = 0; q.trip_slots = 0;
-            }
+            for (int r = 0; r < R; ++r) { md->rep_host[r].flag = 1; clear_build_stats(md->rep_host[r]); }
             rc = md_upload_rep(md);
             if (rc != CHX_OK) return rc;
-            rc = md_rebuild(md);
+            rc = md_rebuild(md, (t & 1) != 0);
             if (rc != CHX_OK) return rc;
             for (int r = 0; r < R; ++r) md->rep_host[r].flag = 0;
             rc = md_upload_rep(md);
             if (rc != CHX_OK) return rc;
         }
         md->tables_fresh = false;
-        rc = (use_graph && te - t == CH) ? launch_chunk_graph(t) : launch_steps(t, te, nullptr);
+        rc = (use_graph && te - t == CH && !(t & 1)) ? launch_chunk_graph(t) : launch_steps(t, te, nullptr);
         if (rc != CHX_OK) return rc;
         rc = md_download_rep(md);
         if (rc != CHX_OK) return rc;
-        // replicas whose tables went stale inside the chunk: rebuild, redo that step's forces, catch up
+        // replicas whose tables went stale inside the chunk (halt = first step that did not run):
+        // rebuild on x_halt and run the rest of the chunk.  halt == te needs tables for the next chunk
+        // (or for the final force evaluation); a proactive rebuild at the next chunk start covers it.
         for (;;) {
             int first = HALT_NONE;
+            bool any = false;
             for (int r = 0; r < R; ++r) {
                 MdRep& q = md->rep_host[r];
-                if (q.halt < te) {
-                    q.flag = 1; q.redo_step = q.halt; q.lo = q.halt + 1; q.halt = HALT_NONE;
-                    q.overflow = 0; q.cand_pairs2 = 0; q.trip_slots = 0;
-                    if (q.redo_step < first) first = q.redo_step;
+                const bool stale = q.halt <= te && !(q.halt == te && proactive && te < nsteps);
+                if (stale) {
+                    q.flag = 1; q.lo = q.halt; q.halt = HALT_NONE;
+                    clear_build_stats(q);
+                    if (q.lo < first) first = q.lo;
+                    any = true;
                 } else {
                     q.flag = 0; q.lo = HALT_NONE;   // done with this chunk
+                    if (q.halt <= te) q.halt = HALT_NONE;
                 }
             }
-            if (first == HALT_NONE) break;
+            if (!any) break;
             rc = md_upload_rep(md);
             if (rc != CHX_OK) return rc;
-            rc = md_rebuild(md);
+            rc = md_rebuild(md, true);
             if (rc != CHX_OK) return rc;
-            rc = md_force(md, FMODE_REDO, -2, report, rint, energies_dev);
-            if (rc != CHX_OK) return rc;
-            rc = launch_steps(first + 1, te, nullptr);
+            rc = launch_steps(first, te, nullptr);
             if (rc != CHX_OK) return rc;
             rc = md_download_rep(md);
             if (rc != CHX_OK) return rc;
         }
-        for (int r = 0; r < R; ++r) { md->rep_host[r].lo = te; md->rep_host[r].flag = 0; }
+        for (int r = 0; r < R; ++r) { md->rep_host[r].lo = te; md->rep_host[r].flag = 0; md->rep_host[r].halt = HALT_NONE; }
         rc = md_upload_rep(md);
         if (rc != CHX_OK) return rc;
         t = te;
     }
+    // forces of x_n (with the bookkeeping of step n - 1: energy report, reference rebuild), then the
     // trailing B of the last step (integrators.py:195)
-    k_md_kick<<<chx_div_up((long long)R * g.np, 256), 256, 0, st>>>(md->vs, md->fs, g, h, R);
+    rc = md_force(md, FMODE_FINAL, nsteps, wants_energy(nsteps), rint, energies_dev);
+    if (rc != CHX_OK) return rc;
+    k_md_kick<<<chx_div_up((long long)R * g.np, 256), 256, 0, st>>>(md->vs, md->fs, g, md_step_const(md).h, R);
     CHX_LAUNCHED(ctx);
+    if (nsteps & 1)   // x_n is in buffer B: outside a run the current positions live in md->xs
+        CHX_CUDA(cudaMemcpyAsync(md->xs, md->xs_b, (size_t)R * g.np * sizeof(float4), cudaMemcpyDeviceToDevice, st));
     rc = md_download_rep(md);
     if (rc != CHX_OK) return rc;
     for (int r = 0; r < R; ++r) {
         keys_host[2 * r] = md->rep_host[r].key[nsteps & 1][0];
         keys_host[2 * r + 1] = md->rep_host[r].key[nsteps & 1][1];
     }
+    md->forces_valid = true;
     md->steps += nsteps;
     return CHX_OK;
 }

@@ -212,7 +212,8 @@ int chx_mc_displace_run(chx_ctx* ctx, const chx_mc_displace_args* args, float* x
 
 /* ---- Fused LJ Langevin engine (integrators.py:110-218 + neighbors.py + potential.py) -------------- */
 /* Runs whole trajectories on the device: cell-sorted particles, counting-sort cell list,
- * tiled neighbour structure, fused BAOAB(+wrap+check) kernel, device-side rebuild decision.
+ * tiled neighbour structure, ONE kernel per Langevin step (forces over the tiles, then the BAOAB
+ * update + wrap + rebuild checks of the warp's own particles), device-side rebuild decision.
  * Produces the same positions / velocities / energies as the building blocks above. */
 typedef struct {
     int n;                 /* particles */

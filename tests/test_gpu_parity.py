@@ -606,10 +606,11 @@ def test_mc_displacement_subset_delta_path(cuda_device):
     assert moved.tolist() == [5]
 
 
-def test_while_graph_loop_matches_chunked_loop(cuda_device, monkeypatch):
-    """Single-system runs can use one CUDA graph with a device-side WHILE node (body = BAOAB, force,
-    loop control) instead of replaying 32-step chunks: same launches on the same data, so positions,
-    velocities, keys and rebuild bookkeeping are bit-identical."""
+def test_graph_replay_matches_direct_launches_and_odd_run_lengths(cuda_device, monkeypatch):
+    """The fused step kernel alternates between two position buffers (step s reads buffer s & 1); full
+    chunks replay one CUDA graph.  Replays vs direct launches (CHX_MD_NOGRAPH=1), with odd run lengths
+    (75 = 2 chunks + 11 steps, state ends in buffer B and is copied back) and table rebuilds at odd
+    steps: positions, velocities, keys and rebuild bookkeeping are bit-identical."""
     from chiron_b200 import random as crandom
     from chiron_b200._engine import LJLangevinEngine
     lj_sys, x, box = _lj_system(12, 0.8, seed=91)
@@ -619,7 +620,7 @@ def test_while_graph_loop_matches_chunked_loop(cuda_device, monkeypatch):
     mass = np.full(n, 39.948, f32)
     out = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("CHX_MD_WHILE", mode)
+        monkeypatch.setenv("CHX_MD_NOGRAPH", mode)
         eng = LJLangevinEngine(n, np.diag(box), 0.34, 0.238 * 4.184, 1.02, 0.3, 0.002, 1.0, 2.494,
                                internal_skin=0.05, device=cuda_device)
         eng.set_state(x, v, mass, [2.494])
