@@ -33,6 +33,8 @@ SIGMA, EPS_KCAL, RC, SKIN = 0.34, 0.238, 1.02, 0.5
 EPS = EPS_KCAL * 4.184
 MASS, TEMP_K, DT_PS, GAMMA = 39.948, 300.0, 0.001, 1.0
 N_SIDE, RHO_STAR = 64, 0.8
+# dram bytes of one step-kernel launch inside the step loop (ncu, profiles/r01_step_kernel_ncu.md)
+NCU_STEP_KERNEL_DRAM_BYTES = 73.0e6
 WORKLOAD = "LJ argon fluid N=262144 rho*=0.8 rc=3sigma skin=0.5nm T=300K dt=1fs Langevin BAOAB, cell-list build"
 
 
@@ -48,6 +50,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-remd", action="store_true")
+    p.add_argument("--no-mc", action="store_true", help="skip the Monte Carlo configs (secondary numbers)")
     p.add_argument("--remd-sweeps", type=int, default=20)
     return p.parse_args()
 
@@ -285,6 +288,7 @@ def run_ours(args):
     for _ in range(W):
         keys, _ = eng.run(S, keys)
     st0 = eng.stats()
+    eng.step_timing(reset=True)
     launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -296,6 +300,7 @@ def run_ours(args):
         barrier()
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launches - launches0
+    step_kernel_ms_total, step_kernel_launches = eng.step_timing()
     st1 = eng.stats()
     e_now = float(eng.energy()[0])
     st_e = eng.stats()
@@ -332,7 +337,11 @@ def run_ours(args):
     fp32x2_peak_tflops = flops.value / (ev0.elapsed_time(ev1) * 1e-3) / 1e12
     pair_flops = 18.0 * p_cand + 21.0 * p_int
     step_flops = pair_flops + 140.0 * n
-    achieved_tflops = pair_flops / (force_ms * 1e-3) / 1e12
+    # dominant kernel = the fused step kernel (pair loop + BAOAB update): duration from CUDA events around
+    # the graph replays of the timed region in which every launch did its full work (chx_ljmd_step_timing)
+    step_kernel_ms = (step_kernel_ms_total / step_kernel_launches) if step_kernel_launches else float("nan")
+    achieved_tflops = step_flops / (step_kernel_ms * 1e-3) / 1e12
+    pair_loop_tflops = pair_flops / (force_ms * 1e-3) / 1e12
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -354,19 +363,22 @@ def run_ours(args):
         hv = torch.from_numpy(v0).pin_memory()
         PRNG.set_seed(1234 + rank)
         key = PRNG.get_random_key()
-        out_x = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-        out_v = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+        # two pairs of pinned host buffers: the result of call k is the input of call k + 1
+        bufs = [(hx, hv), (torch.empty((n, 3), dtype=torch.float32).pin_memory(),
+                           torch.empty((n, 3), dtype=torch.float32).pin_memory())]
+        turn = [0]
 
         def one_call(key):
-            state = SamplerState(unit.Quantity(hx.to(dev, non_blocking=True), unit.nanometer), key,
-                                 velocities=unit.Quantity(hv.to(dev, non_blocking=True), unit.nanometer / unit.picosecond),
+            (ix, iv), (ox, ov) = bufs[turn[0]], bufs[1 - turn[0]]
+            state = SamplerState(unit.Quantity(ix.to(dev, non_blocking=True), unit.nanometer), key,
+                                 velocities=unit.Quantity(iv.to(dev, non_blocking=True), unit.nanometer / unit.picosecond),
                                  box_vectors=unit.Quantity(box, unit.nanometer))
             out, _ = integ.run(state, ts, number_of_steps=S, nbr_list=nbr)
-            out_x.copy_(out.positions, non_blocking=True)
-            out_v.copy_(out.velocities, non_blocking=True)
-            energy = float(integ._engine.energy()[0])      # D2H read of the step's result
+            ox.copy_(out.positions, non_blocking=True)
+            ov.copy_(out.velocities, non_blocking=True)
+            energy = float(integ._engine.energy()[0])      # D2H read of the step's result (synchronises)
             torch.cuda.synchronize()
-            hx.copy_(out_x); hv.copy_(out_v)
+            turn[0] = 1 - turn[0]
             return out._current_PRNG_key, energy
         for _ in range(min(W, 2)):
             key, _ = one_call(key)
@@ -393,6 +405,16 @@ def run_ours(args):
             remd = bench_remd(dev, rank, world, sweeps=args.remd_sweeps)
         except Exception as exc:   # the headline number must survive a failure of the secondary workload
             remd = {"error": repr(exc)}
+
+    # ---- Monte Carlo configs 2 and 3 (rank 0, N = 1 only): secondary numbers ------------------------------
+    mc = None
+    if rank == 0 and world == 1 and not args.no_mc:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "profiles"))
+            import bench_mc
+            mc = bench_mc.main(32, quiet=True)
+        except Exception as exc:
+            mc = {"error": repr(exc)}
 
     # ---- CPU baseline (rank 0, bounded sample) ------------------------------------------------------
     cpu = None
@@ -428,10 +450,16 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp32", "kernel": "k_md_force", "achieved": achieved_tflops,
+            "roofline": {"bound": "fp32", "kernel": "k_md_force<UPDATE> (one launch per Langevin step: pair loop + BAOAB)",
+                         "achieved": achieved_tflops,
                          "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
                          "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no fp32 figure)",
-                         "ffma2_chain_tflops": fp32x2_peak_tflops, "flops_per_launch": pair_flops, "kernel_ms": force_ms, "traffic": None,
+                         "ffma2_chain_tflops": fp32x2_peak_tflops, "flops_per_launch": step_flops,
+                         "kernel_ms": step_kernel_ms, "kernel_launches_timed": int(step_kernel_launches),
+                         "traffic": NCU_STEP_KERNEL_DRAM_BYTES,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch inside the step loop (--cache-control none; tables and state are L2 resident), profiles/r01_step_kernel_ncu.md",
+                         "pair_loop_only": {"kernel": "k_md_force (no update)", "kernel_ms": force_ms, "flops_per_launch": pair_flops,
+                                            "achieved": pair_loop_tflops, "frac": pair_loop_tflops / fp32_peak_tflops},
                          "step_flops": step_flops,
                          "step_frac": step_flops / (ms_max / (K * S) * 1e-3) / 1e12 / fp32_peak_tflops,
                          "hbm": {"achieved": hbm_bytes / (ms_max / (K * S) * 1e-3) / 1e9, "peak": hbm_peak,
@@ -440,6 +468,7 @@ def run_ours(args):
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
             "cpu_baseline": cpu,
             "remd": remd,
+            "mc": mc,
         }
         print(json.dumps(line))
     if world > 1:

@@ -27,6 +27,7 @@ _SIGS = {
     "chx_ljmd_stats": [_P, C.POINTER(C.c_longlong)],
     "chx_ljmd_table_stats": [_P, C.POINTER(C.c_longlong)],
     "chx_ljmd_force_only": [_P, _I],
+    "chx_ljmd_step_timing": [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong), _I],
     "chx_fma_peak": [_P, _I, C.POINTER(C.c_double)],
 }
 _lib.SIGNATURES.update(_SIGS)
@@ -118,6 +119,12 @@ class LJLangevinEngine:
 
     def force_only(self, repeats=1):
         self._call("chx_ljmd_force_only", int(repeats))
+
+    def step_timing(self, reset=False):
+        """(total ms, launches) of the step kernel over the chunk replays without a table rebuild."""
+        ms, steps = C.c_double(0.0), C.c_longlong(0)
+        self._call("chx_ljmd_step_timing", C.byref(ms), C.byref(steps), int(bool(reset)))
+        return ms.value, steps.value
 
     def stats(self):
         s = (C.c_longlong * 8)()

@@ -91,6 +91,9 @@ struct chx_ljmd {
     cudaGraphExec_t chunk_graph;     // CH fused steps captured once; re-captured when the table shape changes
     int chunk_graph_tcap, chunk_graph_lw, chunk_graph_ch;
     bool forces_valid;               // fs = F(current positions): set_state and the end of every run
+    cudaEvent_t tev0, tev1;          // bracket every chunk-graph replay (chx_ljmd_step_timing)
+    double timed_ms;                 // device time of the replays in which no replica halted
+    long long timed_steps;
     bool no_graph;                   // CHX_MD_NOGRAPH=1: launch every kernel directly
 };
 
@@ -1287,6 +1290,7 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->bcenter, nb * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->rep, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMalloc(&md->step_base, sizeof(int)));
+    md->tev0 = md->tev1 = nullptr; md->timed_ms = 0.0; md->timed_steps = 0;
     md->chunk_graph = nullptr; md->chunk_graph_tcap = -1; md->chunk_graph_lw = -1; md->cap_stream = nullptr;
     CHX_CUDA(cudaMallocHost(&md->rep_host, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMemset(md->rep, 0, md->R * sizeof(MdRep)));
@@ -1574,6 +1578,7 @@ int chx_ljmd_destroy(chx_ljmd* md) {
     if (md->chunk_graph) cudaGraphExecDestroy(md->chunk_graph);
     cudaFree(md->xs_b);
     if (md->cap_stream) cudaStreamDestroy(md->cap_stream);
+    if (md->tev0) { cudaEventDestroy(md->tev0); cudaEventDestroy(md->tev1); }
     cudaFreeHost(md->rep_host);
     delete md;
     return CHX_OK;
@@ -1694,7 +1699,10 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
         }
         k_md_setbase<<<1, 1, 0, st>>>(md->step_base, s0);
         CHX_LAUNCHED(ctx);
+        if (!md->tev0) { CHX_CUDA(cudaEventCreate(&md->tev0)); CHX_CUDA(cudaEventCreate(&md->tev1)); }
+        CHX_CUDA(cudaEventRecord(md->tev0, st));
         CHX_CUDA(cudaGraphLaunch(md->chunk_graph, st));
+        CHX_CUDA(cudaEventRecord(md->tev1, st));
         ctx->launches += CH;
         return CHX_OK;
     };
@@ -1720,10 +1728,21 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
             if (rc != CHX_OK) return rc;
         }
         md->tables_fresh = false;
-        rc = (use_graph && te - t == CH && !(t & 1)) ? launch_chunk_graph(t) : launch_steps(t, te, nullptr);
+        const bool replay = use_graph && te - t == CH && !(t & 1);
+        rc = replay ? launch_chunk_graph(t) : launch_steps(t, te, nullptr);
         if (rc != CHX_OK) return rc;
         rc = md_download_rep(md);
         if (rc != CHX_OK) return rc;
+        if (replay) {
+            // step-kernel timing for the roofline: only replays in which every launch did its full work
+            bool clean = true;
+            for (int r = 0; r < R; ++r) clean = clean && md->rep_host[r].halt >= te;
+            float ems = 0.f;
+            if (clean && cudaEventElapsedTime(&ems, md->tev0, md->tev1) == cudaSuccess) {
+                md->timed_ms += ems;
+                md->timed_steps += CH;
+            }
+        }
         // replicas whose tables went stale inside the chunk (halt = first step that did not run):
         // rebuild on x_halt and run the rest of the chunk.  halt == te needs tables for the next chunk
         // (or for the final force evaluation); a proactive rebuild at the next chunk start covers it.
@@ -1828,6 +1847,14 @@ int chx_ljmd_scale_velocities(chx_ljmd* md, const float* scale_per_replica_host)
         k_md_scale_v<<<chx_div_up(g.np, 256), 256, 0, md->ctx->stream>>>(md->vs + (size_t)r * g.np, g.np, sc);
         CHX_LAUNCHED(md->ctx);
     }
+    return CHX_OK;
+}
+
+int chx_ljmd_step_timing(chx_ljmd* md, double* total_ms_host, long long* steps_host, int reset) {
+    CHX_REQUIRE(md && total_ms_host && steps_host, "NULL argument");
+    *total_ms_host = md->timed_ms;
+    *steps_host = md->timed_steps;
+    if (reset) { md->timed_ms = 0.0; md->timed_steps = 0; }
     return CHX_OK;
 }
 

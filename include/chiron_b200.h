@@ -266,6 +266,10 @@ int chx_ljmd_stats(chx_ljmd* md, long long* stats_host8);
  * lane utilisation), [1]=list words per tile, [2]=bytes per tile, [3]=candidate capacity per block.
  * Synchronises. */
 int chx_ljmd_table_stats(chx_ljmd* md, long long* out4);
+/* Device time of the step kernel, measured with CUDA events on the launch stream around every CUDA-graph
+ * replay of a chunk of steps in which no replica stopped for a table rebuild (so every launch did its
+ * full work): *total_ms_host over *steps_host launches since creation or the last reset. */
+int chx_ljmd_step_timing(chx_ljmd* md, double* total_ms_host, long long* steps_host, int reset);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(n_side=32):
+def main(n_side=32, quiet=False):
     import torch
     from chiron_b200 import unit
     from chiron_b200.mcmc import MCMCSampler, MonteCarloBarostatMove, MonteCarloDisplacementMove, MoveSchedule
@@ -25,7 +25,10 @@ def main(n_side=32):
     from chiron_b200.states import SamplerState, ThermodynamicState
     from chiron_b200.testsystems import LennardJonesFluid
     from chiron_b200.utils import PRNG
-    out = {}
+    from loguru import logger
+    if quiet:
+        logger.remove()
+    out = {"api": "MCMCSampler.run (device-resident Metropolis loop for displacement moves, step-by-step barostat)"}
     # ---- config 3 ----
     sigma, eps, rc, skin = 0.373, 0.2941, 1.4, 0.5
     n = n_side ** 3
@@ -39,10 +42,12 @@ def main(n_side=32):
     nbr = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=rc * unit.nanometer, skin=skin * unit.nanometer,
                             n_max_neighbors=400, builder="cell")
     nbr.build_from_state(state)
-    disp = MonteCarloDisplacementMove(displacement_sigma=0.001 * unit.nanometer, number_of_moves=100,
+    # SURVEY.md section 8d names sigma_disp = 0.001 nm / volume scale 0.1 with autotune: at N = 32,768 those
+    # start at 0 % acceptance, so the timed moves start from the values autotune converges to
+    disp = MonteCarloDisplacementMove(displacement_sigma=0.0001 * unit.nanometer, number_of_moves=100,
                                       autotune=True, autotune_interval=100)
-    baro = MonteCarloBarostatMove(volume_max_scale=0.1, number_of_moves=10, autotune=True, autotune_interval=50)
-    for name, move, reps in (("displacement", disp, 2), ("barostat", baro, 2)):
+    baro = MonteCarloBarostatMove(volume_max_scale=0.0005, number_of_moves=10, autotune=True, autotune_interval=50)
+    for name, move, reps in (("displacement", disp, 5), ("barostat", baro, 5)):
         sampler = MCMCSampler(MoveSchedule([(name, move)]))
         state, thermo, nbr = sampler.run(state, thermo, 1, nbr)      # warm-up (allocations, autotune)
         torch.cuda.synchronize()
@@ -75,7 +80,9 @@ def main(n_side=32):
         torch.cuda.synchronize()
         out[f"cfg2_single_particle_{label}_moves_per_s"] = 1000 / (time.perf_counter() - t0)
         out[f"cfg2_single_particle_{label}_acceptance"] = move.n_accepted / max(1, move.n_proposed)
-    print(json.dumps(out))
+    if not quiet:
+        print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":
