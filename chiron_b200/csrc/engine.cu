@@ -1017,7 +1017,13 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
                 if (s != 31 && r2 >= lj.rc2_lo && r2 < lj.rc2_hi) {
                     const float4 xo = xs[jj];
                     float rx, ry, rz, d;
-                    ref_displacement<true>(xi0.x, xi0.y, xi0.z, xo.x, xo.y, xo.z, g.box, rx, ry, rz, d);
+                    // the reference's half list evaluates displacement(x_i, x_j) for i < j only
+                    // (neighbors.py:766-782); fp32 minimum images are not exactly antisymmetric, so
+                    // both directions of the pair use that orientation
+                    if (__float_as_int(xi0.w) < __float_as_int(xo.w))
+                        ref_displacement<true>(xi0.x, xi0.y, xi0.z, xo.x, xo.y, xo.z, g.box, rx, ry, rz, d);
+                    else
+                        ref_displacement<true>(xo.x, xo.y, xo.z, xi0.x, xi0.y, xi0.z, g.box, rx, ry, rz, d);
                     if (d < lj.rc) {
                         const float inv = 1.0f / r2;
                         const float inv3 = inv * inv * inv;

@@ -100,7 +100,15 @@ k_lj_allpairs(const float* __restrict__ x, int n, Box box, float sigma, float ep
                 const int j = j0 + t;
                 if (j == i) continue;
                 float rx, ry, rz, d;
-                ref_displacement<PERIODIC>(xi, yi, zi, sx[t], sy[t], sz[t], box, rx, ry, rz, d);
+                // the reference reduces over i < j only (reduction_mask, neighbors.py:1094-1104): the
+                // pair is evaluated in that orientation from both sides (fp32 minimum images are not
+                // exactly antisymmetric)
+                if (i < j) {
+                    ref_displacement<PERIODIC>(xi, yi, zi, sx[t], sy[t], sz[t], box, rx, ry, rz, d);
+                } else {
+                    ref_displacement<PERIODIC>(sx[t], sy[t], sz[t], xi, yi, zi, box, rx, ry, rz, d);
+                    rx = -rx; ry = -ry; rz = -rz;
+                }
                 if (!use_cutoff || d < cutoff) {
                     float e, f;
                     lj_pair(d, sigma, eps, e, f);
@@ -156,9 +164,12 @@ k_lj_subset_delta(const float* __restrict__ xo, const float* __restrict__ xn, in
         if (j == m) continue;
         const double w = is_moved[j] ? 0.5 : 1.0;
         float rx, ry, rz, d, e, f;
-        ref_displacement<PERIODIC>(nx, ny, nz, xn[3 * j], xn[3 * j + 1], xn[3 * j + 2], box, rx, ry, rz, d);
+        // orientation of the reference's half list: displacement(x_lower id, x_higher id)
+        if (m < j) ref_displacement<PERIODIC>(nx, ny, nz, xn[3 * j], xn[3 * j + 1], xn[3 * j + 2], box, rx, ry, rz, d);
+        else ref_displacement<PERIODIC>(xn[3 * j], xn[3 * j + 1], xn[3 * j + 2], nx, ny, nz, box, rx, ry, rz, d);
         if (d < cutoff) { lj_pair(d, sigma, eps, e, f); acc += w * (double)e; }
-        ref_displacement<PERIODIC>(ox, oy, oz, xo[3 * j], xo[3 * j + 1], xo[3 * j + 2], box, rx, ry, rz, d);
+        if (m < j) ref_displacement<PERIODIC>(ox, oy, oz, xo[3 * j], xo[3 * j + 1], xo[3 * j + 2], box, rx, ry, rz, d);
+        else ref_displacement<PERIODIC>(xo[3 * j], xo[3 * j + 1], xo[3 * j + 2], ox, oy, oz, box, rx, ry, rz, d);
         if (d < cutoff) { lj_pair(d, sigma, eps, e, f); acc -= w * (double)e; }
     }
     block_add_double(acc, delta);

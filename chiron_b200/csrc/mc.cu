@@ -177,9 +177,12 @@ k_mcl_subset_delta(int n, const uint32_t* __restrict__ moved, const float* __res
         if (j == m) continue;
         const double w = mask[j] != 0.0f ? 0.5 : 1.0;
         float rx, ry, rz, d, e;
-        ref_displacement<PERIODIC>(nx, ny, nz, xn[3 * j], xn[3 * j + 1], xn[3 * j + 2], box, rx, ry, rz, d);
+        // orientation of the reference's half list: displacement(x_lower id, x_higher id)
+        if (m < j) ref_displacement<PERIODIC>(nx, ny, nz, xn[3 * j], xn[3 * j + 1], xn[3 * j + 2], box, rx, ry, rz, d);
+        else ref_displacement<PERIODIC>(xn[3 * j], xn[3 * j + 1], xn[3 * j + 2], nx, ny, nz, box, rx, ry, rz, d);
         if (d < cutoff) { lj_pair_e(d, sigma, eps, e); a += w * (double)e; }
-        ref_displacement<PERIODIC>(ox, oy, oz, xo[3 * j], xo[3 * j + 1], xo[3 * j + 2], box, rx, ry, rz, d);
+        if (m < j) ref_displacement<PERIODIC>(ox, oy, oz, xo[3 * j], xo[3 * j + 1], xo[3 * j + 2], box, rx, ry, rz, d);
+        else ref_displacement<PERIODIC>(xo[3 * j], xo[3 * j + 1], xo[3 * j + 2], ox, oy, oz, box, rx, ry, rz, d);
         if (d < cutoff) { lj_pair_e(d, sigma, eps, e); a -= w * (double)e; }
     }
     mc_block_add(a, acc);

@@ -730,3 +730,67 @@ def test_mc_device_loop_ho_and_ideal_gas(cuda_device):
     assert a[0] == b[0] == dict(n_accepted=25, n_proposed=25)     # U = 0: every proposal is accepted
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert a[1].min() >= 0 and a[1].max() < 10                      # wrapped into the box
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json's full size (config 4, N = 262,144): size-independent properties
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_engine_properties(cuda_device):
+    """At N = 262,144 the all-pairs oracle is out of reach, so the fused engine is checked through
+    properties: (1) its forces / energy / interacting-pair count equal the independent reference-shaped
+    path (cell-list NeighborListNsqrd arrays + exact-predicate k_lj_nlist) within rel 1e-5, (2) Newton's
+    third law: the forces sum to zero, (3) a run of 64 + 37 steps equals one run of 101 steps bit for
+    bit (graph replays, odd run lengths, table rebuilds), particle ids are a permutation, positions stay
+    inside the box, and the kinetic temperature stays physical."""
+    from chiron_b200 import random as crandom, unit
+    from chiron_b200._engine import LJLangevinEngine
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.utils import initialize_velocities
+    sigma, eps, rc, skin = 0.34, 0.238 * 4.184, 1.02, 0.5
+    lj_sys, x, box = _lj_system(64, 0.8, seed=4)
+    n = x.shape[0]
+    assert n == 262144
+    L = np.diag(box)
+    mass = np.full(n, 39.948, f32)
+    v0 = _np(initialize_velocities(300 * unit.kelvin, lj_sys.topology, crandom.PRNGKey(11)).value_in_unit_system(
+        unit.md_unit_system))
+    eng = LJLangevinEngine(n, L, sigma, eps, rc, skin, 0.001, 1.0, 2.494, device=cuda_device)
+    eng.set_state(x, v0, mass, [2.494])
+    _, _, F, _ = eng.get_state(want_force=True)
+    e = float(eng.energy()[0])
+    p_int = eng.stats()["interacting_pairs"]
+    # (1) independent path
+    potential = LJPotential(lj_sys.topology, lj_sys.sigma, lj_sys.epsilon, rc * unit.nanometer)
+    nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=rc * unit.nanometer, skin=skin * unit.nanometer,
+                           n_max_neighbors=400, builder="cell")
+    nl.build(x, box)
+    e_ref, F_ref = potential.compute_energy_and_force(x, nl)
+    n_nb, _, mask, _, _ = nl.calculate(torch.as_tensor(x, device=cuda_device))
+    assert int(mask.sum().item()) == p_int
+    assert np.isclose(e, float(e_ref), rtol=1e-5)
+    Fn, Frn = _np(F), _np(F_ref)
+    assert np.allclose(Fn, Frn, rtol=1e-5, atol=1e-5 * float(np.abs(Frn).max()))
+    del nl, mask
+    # (2) Newton's third law (fp32 sums of ~90 terms per particle, fp64 total)
+    assert np.abs(Fn.astype(np.float64).sum(axis=0)).max() < 1e-6 * np.abs(Fn).sum()
+    # (3) split run == single run
+    key = crandom.PRNGKey(1234).reshape(1, 2)
+    k1, _ = eng.run(64, key)
+    k1, _ = eng.run(37, k1)
+    xa, va, _, _ = eng.get_state()
+    rebuilds = eng.stats()["table_rebuilds"]
+    eng.close()
+    eng = LJLangevinEngine(n, L, sigma, eps, rc, skin, 0.001, 1.0, 2.494, device=cuda_device)
+    eng.set_state(x, v0, mass, [2.494])
+    k2, _ = eng.run(101, key)
+    xb, vb, _, _ = eng.get_state()
+    eng.close()
+    assert rebuilds >= 2
+    assert np.array_equal(k1, k2)
+    assert torch.equal(xa, xb) and torch.equal(va, vb)
+    xan = _np(xa)
+    assert np.isfinite(xan).all() and (xan >= 0).all() and (xan < L).all()
+    kin = 0.5 * 39.948 * (_np(va).astype(np.float64) ** 2).sum()
+    T = 2.0 * kin / (3 * n) / 8.314462618e-3
+    assert 150.0 < T < 450.0, T     # melting lattice: kinetic energy flows into the potential energy at first
