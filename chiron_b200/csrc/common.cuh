@@ -104,6 +104,97 @@ __device__ __forceinline__ void ref_displacement(float ax, float ay, float az, f
     d = __fsqrt_rn(s);
 }
 
+// Fast classification of a pair against a cutoff c: the squared distance from FMA arithmetic decides
+// every pair that is not within a few ulps of c; only those go through the exact predicate above.
+// Kernels that use it evaluate exactly the reference's pair set {d < c} at a fraction of its cost.
+struct FastCut {
+    float c;             // the cutoff (exact predicate)
+    float c2_lo, c2_hi;  // r2 < c2_lo: inside, r2 >= c2_hi: outside
+    float inv_lx, inv_ly, inv_lz;
+};
+
+static inline FastCut make_fast_cut(float c, float lx, float ly, float lz, bool periodic) {
+    FastCut f;
+    f.c = c;
+    const double c2 = (double)c * (double)c;
+    double lmax = periodic ? (lx > ly ? (lx > lz ? lx : lz) : (ly > lz ? ly : lz)) : 0.0;
+    // |fast r2 - d_ref^2| <= ~2 c (a few ulps of the largest coordinate DIFFERENCE; a - b itself is
+    // correctly rounded): the band is generous enough for positions spread over +-4 box lengths
+    const double band = c2 * 4e-6 + 64.0 * 1.2e-7 * (lmax + 4.0 * (double)c) * (double)c;
+    f.c2_lo = (float)(c2 - band);
+    f.c2_hi = (float)(c2 + band);
+    f.inv_lx = 1.0f / lx; f.inv_ly = 1.0f / ly; f.inv_lz = 1.0f / lz;
+    return f;
+}
+
+// true iff the reference's predicate d(a, b) < c holds; r2 and (dx, dy, dz) = minimum image of a - b
+// from the fast arithmetic (relative error ~1e-7, far inside the 1e-5 energy / force tolerance).
+template <bool PERIODIC>
+__device__ __forceinline__ bool fast_within(float ax, float ay, float az, float bx, float by, float bz,
+                                            const Box& box, const FastCut& fc, float& r2, float& dx,
+                                            float& dy, float& dz) {
+    dx = ax - bx; dy = ay - by; dz = az - bz;
+    if (PERIODIC) {
+        dx -= box.lx * rintf(dx * fc.inv_lx);
+        dy -= box.ly * rintf(dy * fc.inv_ly);
+        dz -= box.lz * rintf(dz * fc.inv_lz);
+    }
+    r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    if (r2 >= fc.c2_hi) return false;
+    if (r2 >= fc.c2_lo) {
+        float rx, ry, rz, d;
+        ref_displacement<PERIODIC>(ax, ay, az, bx, by, bz, box, rx, ry, rz, d);
+        return d < fc.c;
+    }
+    return true;
+}
+
+// LJ pair energy and force scalar (f * (dx,dy,dz) = force on a) from r2, without sqrt or division
+__device__ __forceinline__ void lj_pair_r2(float r2, float sigma2, float eps, float& e, float& f_over_r) {
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r2));
+    inv = inv * (2.0f - r2 * inv);                 // one Newton step: ~1 ulp
+    const float s2 = sigma2 * inv;
+    const float s6 = s2 * s2 * s2;
+    e = 4.0f * eps * s6 * (s6 - 1.0f);
+    f_over_r = 24.0f * eps * inv * s6 * (2.0f * s6 - 1.0f);
+}
+
+// Energy of one row of a NeighborListNsqrd half list, this lane's share (entries lane, lane + 32, ...).
+// Four entries in flight per lane: the index loads and the position gathers of a batch are issued
+// before any arithmetic, so the two dependent memory latencies per entry overlap.  Shared by
+// LJPotential.compute_energy (lj.cu) and the Metropolis loop (mc.cu): identical summation order.
+template <bool PERIODIC>
+__device__ __forceinline__ float lj_nlist_row_energy(const float* __restrict__ x, int i, int lane,
+                                                     const Box& box, const FastCut& fc,
+                                                     const uint32_t* __restrict__ row, int cnt,
+                                                     float sigma2, float eps) {
+    const float xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+    float e_row = 0.f;
+    for (int k0 = lane; k0 < cnt; k0 += 128) {
+        uint32_t j[4];
+        float px[4], py[4], pz[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) j[u] = (k0 + 32 * u < cnt) ? row[k0 + 32 * u] : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t jj = j[u] != 0xffffffffu ? j[u] : (uint32_t)i;
+            px[u] = x[3 * jj]; py[u] = x[3 * jj + 1]; pz[u] = x[3 * jj + 2];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float r2, dx, dy, dz;
+            if (j[u] != 0xffffffffu &&
+                fast_within<PERIODIC>(xi, yi, zi, px[u], py[u], pz[u], box, fc, r2, dx, dy, dz)) {
+                float e, f;
+                lj_pair_r2(r2, sigma2, eps, e, f);
+                e_row += e;
+            }
+        }
+    }
+    return e_row;
+}
+
 // Space.wrap, one component: x - floor(x / L) * L.
 __device__ __forceinline__ float ref_wrap(float x, float L) {
     return __fsub_rn(x, __fmul_rn(floorf(__fdiv_rn(x, L)), L));

@@ -31,31 +31,35 @@ __device__ __forceinline__ void block_add_double(double v, double* target) {
     }
 }
 
-// one warp per row of the half list; f_i reduced in the warp, f_j scattered with atomics
+// one warp per row of the half list; f_i reduced in the warp, f_j scattered with atomics.  Pairs are
+// classified with the fast test (exact predicate only within a few ulps of the cutoff); energies and
+// forces come from r2 without sqrt / division (relative error ~1e-7).
 template <bool PERIODIC, bool WANT_E, bool WANT_F>
 __global__ void __launch_bounds__(256)
-k_lj_nlist(const float* __restrict__ x, int n, Box box, const uint32_t* __restrict__ list,
-           const int32_t* __restrict__ nn, int M, float sigma, float eps, float cutoff,
+k_lj_nlist(const float* __restrict__ x, int n, Box box, FastCut fc, const uint32_t* __restrict__ list,
+           const int32_t* __restrict__ nn, int M, float sigma, float eps,
            double* __restrict__ energy, float* __restrict__ force) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     double e_acc = 0.0;
     if (i < n) {
         const float xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+        const float sigma2 = sigma * sigma;
         int cnt = nn[i];
         cnt = cnt < M ? cnt : M;
-        float fx = 0.f, fy = 0.f, fz = 0.f;
+        float fx = 0.f, fy = 0.f, fz = 0.f, e_row = 0.f;
+        if (!WANT_F) {
+            e_row = lj_nlist_row_energy<PERIODIC>(x, i, lane, box, fc, list + (size_t)i * M, cnt, sigma2, eps);
+        } else
         for (int k = lane; k < cnt; k += 32) {
             const uint32_t j = list[(size_t)i * M + k];
-            float rx, ry, rz, d;
-            ref_displacement<PERIODIC>(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2], box, rx,
-                                       ry, rz, d);
-            if (d < cutoff) {
+            float r2, dx, dy, dz;
+            if (fast_within<PERIODIC>(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2], box, fc, r2, dx, dy, dz)) {
                 float e, f;
-                lj_pair(d, sigma, eps, e, f);
-                if (WANT_E) e_acc += (double)e;
+                lj_pair_r2(r2, sigma2, eps, e, f);
+                if (WANT_E) e_row += e;
                 if (WANT_F) {
-                    const float px = f * rx, py = f * ry, pz = f * rz;
+                    const float px = f * dx, py = f * dy, pz = f * dz;
                     fx += px; fy += py; fz += pz;
                     atomicAdd(&force[3 * j], -px);
                     atomicAdd(&force[3 * j + 1], -py);
@@ -63,6 +67,7 @@ k_lj_nlist(const float* __restrict__ x, int n, Box box, const uint32_t* __restri
                 }
             }
         }
+        e_acc = (double)e_row;      // at most M / 32 terms per lane in fp32, rows summed in fp64
         if (WANT_F) {
             fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
             if (lane == 0) {
@@ -193,9 +198,10 @@ int chx_lj_nlist_energy_force(chx_ctx* ctx, const float* x, int n, float lx, flo
     if (energy_dev) CHX_CUDA(cudaMemsetAsync(energy_dev, 0, sizeof(double), ctx->stream));
     if (force) CHX_CUDA(cudaMemsetAsync(force, 0, sizeof(float) * 3 * (size_t)n, ctx->stream));
     const int blocks = chx_div_up(n, 8);
-#define LAUNCH(P, E, F)                                                                          \
-    k_lj_nlist<P, E, F><<<blocks, 256, 0, ctx->stream>>>(x, n, box, neighbor_list, n_neighbors, M, \
-                                                         sigma, epsilon, cutoff, energy_dev, force)
+    const FastCut fc = make_fast_cut(cutoff, lx, ly, lz, periodic != 0);
+#define LAUNCH(P, E, F)                                                                              \
+    k_lj_nlist<P, E, F><<<blocks, 256, 0, ctx->stream>>>(x, n, box, fc, neighbor_list, n_neighbors, M, \
+                                                         sigma, epsilon, energy_dev, force)
     if (periodic) {
         if (energy_dev && force) LAUNCH(true, true, true);
         else if (energy_dev) LAUNCH(true, true, false);

@@ -90,8 +90,8 @@ __device__ __forceinline__ const float* mc_buf(const chx_mc_state* st, const flo
 
 template <bool PERIODIC>
 __global__ void __launch_bounds__(256)
-k_mcl_lj_nlist(int n, Box box, const uint32_t* __restrict__ list, const int32_t* __restrict__ nn, int M,
-               float sigma, float eps, float cutoff, const float* __restrict__ x0,
+k_mcl_lj_nlist(int n, Box box, FastCut fc, const uint32_t* __restrict__ list, const int32_t* __restrict__ nn, int M,
+               float sigma, float eps, const float* __restrict__ x0,
                const float* __restrict__ x1, const chx_mc_state* __restrict__ st, int which,
                double* __restrict__ acc) {
     if (st->halt) return;
@@ -100,19 +100,12 @@ k_mcl_lj_nlist(int n, Box box, const uint32_t* __restrict__ list, const int32_t*
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     double e_acc = 0.0;
     if (i < n) {
-        const float xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+        // same code as LJPotential.compute_energy (k_lj_nlist, lj.cu): identical reduced potentials
         int cnt = nn[i];
         cnt = cnt < M ? cnt : M;
-        for (int k = lane; k < cnt; k += 32) {
-            const uint32_t j = list[(size_t)i * M + k];
-            float rx, ry, rz, d;
-            ref_displacement<PERIODIC>(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2], box, rx, ry, rz, d);
-            if (d < cutoff) {
-                float e;
-                lj_pair_e(d, sigma, eps, e);
-                e_acc += (double)e;
-            }
-        }
+        const float e_row = lj_nlist_row_energy<PERIODIC>(x, i, lane, box, fc, list + (size_t)i * M, cnt,
+                                                          sigma * sigma, eps);
+        e_acc = (double)e_row;
     }
     mc_block_add(e_acc, acc);
 }
@@ -248,12 +241,14 @@ static int mc_launch_energy(chx_ctx* ctx, const McArgs& m, int which) {
     const Box box = make_box(a.lx, a.ly, a.lz);
     cudaStream_t st = ctx->stream;
     switch (a.potential) {
-    case CHX_MC_LJ_NLIST:
+    case CHX_MC_LJ_NLIST: {
+        const FastCut fc = make_fast_cut(a.cutoff, a.lx, a.ly, a.lz, a.periodic != 0);
         if (a.periodic)
-            k_mcl_lj_nlist<true><<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, box, a.neighbor_list, a.n_neighbors, a.M, a.sigma, a.epsilon, a.cutoff, m.x0, m.x1, m.st, which, m.acc);
+            k_mcl_lj_nlist<true><<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, box, fc, a.neighbor_list, a.n_neighbors, a.M, a.sigma, a.epsilon, m.x0, m.x1, m.st, which, m.acc);
         else
-            k_mcl_lj_nlist<false><<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, box, a.neighbor_list, a.n_neighbors, a.M, a.sigma, a.epsilon, a.cutoff, m.x0, m.x1, m.st, which, m.acc);
+            k_mcl_lj_nlist<false><<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, box, fc, a.neighbor_list, a.n_neighbors, a.M, a.sigma, a.epsilon, m.x0, m.x1, m.st, which, m.acc);
         break;
+    }
     case CHX_MC_LJ_SUBSET_DELTA:
         if (which == 0) {
             // the loop only needs differences; u of the current state is whatever the caller set
