@@ -179,7 +179,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -470,14 +470,36 @@ def run_ours(args):
             "remd": remd,
             "mc": mc,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-if __name__ == "__main__":
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything libraries print while the bench
+    runs (NCCL's version banner, loguru, nvcc) was redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def main():
+    global _REAL_STDOUT
     a = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)           # C libraries included
     if a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
+
+
+if __name__ == "__main__":
+    main()
