@@ -164,12 +164,28 @@ __device__ __forceinline__ void lj_pair_r2(float r2, float sigma2, float eps, fl
 // Four entries in flight per lane: the index loads and the position gathers of a batch are issued
 // before any arithmetic, so the two dependent memory latencies per entry overlap.  Shared by
 // LJPotential.compute_energy (lj.cu) and the Metropolis loop (mc.cu): identical summation order.
-template <bool PERIODIC>
-__device__ __forceinline__ float lj_nlist_row_energy(const float* __restrict__ x, int i, int lane,
+// position accessors: the API's (N,3) float array, or a float4 copy (one 16-byte gather per neighbour)
+struct Pos3 {
+    const float* __restrict__ x;
+    __device__ __forceinline__ void get(uint32_t j, float& a, float& b, float& c) const {
+        a = x[3 * j]; b = x[3 * j + 1]; c = x[3 * j + 2];
+    }
+};
+struct Pos4 {
+    const float4* __restrict__ x;
+    __device__ __forceinline__ void get(uint32_t j, float& a, float& b, float& c) const {
+        const float4 p = x[j];
+        a = p.x; b = p.y; c = p.z;
+    }
+};
+
+template <bool PERIODIC, class POS>
+__device__ __forceinline__ float lj_nlist_row_energy(const POS pos, int i, int lane,
                                                      const Box& box, const FastCut& fc,
                                                      const uint32_t* __restrict__ row, int cnt,
                                                      float sigma2, float eps) {
-    const float xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+    float xi, yi, zi;
+    pos.get((uint32_t)i, xi, yi, zi);
     float e_row = 0.f;
     for (int k0 = lane; k0 < cnt; k0 += 128) {
         uint32_t j[4];
@@ -179,7 +195,7 @@ __device__ __forceinline__ float lj_nlist_row_energy(const float* __restrict__ x
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const uint32_t jj = j[u] != 0xffffffffu ? j[u] : (uint32_t)i;
-            px[u] = x[3 * jj]; py[u] = x[3 * jj + 1]; pz[u] = x[3 * jj + 2];
+            pos.get(jj, px[u], py[u], pz[u]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {

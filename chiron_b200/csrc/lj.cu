@@ -49,7 +49,7 @@ k_lj_nlist(const float* __restrict__ x, int n, Box box, FastCut fc, const uint32
         cnt = cnt < M ? cnt : M;
         float fx = 0.f, fy = 0.f, fz = 0.f, e_row = 0.f;
         if (!WANT_F) {
-            e_row = lj_nlist_row_energy<PERIODIC>(x, i, lane, box, fc, list + (size_t)i * M, cnt, sigma2, eps);
+            e_row = lj_nlist_row_energy<PERIODIC>(Pos3{x}, i, lane, box, fc, list + (size_t)i * M, cnt, sigma2, eps);
         } else
         for (int k = lane; k < cnt; k += 32) {
             const uint32_t j = list[(size_t)i * M + k];

@@ -19,6 +19,8 @@ struct McArgs {
     chx_mc_displace_args a;
     float* x0;
     float* x1;
+    float4* q0;          // float4 copies of x0 / x1 (context scratch): one gather per neighbour
+    float4* q1;
     chx_mc_state* st;
     double* acc;
 };
@@ -50,7 +52,7 @@ template <bool WRAP, bool CHECK>
 __global__ void __launch_bounds__(256)
 k_mcl_propose(int n, const float* __restrict__ mask, Box box, const float* __restrict__ ref,
               float half_skin, float* __restrict__ x0, float* __restrict__ x1,
-              chx_mc_state* __restrict__ st) {
+              float4* __restrict__ q0, float4* __restrict__ q1, chx_mc_state* __restrict__ st) {
     if (*((volatile int*)&st->halt)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool moved = false;
@@ -72,6 +74,7 @@ k_mcl_propose(int n, const float* __restrict__ mask, Box box, const float* __res
             xp[3 * i + c] = v;
             xn[c] = v;
         }
+        (st->sel ? q0 : q1)[i] = make_float4(xn[0], xn[1], xn[2], 0.f);
         if (CHECK) {
             float rx, ry, rz, d;
             ref_displacement<WRAP>(xn[0], xn[1], xn[2], ref[3 * i], ref[3 * i + 1], ref[3 * i + 2], box, rx, ry, rz, d);
@@ -91,11 +94,11 @@ __device__ __forceinline__ const float* mc_buf(const chx_mc_state* st, const flo
 template <bool PERIODIC>
 __global__ void __launch_bounds__(256)
 k_mcl_lj_nlist(int n, Box box, FastCut fc, const uint32_t* __restrict__ list, const int32_t* __restrict__ nn, int M,
-               float sigma, float eps, const float* __restrict__ x0,
-               const float* __restrict__ x1, const chx_mc_state* __restrict__ st, int which,
+               float sigma, float eps, const float4* __restrict__ q0,
+               const float4* __restrict__ q1, const chx_mc_state* __restrict__ st, int which,
                double* __restrict__ acc) {
     if (st->halt) return;
-    const float* x = mc_buf(st, x0, x1, which);
+    const float4* x = ((st->sel ^ which) & 1) ? q1 : q0;
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     double e_acc = 0.0;
@@ -103,7 +106,7 @@ k_mcl_lj_nlist(int n, Box box, FastCut fc, const uint32_t* __restrict__ list, co
         // same code as LJPotential.compute_energy (k_lj_nlist, lj.cu): identical reduced potentials
         int cnt = nn[i];
         cnt = cnt < M ? cnt : M;
-        const float e_row = lj_nlist_row_energy<PERIODIC>(x, i, lane, box, fc, list + (size_t)i * M, cnt,
+        const float e_row = lj_nlist_row_energy<PERIODIC>(Pos4{x}, i, lane, box, fc, list + (size_t)i * M, cnt,
                                                           sigma * sigma, eps);
         e_acc = (double)e_row;
     }
@@ -181,6 +184,16 @@ k_mcl_subset_delta(int n, const uint32_t* __restrict__ moved, const float* __res
     mc_block_add(a, acc);
 }
 
+// float4 copy of the current configuration at the start of a call
+__global__ void k_mcl_pack(int n, const float* __restrict__ x0, const float* __restrict__ x1,
+                           float4* __restrict__ q0, float4* __restrict__ q1,
+                           const chx_mc_state* __restrict__ st) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* x = st->sel ? x1 : x0;
+    (st->sel ? q1 : q0)[i] = make_float4(x[3 * i], x[3 * i + 1], x[3 * i + 2], 0.f);
+}
+
 // ---- reduced potential and the Metropolis decision ---------------------------------------------------
 struct McThermo {
     int potential;
@@ -244,9 +257,9 @@ static int mc_launch_energy(chx_ctx* ctx, const McArgs& m, int which) {
     case CHX_MC_LJ_NLIST: {
         const FastCut fc = make_fast_cut(a.cutoff, a.lx, a.ly, a.lz, a.periodic != 0);
         if (a.periodic)
-            k_mcl_lj_nlist<true><<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, box, fc, a.neighbor_list, a.n_neighbors, a.M, a.sigma, a.epsilon, m.x0, m.x1, m.st, which, m.acc);
+            k_mcl_lj_nlist<true><<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, box, fc, a.neighbor_list, a.n_neighbors, a.M, a.sigma, a.epsilon, m.q0, m.q1, m.st, which, m.acc);
         else
-            k_mcl_lj_nlist<false><<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, box, fc, a.neighbor_list, a.n_neighbors, a.M, a.sigma, a.epsilon, m.x0, m.x1, m.st, which, m.acc);
+            k_mcl_lj_nlist<false><<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, box, fc, a.neighbor_list, a.n_neighbors, a.M, a.sigma, a.epsilon, m.q0, m.q1, m.st, which, m.acc);
         break;
     }
     case CHX_MC_LJ_SUBSET_DELTA:
@@ -292,7 +305,7 @@ static int mc_launch_move(chx_ctx* ctx, const McArgs& m) {
     const float hs = 0.5f * a.skin;
 #define PROPOSE(W, C)                                                                                   \
     k_mcl_propose<W, C><<<blocks, 256, 0, ctx->stream>>>(a.n, a.subset_mask, box, a.ref_positions, hs, \
-                                                         m.x0, m.x1, m.st)
+                                                         m.x0, m.x1, m.q0, m.q1, m.st)
     if (a.periodic) { if (check) PROPOSE(true, true); else PROPOSE(true, false); }
     else { if (check) PROPOSE(false, true); else PROPOSE(false, false); }
 #undef PROPOSE
@@ -377,13 +390,19 @@ int chx_mc_displace_run(chx_ctx* ctx, const chx_mc_displace_args* args, float* x
     McArgs m;
     memset(&m, 0, sizeof(m));   // padding bytes too: the struct is the graph cache key
     m.a = a; m.x0 = x0; m.x1 = x1; m.st = state_dev;
-    m.acc = (double*)chx_scratch(ctx, 256);
-    if (!m.acc) return CHX_CUDA_ERROR;
+    // context scratch: [acc 256 B][q0 n float4][q1 n float4]
+    unsigned char* scratch = (unsigned char*)chx_scratch(ctx, 256 + 2 * (size_t)a.n * sizeof(float4));
+    if (!scratch) return CHX_CUDA_ERROR;
+    m.acc = (double*)scratch;
+    m.q0 = (float4*)(scratch + 256);
+    m.q1 = m.q0 + a.n;
     cudaStream_t st = ctx->stream;
     state_host->halt = 0;
     state_host->moves_done = 0;
     CHX_CUDA(cudaMemcpyAsync(state_dev, state_host, sizeof(chx_mc_state), cudaMemcpyHostToDevice, st));
     CHX_CUDA(cudaMemsetAsync(m.acc, 0, sizeof(double), st));
+    k_mcl_pack<<<chx_div_up(a.n, 256), 256, 0, st>>>(a.n, x0, x1, m.q0, m.q1, state_dev);
+    CHX_LAUNCHED(ctx);
     int rc = CHX_OK;
     if (!state_host->have_u) {
         rc = mc_launch_energy(ctx, m, 0);

@@ -80,6 +80,41 @@ def main(n_side=32, quiet=False):
         torch.cuda.synchronize()
         out[f"cfg2_single_particle_{label}_moves_per_s"] = 1000 / (time.perf_counter() - t0)
         out[f"cfg2_single_particle_{label}_acceptance"] = move.n_accepted / max(1, move.n_proposed)
+    # ---- config 2: harmonic oscillator (N = 5, tests/test_mcmc.py:166-286) and ideal gas (N = 216, Examples/Idealgas.py) ----
+    from chiron_b200.neighbors import PairListNsqrd
+    from chiron_b200.potential import HarmonicOscillatorPotential, IdealGasPotential
+    from chiron_b200.testsystems import _topology
+    ho = HarmonicOscillatorPotential(_topology(5), k=100.0 * unit.kilocalories_per_mole / unit.angstrom ** 2,
+                                     x0=np.zeros((5, 3)) * unit.angstrom)
+    PRNG.set_seed(1234)
+    state = SamplerState(np.zeros((5, 3), np.float32) * unit.nanometer, PRNG.get_random_key())
+    thermo = ThermodynamicState(ho, temperature=300 * unit.kelvin)
+    move = MonteCarloDisplacementMove(displacement_sigma=0.1 * unit.angstrom, number_of_moves=1000)
+    sampler = MCMCSampler(MoveSchedule([("d", move)]))
+    state, thermo, _ = sampler.run(state, thermo, 1, None)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    state, thermo, _ = sampler.run(state, thermo, 5, None)
+    torch.cuda.synchronize()
+    out["cfg2_harmonic_oscillator_moves_per_s"] = 5000 / (time.perf_counter() - t0)
+    out["cfg2_harmonic_oscillator_acceptance"] = move.n_accepted / max(1, move.n_proposed)
+    rng = np.random.default_rng(3)
+    box = np.eye(3, dtype=np.float32) * 20.6
+    PRNG.set_seed(1234)
+    state = SamplerState((rng.random((216, 3)) * 20.6).astype(np.float32) * unit.nanometer, PRNG.get_random_key(),
+                         box_vectors=box * unit.nanometer)
+    thermo = ThermodynamicState(IdealGasPotential(_topology(216)), temperature=298 * unit.kelvin,
+                                pressure=1.0 * unit.atmosphere)
+    nbr = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=0 * unit.nanometer)
+    nbr.build_from_state(state)
+    move = MonteCarloDisplacementMove(displacement_sigma=0.1 * unit.nanometer, number_of_moves=1000)
+    sampler = MCMCSampler(MoveSchedule([("d", move)]))
+    state, thermo, nbr = sampler.run(state, thermo, 1, nbr)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    state, thermo, nbr = sampler.run(state, thermo, 5, nbr)
+    torch.cuda.synchronize()
+    out["cfg2_ideal_gas_moves_per_s"] = 5000 / (time.perf_counter() - t0)
     if not quiet:
         print(json.dumps(out))
     return out
