@@ -794,3 +794,31 @@ def test_full_size_engine_properties(cuda_device):
     kin = 0.5 * 39.948 * (_np(va).astype(np.float64) ** 2).sum()
     T = 2.0 * kin / (3 * n) / 8.314462618e-3
     assert 150.0 < T < 450.0, T     # melting lattice: kinetic energy flows into the potential energy at first
+
+
+@pytest.mark.parametrize("with_pairlist", [False, True])
+def test_mc_device_loop_lj_all_pairs(cuda_device, with_pairlist):
+    """LJ without a neighbour list (non-periodic N^2 pairs, potential.py:235-258) and over a periodic
+    PairListNsqrd: the device loop's all-pairs energy kernel against the step-by-step path."""
+    from chiron_b200 import unit
+    from chiron_b200.neighbors import OrthogonalPeriodicSpace, PairListNsqrd
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.utils import PRNG
+
+    def make():
+        lj_sys, x, box = _lj_system(5, 0.6, seed=81)
+        potential = LJPotential(lj_sys.topology, lj_sys.sigma, lj_sys.epsilon, 1.02 * unit.nanometer)
+        PRNG.set_seed(1234)
+        state = SamplerState(positions=lj_sys.positions, current_PRNG_key=PRNG.get_random_key(),
+                             box_vectors=lj_sys.box_vectors)
+        ts = ThermodynamicState(potential=potential, temperature=300 * unit.kelvin)
+        nl = None
+        if with_pairlist:
+            nl = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.02 * unit.nanometer)
+            nl.build_from_state(state)
+        return state, ts, nl
+    out = _run_move_both_ways(make, 40, displacement_sigma=0.003 * unit.nanometer)
+    a, b = out[True], out[False]
+    assert a[0] == b[0] and 0 < a[0]["n_accepted"] < 40
+    assert np.allclose(a[1], b[1], rtol=0, atol=1e-6) and np.array_equal(a[2], b[2])
