@@ -21,6 +21,7 @@ struct chx_ctx {
 };
 
 void chx_set_error(const char* fmt, ...);
+void chx_mc_forget_context(chx_ctx* ctx);   // mc.cu: drop the Metropolis-loop graphs cached for this context
 void* chx_scratch(chx_ctx* ctx, size_t bytes);  // device scratch of at least `bytes`, 256B aligned
 
 #define CHX_CUDA(call)                                                                      \

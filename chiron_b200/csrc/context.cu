@@ -65,6 +65,7 @@ int chx_context_set_stream(chx_ctx* ctx, void* cuda_stream) {
 int chx_context_destroy(chx_ctx* ctx) {
     if (!ctx) return CHX_OK;
     cudaSetDevice(ctx->device);
+    chx_mc_forget_context(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
     delete ctx;

@@ -375,6 +375,19 @@ static int mc_graph_get(chx_ctx* ctx, const McArgs& m, cudaGraphExec_t* out) {
     return CHX_OK;
 }
 
+// chx_context_destroy: the graphs captured for this context go with it (a later context may reuse
+// the address)
+void chx_mc_forget_context(chx_ctx* ctx) {
+    for (size_t k = 0; k < g_mc_graphs.size();) {
+        if (g_mc_graphs[k].ctx == ctx) {
+            cudaGraphExecDestroy(g_mc_graphs[k].exec);
+            g_mc_graphs.erase(g_mc_graphs.begin() + k);
+        } else {
+            ++k;
+        }
+    }
+}
+
 extern "C" {
 
 int chx_mc_displace_run(chx_ctx* ctx, const chx_mc_displace_args* args, float* x0, float* x1,
