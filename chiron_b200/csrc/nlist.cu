@@ -3,25 +3,11 @@
 //   chiron/neighbors.py:513-907 (neighbor list), :1018-1289 (pair list)
 #include <stdlib.h>
 #include <math.h>
+#include <string.h>
 #include "common.cuh"
+#include "cell_list.cuh"
 
 #define WARPS_PER_BLOCK 8
-
-// ---------------------------------------------------------------------------------------------
-// Row finalisation shared by both builders: padding value, pad mask, count.
-// `first` is the smallest listed neighbour id (valid when count > 0).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void finish_row(int i, int count, uint32_t first, int M,
-                                           uint32_t* __restrict__ list, int32_t* __restrict__ mask,
-                                           int32_t* __restrict__ nn, int lane) {
-    // neighbors.py:606-609: fill = argmax(mask) (first True, 0 if none); if fill == i: fill += 1
-    uint32_t fill = count > 0 ? first : 0u;
-    if (fill == (uint32_t)i) fill += 1u;
-    const int stored = count < M ? count : M;
-    for (int k = stored + lane; k < M; k += 32) list[(size_t)i * M + k] = fill;
-    for (int k = lane; k < M; k += 32) mask[(size_t)i * M + k] = (k < count) ? 1 : 0;
-    if (lane == 0) nn[i] = count;
-}
 
 // ---------------------------------------------------------------------------------------------
 // O(N^2) builder: one warp per row, j ascending, ballot compaction keeps the order.
@@ -59,21 +45,6 @@ k_build_nsq(const float* __restrict__ x, int n, Box box, float c, int M,
 }
 
 // max_i n_i and #{i : n_i == M}
-__global__ void k_count_stats(const int32_t* __restrict__ nn, int n, int M, int* __restrict__ out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int v = i < n ? nn[i] : 0;
-    int eq = (i < n && v == M) ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-        eq += __shfl_xor_sync(0xffffffffu, eq, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (v > 0) atomicMax(&out[0], v);
-        if (eq > 0) atomicAdd(&out[1], eq);
-    }
-}
-
 static int finish_build(chx_ctx* ctx, const int32_t* nn, int n, int M, int* max_count_host,
                         int* count_eq_M_host, int* extra_flag_dev, int* extra_flag_host) {
     int* stats = (int*)chx_scratch(ctx, 256);
@@ -98,73 +69,6 @@ static int finish_build(chx_ctx* ctx, const int32_t* nn, int n, int M, int* max_
 // Cell list: counting sort of particles into cells of edge >= cutoff+skin, 27-cell sweep with the
 // exact predicate, per-row bitonic sort so rows come out in ascending id order.
 // ---------------------------------------------------------------------------------------------
-struct CellGrid {
-    int nx, ny, nz;
-    float inv_cx, inv_cy, inv_cz;  // 1 / cell edge
-};
-
-__device__ __forceinline__ int cell_coord(float x, float L, float inv_c, int nc) {
-    float w = ref_wrap(x, L);
-    int c = (int)(w * inv_c);
-    c = c < 0 ? 0 : c;
-    return c >= nc ? nc - 1 : c;
-}
-
-__global__ void k_cell_count(const float* __restrict__ x, int n, Box box, CellGrid g,
-                             int* __restrict__ cell_of, int* __restrict__ cell_count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int cx = cell_coord(x[3 * i], box.lx, g.inv_cx, g.nx);
-    int cy = cell_coord(x[3 * i + 1], box.ly, g.inv_cy, g.ny);
-    int cz = cell_coord(x[3 * i + 2], box.lz, g.inv_cz, g.nz);
-    int c = (cx * g.ny + cy) * g.nz + cz;
-    cell_of[i] = c;
-    atomicAdd(&cell_count[c], 1);
-}
-
-// single-block exclusive scan: start[c] = sum_{c'<c} count[c'], start[ncell] = n; count is reset
-// to 0 so it can serve as the fill cursor.
-__global__ void k_cell_scan(int* __restrict__ count, int* __restrict__ start, int ncell) {
-    __shared__ int part[1024];
-    const int t = threadIdx.x;
-    const int per = (ncell + blockDim.x - 1) / blockDim.x;
-    const int lo = t * per, hi = min(ncell, lo + per);
-    int s = 0;
-    for (int c = lo; c < hi; ++c) s += count[c];
-    part[t] = s;
-    __syncthreads();
-    for (int o = 1; o < blockDim.x; o <<= 1) {
-        int v = t >= o ? part[t - o] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    int run = part[t] - s;
-    for (int c = lo; c < hi; ++c) {
-        int k = count[c];
-        start[c] = run;
-        count[c] = 0;
-        run += k;
-    }
-    if (t == blockDim.x - 1) start[ncell] = part[t];
-}
-
-// slot of particle i in cell order; xs4[slot] = (x, y, z, id) so that the sweep reads one coalesced
-// float4 per candidate instead of an index and three scattered floats
-__global__ void k_cell_fill(const float* __restrict__ x, const int* __restrict__ cell_of, int n, Box box,
-                            const int* __restrict__ start, int* __restrict__ cursor,
-                            int* __restrict__ order, float4* __restrict__ xs4) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int c = cell_of[i];
-    const int slot = start[c] + atomicAdd(&cursor[c], 1);
-    order[slot] = i;
-    // wrapped into [0, L): the sweep's fast test resolves periodic images per CELL (a shift of the
-    // row particle), not per pair; the exact predicate reads the caller's coordinates
-    xs4[slot] = make_float4(ref_wrap(x[3 * i], box.lx), ref_wrap(x[3 * i + 1], box.ly),
-                            ref_wrap(x[3 * i + 2], box.lz), __int_as_float(i));
-}
-
 // warp-level bitonic sort of `len` (power of two) uint32 in shared memory, ascending
 __device__ __forceinline__ void warp_bitonic_sort(uint32_t* buf, int len, int lane) {
     for (int k = 2; k <= len; k <<= 1) {
@@ -243,105 +147,6 @@ k_build_cell(const float* __restrict__ x, int n, Box box, CellGrid g, float c, i
     const int stored = count < M ? count : M;
     for (int k = lane; k < stored; k += 32) list[(size_t)i * M + k] = buf[k];
     const uint32_t first = count > 0 ? buf[0] : 0u;
-    finish_row(i, count, first, M, list, mask, nn, lane);
-}
-
-// 27-cell sweep, bitmap variant (n <= 32 * 32 * W particles).  One warp per row i.  Candidates come as
-// coalesced float4 (cell order); a fast FMA test decides the clear cases and only pairs within a few
-// ulps of the cutoff go through the reference's exact predicate (orientation i < j, like the half
-// list); hits set bit j of a per-warp bitmap in shared memory, and reading the bitmap back in word
-// order yields the row in ascending id order -- no sort.  Lane l owns bitmap words [l W, (l+1) W),
-// stored with a stride of W + 1 words so that the lanes hit different banks.
-struct SweepConst {
-    float c;               // cutoff + skin (exact predicate)
-    float c2_lo, c2_hi;    // r2 < c2_lo: inside, r2 >= c2_hi: outside, in between: exact predicate
-    float inv_lx, inv_ly, inv_lz;
-};
-
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-k_build_cell_bm(const float* __restrict__ x, const float4* __restrict__ xs4, int n, Box box, CellGrid g,
-                SweepConst sc, int M, int wshift, const int* __restrict__ cell_of,
-                const int* __restrict__ start, uint32_t* __restrict__ list, int32_t* __restrict__ mask,
-                int32_t* __restrict__ nn) {
-    extern __shared__ uint32_t smem[];
-    const int lane = threadIdx.x & 31;
-    const int w = threadIdx.x >> 5;
-    const int i = blockIdx.x * WARPS + w;
-    if (i >= n) return;
-    const int W = 1 << wshift;
-    uint32_t* bm = smem + (size_t)w * 32 * (W + 1);
-    for (int k = lane; k < 32 * (W + 1); k += 32) bm[k] = 0u;
-    __syncwarp();
-    const float xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
-    const float xw = ref_wrap(xi, box.lx), yw = ref_wrap(yi, box.ly), zw = ref_wrap(zi, box.lz);
-    const int ci = cell_of[i];
-    const int cz = ci % g.nz, cy = (ci / g.nz) % g.ny, cx = ci / (g.nz * g.ny);
-    for (int dx = -1; dx <= 1; ++dx) {
-        int ax = cx + dx;
-        float xs = xw;                       // row particle shifted into the neighbour cell's image
-        if (ax < 0) { ax += g.nx; xs = xw + box.lx; } else if (ax >= g.nx) { ax -= g.nx; xs = xw - box.lx; }
-        for (int dy = -1; dy <= 1; ++dy) {
-            int ay = cy + dy;
-            float ys = yw;
-            if (ay < 0) { ay += g.ny; ys = yw + box.ly; } else if (ay >= g.ny) { ay -= g.ny; ys = yw - box.ly; }
-            for (int dz = -1; dz <= 1; ++dz) {
-                int az = cz + dz;
-                float zs = zw;
-                if (az < 0) { az += g.nz; zs = zw + box.lz; } else if (az >= g.nz) { az -= g.nz; zs = zw - box.lz; }
-                const int cc = (ax * g.ny + ay) * g.nz + az;
-                const int s = start[cc], e = start[cc + 1];
-                for (int t = s + lane; t < e; t += 32) {
-                    const float4 p = xs4[t];
-                    const int j = __float_as_int(p.w);
-                    if (j <= i) continue;
-                    const float ddx = xs - p.x, ddy = ys - p.y, ddz = zs - p.z;
-                    const float r2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
-                    if (r2 >= sc.c2_hi) continue;
-                    if (r2 >= sc.c2_lo) {
-                        float rx, ry, rz, d;
-                        ref_displacement<true>(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2], box, rx, ry, rz, d);
-                        if (!(d < sc.c)) continue;
-                    }
-                    const int q = j >> 5;
-                    atomicOr(&bm[q + (q >> wshift)], 1u << (j & 31));
-                }
-            }
-        }
-    }
-    __syncwarp();
-    // read back: lane l scans its W words in order
-    const uint32_t* mine = bm + (size_t)lane * (W + 1);
-    int cnt = 0;
-    uint32_t first = 0xffffffffu;
-    for (int k = 0; k < W; ++k) {
-        const uint32_t v = mine[k];
-        if (v && first == 0xffffffffu) first = (uint32_t)(((lane << wshift) + k) << 5) + (uint32_t)(__ffs(v) - 1);
-        cnt += __popc(v);
-    }
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const int count = __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-    int pos = incl - cnt;
-    if (cnt > 0 && pos < M) {
-        for (int k = 0; k < W && pos < M; ++k) {
-            uint32_t v = mine[k];
-            const uint32_t base = (uint32_t)(((lane << wshift) + k) << 5);
-            while (v && pos < M) {
-                const int b = __ffs(v) - 1;
-                v &= v - 1u;
-                list[(size_t)i * M + pos] = base + (uint32_t)b;
-                ++pos;
-            }
-        }
-    }
-    __syncwarp();
     finish_row(i, count, first, M, list, mask, nn, lane);
 }
 
@@ -455,68 +260,47 @@ int chx_nlist_build_cell(chx_ctx* ctx, const float* x, int n, float lx, float ly
                          int* count_eq_M_host) {
     CHX_REQUIRE(ctx && x && neighbor_list && neighbor_mask && n_neighbors, "NULL argument");
     CHX_REQUIRE(n > 0 && M > 0, "n and M must be positive");
-    // cell edge >= (cutoff+skin)(1+1e-5): binning uses a rounded wrapped coordinate, the margin
-    // keeps every pair inside the predicate within the 27-cell stencil.
-    const double rc = (double)cutoff_plus_skin * (1.0 + 1e-5);
-    int nx = (int)floor((double)lx / rc), ny = (int)floor((double)ly / rc),
-        nz = (int)floor((double)lz / rc);
-    if (!periodic || nx < 3 || ny < 3 || nz < 3)
+    CellParams P;
+    if (!periodic || !make_cell_params(lx, ly, lz, cutoff_plus_skin, 0, P))
         return chx_nlist_build_nsq(ctx, x, n, lx, ly, lz, periodic, cutoff_plus_skin, M,
                                    neighbor_list, neighbor_mask, n_neighbors, max_count_host,
                                    count_eq_M_host);
-    nx = nx > 256 ? 256 : nx; ny = ny > 256 ? 256 : ny; nz = nz > 256 ? 256 : nz;
-    CellGrid g;
-    g.nx = nx; g.ny = ny; g.nz = nz;
-    g.inv_cx = (float)(nx / (double)lx); g.inv_cy = (float)(ny / (double)ly);
-    g.inv_cz = (float)(nz / (double)lz);
-    const int ncell = nx * ny * nz;
-    Box box = make_box(lx, ly, lz);
-    // scratch layout: [stats 256B][overflow flag][xs4 n float4][cell_of n][count ncell+1][start ncell+1][order n]
-    const size_t ints = 64 + 64 + 4 * (size_t)n + (size_t)n + 2 * ((size_t)ncell + 1) + (size_t)n;
+    const CellGrid g = P.g;
+    const int ncell = P.ncell;
+    const Box box = P.box;
+    // scratch layout: [stats 256B][overflow flag 256B][CellParams 256B][xs4 n float4][cell_of n][count ncell+1][start ncell+1][order n]
+    const size_t ints = 192 + 4 * (size_t)n + (size_t)n + 2 * ((size_t)ncell + 1) + (size_t)n;
     int* base = (int*)chx_scratch(ctx, ints * sizeof(int));
     if (!base) return CHX_CUDA_ERROR;
     int* overflow = base + 64;
-    float4* xs4 = reinterpret_cast<float4*>(base + 128);     // 512 B into a 256 B aligned block
-    int* cell_of = base + 128 + 4 * (size_t)n;
+    CellParams* P_dev = reinterpret_cast<CellParams*>(base + 128);
+    float4* xs4 = reinterpret_cast<float4*>(base + 192);     // 768 B into a 256 B aligned block
+    int* cell_of = base + 192 + 4 * (size_t)n;
     int* count = cell_of + n;
     int* start = count + ncell + 1;
     int* order = start + ncell + 1;
+    // the build kernels read their geometry from device memory (shared with the barostat loop, mc.cu)
+    static_assert(sizeof(CellParams) <= 256, "CellParams must fit its scratch slot");
+    memcpy(ctx->host_pinned + 8, &P, sizeof(P));
+    CHX_CUDA(cudaMemcpyAsync(P_dev, ctx->host_pinned + 8, sizeof(P), cudaMemcpyHostToDevice, ctx->stream));
     CHX_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), ctx->stream));
     CHX_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (ncell + 1), ctx->stream));
-    k_cell_count<<<chx_div_up(n, 256), 256, 0, ctx->stream>>>(x, n, box, g, cell_of, count);
+    k_cell_count<<<chx_div_up(n, 256), 256, 0, ctx->stream>>>(x, n, P_dev, cell_of, count);
     CHX_LAUNCHED(ctx);
-    k_cell_scan<<<1, 1024, 0, ctx->stream>>>(count, start, ncell);
+    k_cell_scan<<<1, 1024, 0, ctx->stream>>>(count, start, P_dev);
     CHX_LAUNCHED(ctx);
-    k_cell_fill<<<chx_div_up(n, 256), 256, 0, ctx->stream>>>(x, cell_of, n, box, start, count, order, xs4);
+    k_cell_fill<<<chx_div_up(n, 256), 256, 0, ctx->stream>>>(x, cell_of, n, P_dev, start, count, order, xs4);
     CHX_LAUNCHED(ctx);
-    // bitmap sweep while one warp's bitmap (n bits, padded) fits next to seven others in shared memory
+    // bitmap sweep while one warp's bitmap (n bits, padded) fits next to another one in shared memory
     {
-        const int nwords = chx_div_up(n, 32);
-        int wshift = 0;
-        while ((32 << wshift) < nwords) ++wshift;
-        const size_t per_warp = (size_t)32 * ((1u << wshift) + 1) * sizeof(uint32_t);
+        int wshift, warps;
+        size_t smem;
         static int use_bm = -1;
         if (use_bm < 0) { const char* e = getenv("CHX_NLIST_SORT_SWEEP"); use_bm = (e && e[0] == '1') ? 0 : 1; }
-        if (use_bm && per_warp * 2 <= 200 * 1024) {
-            SweepConst sc;
-            sc.c = cutoff_plus_skin;
-            const double c2 = (double)cutoff_plus_skin * (double)cutoff_plus_skin;
-            const double lmax = fmax(lx, fmax(ly, lz));
-            const double band = c2 * 4e-6 + 8.0 * 1.2e-7 * lmax * cutoff_plus_skin;
-            sc.c2_lo = (float)(c2 - band); sc.c2_hi = (float)(c2 + band);
-            sc.inv_lx = 1.0f / lx; sc.inv_ly = 1.0f / ly; sc.inv_lz = 1.0f / lz;
-            int warps = 8;
-            while (warps > 2 && per_warp * warps > 200 * 1024) warps >>= 1;
-            const size_t smem = per_warp * warps;
-#define BM_LAUNCH(WN)                                                                                   \
-            do {                                                                                        \
-                CHX_CUDA(cudaFuncSetAttribute(k_build_cell_bm<WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                k_build_cell_bm<WN><<<chx_div_up(n, WN), WN * 32, smem, ctx->stream>>>(                   \
-                    x, xs4, n, box, g, sc, M, wshift, cell_of, start, neighbor_list, neighbor_mask, n_neighbors); \
-            } while (0)
-            if (warps == 8) BM_LAUNCH(8); else if (warps == 4) BM_LAUNCH(4); else BM_LAUNCH(2);
-#undef BM_LAUNCH
-            CHX_LAUNCHED(ctx);
+        if (use_bm && cell_bm_config(n, wshift, warps, smem)) {
+            int rc = cell_bm_launch(ctx, x, xs4, n, P_dev, M, wshift, warps, smem, cell_of, start, neighbor_list,
+                                    neighbor_mask, n_neighbors);
+            if (rc != CHX_OK) return rc;
             return finish_build(ctx, n_neighbors, n, M, max_count_host, count_eq_M_host, nullptr, nullptr);
         }
     }
