@@ -59,6 +59,7 @@ SIGNATURES = {
     "chx_mc_displace": [_P, _P, _I, _U, _U, _F, _P, _F, _F, _F, _I, _P],
     "chx_scale": [_P, _P, _L, _F, _P],
     "chx_mc_displace_run": [_P, _P, _P, _P, _P, _P, _I],
+    "chx_mc_barostat_run": [_P, _P, _P, _P, _P, _P, _I],
 }
 
 
@@ -80,6 +81,21 @@ class McState(C.Structure):
 
 
 MC_LJ_NLIST, MC_LJ_ALLPAIRS, MC_HO, MC_IDEAL, MC_LJ_SUBSET_DELTA = range(5)
+
+
+class McBarostatArgs(C.Structure):
+    """chx_mc_barostat_args (include/chiron_b200.h)."""
+    _fields_ = [("n", _I), ("sigma", _F), ("epsilon", _F), ("cutoff", _F), ("cutoff_plus_skin", _F), ("M", _I),
+                ("neighbor_list", _P * 2), ("neighbor_mask", _P * 2), ("n_neighbors", _P * 2),
+                ("beta", C.c_double), ("pressure", C.c_double), ("ncell_capacity", _I)]
+
+
+class McBaroState(C.Structure):
+    """chx_mc_baro_state (include/chiron_b200.h), 64 bytes."""
+    _fields_ = [("key", _U * 2), ("sel", C.c_int32), ("have_u", C.c_int32), ("u_current", _F),
+                ("volume_max_scale", _F), ("n_accepted", C.c_int32), ("n_proposed", C.c_int32),
+                ("moves_done", C.c_int32), ("halt", C.c_int32), ("nan_seen", C.c_int32), ("box", _F * 3),
+                ("last_volume", _F), ("reserved", C.c_int32)]
 _RESTYPES = {"chx_launch_count": _L, "chx_last_error_string": C.c_char_p}
 
 

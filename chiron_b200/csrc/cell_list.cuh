@@ -22,8 +22,20 @@ static __device__ __forceinline__ void finish_row(int i, int count, uint32_t fir
 }
 
 
+// Optional double buffering: when `flip` is given and *flip != 0 a kernel works on the alternate
+// pointers (the barostat loop builds into whichever list set is NOT current; the host path passes
+// flip = NULL).
+template <class T>
+static __device__ __forceinline__ T* cl_pick(T* a, T* b, const int* flip) {
+    return (flip != nullptr && *flip != 0) ? b : a;
+}
+
 // max_i n_i and the number of rows with n_i == M (the reference's growth trigger, neighbors.py:709)
-static __global__ void k_count_stats(const int32_t* __restrict__ nn, int n, int M, int* __restrict__ out) {
+static __global__ void k_count_stats(const int32_t* nn, int n, int M, int* __restrict__ out,
+                                     const int32_t* nn_alt = nullptr, const int* flip = nullptr,
+                                     const int* skip = nullptr) {
+    if (skip != nullptr && *skip != 0) return;
+    nn = cl_pick(nn, nn_alt, flip);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int v = i < n ? nn[i] : 0;
     int eq = (i < n && v == M) ? 1 : 0;
@@ -92,9 +104,11 @@ __device__ __forceinline__ int cell_coord(float x, float L, float inv_c, int nc)
     return c >= nc ? nc - 1 : c;
 }
 
-static __global__ void k_cell_count(const float* __restrict__ x, int n, const CellParams* __restrict__ P,
-                                    int* __restrict__ cell_of, int* __restrict__ cell_count) {
+static __global__ void k_cell_count(const float* x, int n, const CellParams* __restrict__ P,
+                                    int* __restrict__ cell_of, int* __restrict__ cell_count,
+                                    const float* x_alt = nullptr, const int* flip = nullptr) {
     if (!P->valid) return;
+    x = cl_pick(x, x_alt, flip);
     const Box box = P->box;
     const CellGrid g = P->g;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,10 +153,12 @@ static __global__ void k_cell_scan(int* __restrict__ count, int* __restrict__ st
 
 // slot of particle i in cell order; xs4[slot] = (x, y, z, id) so that the sweep reads one coalesced
 // float4 per candidate instead of an index and three scattered floats
-static __global__ void k_cell_fill(const float* __restrict__ x, const int* __restrict__ cell_of, int n,
+static __global__ void k_cell_fill(const float* x, const int* __restrict__ cell_of, int n,
                                    const CellParams* __restrict__ P, const int* __restrict__ start,
-                                   int* __restrict__ cursor, int* __restrict__ order, float4* __restrict__ xs4) {
+                                   int* __restrict__ cursor, int* __restrict__ order, float4* __restrict__ xs4,
+                                   const float* x_alt = nullptr, const int* flip = nullptr) {
     if (!P->valid) return;
+    x = cl_pick(x, x_alt, flip);
     const Box box = P->box;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -164,12 +180,17 @@ static __global__ void k_cell_fill(const float* __restrict__ x, const int* __res
 // stored with a stride of W + 1 words so that the lanes hit different banks.
 template <int WARPS>
 static __global__ void __launch_bounds__(WARPS * 32)
-k_build_cell_bm(const float* __restrict__ x, const float4* __restrict__ xs4, int n,
+k_build_cell_bm(const float* x, const float4* __restrict__ xs4, int n,
                 const CellParams* __restrict__ P, int M, int wshift, const int* __restrict__ cell_of,
-                const int* __restrict__ start, uint32_t* __restrict__ list, int32_t* __restrict__ mask,
-                int32_t* __restrict__ nn) {
+                const int* __restrict__ start, uint32_t* list, int32_t* mask, int32_t* nn,
+                const float* x_alt = nullptr, uint32_t* list_alt = nullptr, int32_t* mask_alt = nullptr,
+                int32_t* nn_alt = nullptr, const int* flip = nullptr) {
     extern __shared__ uint32_t smem[];
     if (!P->valid) return;
+    x = cl_pick(x, x_alt, flip);
+    list = cl_pick(list, list_alt, flip);
+    mask = cl_pick(mask, mask_alt, flip);
+    nn = cl_pick(nn, nn_alt, flip);
     const Box box = P->box;
     const CellGrid g = P->g;
     const SweepConst sc = P->sc;
@@ -269,12 +290,15 @@ static inline bool cell_bm_config(int n, int& wshift, int& warps, size_t& smem) 
 
 static inline int cell_bm_launch(chx_ctx* ctx, const float* x, const float4* xs4, int n, const CellParams* P_dev,
                                  int M, int wshift, int warps, size_t smem, const int* cell_of, const int* start,
-                                 uint32_t* list, int32_t* mask, int32_t* nn) {
+                                 uint32_t* list, int32_t* mask, int32_t* nn, const float* x_alt = nullptr,
+                                 uint32_t* list_alt = nullptr, int32_t* mask_alt = nullptr,
+                                 int32_t* nn_alt = nullptr, const int* flip = nullptr) {
 #define BM_LAUNCH(WN)                                                                                       \
     do {                                                                                                    \
         CHX_CUDA(cudaFuncSetAttribute(k_build_cell_bm<WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_build_cell_bm<WN><<<chx_div_up(n, WN), WN * 32, smem, ctx->stream>>>(x, xs4, n, P_dev, M, wshift, cell_of, \
-                                                                                start, list, mask, nn);      \
+                                                                                start, list, mask, nn, x_alt,   \
+                                                                                list_alt, mask_alt, nn_alt, flip); \
     } while (0)
     if (warps == 8) BM_LAUNCH(8); else if (warps == 4) BM_LAUNCH(4); else BM_LAUNCH(2);
 #undef BM_LAUNCH

@@ -114,7 +114,7 @@ struct FastCut {
     float inv_lx, inv_ly, inv_lz;
 };
 
-static inline FastCut make_fast_cut(float c, float lx, float ly, float lz, bool periodic) {
+__host__ __device__ inline FastCut make_fast_cut(float c, float lx, float ly, float lz, bool periodic) {
     FastCut f;
     f.c = c;
     const double c2 = (double)c * (double)c;

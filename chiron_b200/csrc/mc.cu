@@ -14,6 +14,7 @@
 #include <string.h>
 #include <vector>
 #include "common.cuh"
+#include "cell_list.cuh"
 
 struct McArgs {
     chx_mc_displace_args a;
@@ -439,6 +440,267 @@ int chx_mc_displace_run(chx_ctx* ctx, const chx_mc_displace_args* args, float* x
     for (; left > 0 && rc == CHX_OK; --left) rc = mc_launch_move(ctx, m);
     if (rc != CHX_OK) return rc;
     CHX_CUDA(cudaMemcpyAsync(state_host, state_dev, sizeof(chx_mc_state), cudaMemcpyDeviceToHost, st));
+    CHX_CUDA(cudaStreamSynchronize(st));
+    return CHX_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// Barostat loop (chiron/mcmc.py:913-1009): propose a volume, rebuild the list on the scaled system,
+// energy, decide -- all on the device.  The geometry of a proposal (cell grid, sweep and energy
+// cutoffs of the proposed box) lives in device memory because it changes with every move.
+// =====================================================================================================
+struct McbMove {
+    CellParams P;          // list build on the proposed box
+    FastCut fc;            // energy cutoff with the proposed box (or the current one: initial energy)
+    float box_new[3];
+    float volume_box;      // lx' ly' lz' (the volume get_reduced_potential sees, states.py:313-323)
+    float log_volume;      // N log(V1 / V0) (mcmc.py:1000-1003)
+};
+
+struct McbArgs {
+    chx_mc_barostat_args a;
+    float* x0;
+    float* x1;
+    float4* q0;
+    float4* q1;
+    chx_mc_baro_state* st;
+    double* acc;
+    int* stats;            // [0] max row count, [1] rows with count == M of the list just built
+    McbMove* mv;
+    float4* xs4;
+    int* cell_of;
+    int* count;
+    int* start;
+    int* order;
+    int ncell_cap;
+};
+
+__global__ void __launch_bounds__(256)
+k_mcb_propose(int n, float cutoff, float list_radius, int ncell_cap, float* __restrict__ x0,
+              float* __restrict__ x1, float4* __restrict__ q0, float4* __restrict__ q1,
+              chx_mc_baro_state* __restrict__ st, McbMove* __restrict__ mv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (*((volatile int*)&st->halt)) {
+        if (i == 0) mv->P.valid = 0;      // nothing of this move runs
+        return;
+    }
+    // scalar chain of mcmc.py:956-974 in fp32 (every thread, identical)
+    uint32_t c0, c1, s0, s1;
+    threefry_split(st->key[0], st->key[1], c0, c1, s0, s1);
+    const float lx = st->box[0], ly = st->box[1], lz = st->box[2];
+    const float v0 = __fmul_rn(__fmul_rn(lx, ly), lz);
+    const float dvmax = __fmul_rn(st->volume_max_scale, v0);
+    const float dv = __fmul_rn(uniform_from_bits(random_bits_elem(s0, s1, 0ull, 1ull), -1.0f, 1.0f), dvmax);
+    const float v1 = __fadd_rn(v0, dv);
+    const float ratio = __fdiv_rn(v1, v0);
+    const float sc = powf(ratio, 0.33333334f);
+    if (i < n) {
+        const float* xc = st->sel ? x1 : x0;
+        float* xp = st->sel ? x0 : x1;
+        const float a = __fmul_rn(xc[3 * i], sc), b = __fmul_rn(xc[3 * i + 1], sc), c = __fmul_rn(xc[3 * i + 2], sc);
+        xp[3 * i] = a; xp[3 * i + 1] = b; xp[3 * i + 2] = c;
+        (st->sel ? q0 : q1)[i] = make_float4(a, b, c, 0.f);
+    }
+    if (i == 0) {
+        const float nlx = __fmul_rn(lx, sc), nly = __fmul_rn(ly, sc), nlz = __fmul_rn(lz, sc);
+        mv->box_new[0] = nlx; mv->box_new[1] = nly; mv->box_new[2] = nlz;
+        mv->volume_box = __fmul_rn(__fmul_rn(nlx, nly), nlz);
+        mv->log_volume = __fmul_rn((float)n, logf(ratio));
+        mv->fc = make_fast_cut(cutoff, nlx, nly, nlz, true);
+        CellParams P;
+        const bool ok = v1 > 0.0f && make_cell_params(nlx, nly, nlz, list_radius, ncell_cap, P);
+        if (ok) mv->P = P;
+        else { mv->P.valid = 0; atomicExch(&st->halt, 1); }
+    }
+}
+
+// geometry of the CURRENT box (initial energy of a call)
+__global__ void k_mcb_current(float cutoff, const chx_mc_baro_state* __restrict__ st, McbMove* __restrict__ mv) {
+    mv->fc = make_fast_cut(cutoff, st->box[0], st->box[1], st->box[2], true);
+    mv->volume_box = __fmul_rn(__fmul_rn(st->box[0], st->box[1]), st->box[2]);
+    mv->P.valid = 0;
+}
+
+__global__ void k_mcb_pack(int n, const float* __restrict__ x0, const float* __restrict__ x1,
+                           float4* __restrict__ q0, float4* __restrict__ q1,
+                           const chx_mc_baro_state* __restrict__ st) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* x = st->sel ? x1 : x0;
+    (st->sel ? q1 : q0)[i] = make_float4(x[3 * i], x[3 * i + 1], x[3 * i + 2], 0.f);
+}
+
+// energy over list set (sel ^ which) at positions q(sel ^ which); box and cutoffs from mv
+__global__ void __launch_bounds__(256)
+k_mcb_lj_nlist(int n, int M, float sigma, float eps, const uint32_t* __restrict__ list0,
+               const uint32_t* __restrict__ list1, const int32_t* __restrict__ nn0,
+               const int32_t* __restrict__ nn1, const float4* __restrict__ q0, const float4* __restrict__ q1,
+               const chx_mc_baro_state* __restrict__ st, const McbMove* __restrict__ mv, int which,
+               double* __restrict__ acc) {
+    if (st->halt) return;
+    const int set = (st->sel ^ which) & 1;
+    const float4* x = set ? q1 : q0;
+    const uint32_t* list = set ? list1 : list0;
+    const int32_t* nn = set ? nn1 : nn0;
+    const FastCut fc = mv->fc;
+    const Box box = which ? make_box(mv->box_new[0], mv->box_new[1], mv->box_new[2])
+                          : make_box(st->box[0], st->box[1], st->box[2]);
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    double e_acc = 0.0;
+    if (i < n) {
+        int cnt = nn[i];
+        cnt = cnt < M ? cnt : M;
+        e_acc = (double)lj_nlist_row_energy<true>(Pos4{x}, i, lane, box, fc, list + (size_t)i * M, cnt,
+                                                  sigma * sigma, eps);
+    }
+    mc_block_add(e_acc, acc);
+}
+
+__global__ void k_mcb_init(double beta, double pressure, chx_mc_baro_state* __restrict__ st,
+                           const McbMove* __restrict__ mv, double* __restrict__ acc) {
+    const double a = *acc;
+    *acc = 0.0;
+    st->u_current = (float)(beta * ((double)(float)a + pressure * (double)mv->volume_box));
+    st->have_u = 1;
+}
+
+__global__ void k_mcb_decide(int M, double beta, double pressure, chx_mc_baro_state* __restrict__ st,
+                             const McbMove* __restrict__ mv, double* __restrict__ acc, int* __restrict__ stats) {
+    const double a = *acc;
+    *acc = 0.0;
+    const int max_count = stats[0], eq_m = stats[1];
+    stats[0] = 0; stats[1] = 0;
+    if (st->halt) return;
+    (void)eq_m;
+    if (max_count >= M) {                 // n_max_neighbors must grow (neighbors.py:700-729): caller's job
+        st->halt = 1;
+        return;
+    }
+    const float u_cur = st->u_current;
+    const float u_new = (float)(beta * ((double)(float)a + pressure * (double)mv->volume_box));
+    const float lr = __fadd_rn(-__fsub_rn(u_new, u_cur), mv->log_volume);      // mcmc.py:1004-1006
+    uint32_t c0, c1, s0, s1;
+    threefry_split(st->key[0], st->key[1], c0, c1, s0, s1);
+    bool accept = false;
+    if (u_new != u_new) {
+        st->nan_seen += 1;
+    } else {
+        uint32_t d0, d1, t0, t1;
+        threefry_split(c0, c1, d0, d1, t0, t1);
+        c0 = d0; c1 = d1;
+        const float uni = uniform_from_bits(random_bits_elem(t0, t1, 0ull, 1ull), 0.0f, 1.0f);
+        accept = (-lr <= 0.0f) || (uni < expf(lr));
+    }
+    st->key[0] = c0; st->key[1] = c1;
+    st->last_volume = mv->volume_box;
+    if (accept) {
+        st->sel ^= 1;
+        st->u_current = u_new;
+        st->box[0] = mv->box_new[0]; st->box[1] = mv->box_new[1]; st->box[2] = mv->box_new[2];
+        st->n_accepted += 1;
+    }
+    st->n_proposed += 1;
+    st->moves_done += 1;
+}
+
+static int mcb_launch_energy(chx_ctx* ctx, const McbArgs& m, int which) {
+    const chx_mc_barostat_args& a = m.a;
+    k_mcb_lj_nlist<<<chx_div_up(a.n, 8), 256, 0, ctx->stream>>>(
+        a.n, a.M, a.sigma, a.epsilon, a.neighbor_list[0], a.neighbor_list[1], a.n_neighbors[0], a.n_neighbors[1],
+        m.q0, m.q1, m.st, m.mv, which, m.acc);
+    CHX_LAUNCHED(ctx);
+    return CHX_OK;
+}
+
+static int mcb_launch_move(chx_ctx* ctx, const McbArgs& m, int wshift, int warps, size_t smem) {
+    const chx_mc_barostat_args& a = m.a;
+    cudaStream_t st = ctx->stream;
+    const int* flip = &m.st->sel;
+    k_mcb_propose<<<chx_div_up(a.n, 256), 256, 0, st>>>(a.n, a.cutoff, a.cutoff_plus_skin, m.ncell_cap, m.x0, m.x1,
+                                                        m.q0, m.q1, m.st, m.mv);
+    CHX_LAUNCHED(ctx);
+    // list build on the proposal: positions x[1 - sel] -> list set 1 - sel
+    CHX_CUDA(cudaMemsetAsync(m.count, 0, sizeof(int) * ((size_t)m.ncell_cap + 1), st));
+    k_cell_count<<<chx_div_up(a.n, 256), 256, 0, st>>>(m.x1, a.n, &m.mv->P, m.cell_of, m.count, m.x0, flip);
+    CHX_LAUNCHED(ctx);
+    k_cell_scan<<<1, 1024, 0, st>>>(m.count, m.start, &m.mv->P);
+    CHX_LAUNCHED(ctx);
+    k_cell_fill<<<chx_div_up(a.n, 256), 256, 0, st>>>(m.x1, m.cell_of, a.n, &m.mv->P, m.start, m.count, m.order,
+                                                      m.xs4, m.x0, flip);
+    CHX_LAUNCHED(ctx);
+    int rc = cell_bm_launch(ctx, m.x1, m.xs4, a.n, &m.mv->P, a.M, wshift, warps, smem, m.cell_of, m.start,
+                            a.neighbor_list[1], a.neighbor_mask[1], a.n_neighbors[1], m.x0, a.neighbor_list[0],
+                            a.neighbor_mask[0], a.n_neighbors[0], flip);
+    if (rc != CHX_OK) return rc;
+    k_count_stats<<<chx_div_up(a.n, 256), 256, 0, st>>>(a.n_neighbors[1], a.n, a.M, m.stats, a.n_neighbors[0], flip,
+                                                        &m.st->halt);
+    CHX_LAUNCHED(ctx);
+    rc = mcb_launch_energy(ctx, m, 1);
+    if (rc != CHX_OK) return rc;
+    k_mcb_decide<<<1, 1, 0, st>>>(a.M, a.beta, a.pressure, m.st, m.mv, m.acc, m.stats);
+    CHX_LAUNCHED(ctx);
+    return CHX_OK;
+}
+
+extern "C" {
+
+int chx_mc_barostat_run(chx_ctx* ctx, const chx_mc_barostat_args* args, float* x0, float* x1,
+                        chx_mc_baro_state* state_dev, chx_mc_baro_state* state_host, int n_moves) {
+    CHX_REQUIRE(ctx && args && x0 && x1 && state_dev && state_host, "NULL argument");
+    const chx_mc_barostat_args& a = *args;
+    CHX_REQUIRE(a.n > 0 && a.M > 0 && n_moves >= 0, "n and M must be positive, n_moves non-negative");
+    for (int k = 0; k < 2; ++k)
+        CHX_REQUIRE(a.neighbor_list[k] && a.neighbor_mask[k] && a.n_neighbors[k], "two complete list sets are required");
+    int wshift, warps;
+    size_t smem;
+    CHX_REQUIRE(cell_bm_config(a.n, wshift, warps, smem), "too many particles for the bitmap list builder");
+    CellParams P0;
+    CHX_REQUIRE(make_cell_params(state_host->box[0], state_host->box[1], state_host->box[2], a.cutoff_plus_skin, 0, P0),
+                "the box must hold at least 3 cells of edge cutoff + skin per dimension");
+    McbArgs m;
+    memset(&m, 0, sizeof(m));
+    m.a = a; m.x0 = x0; m.x1 = x1; m.st = state_dev;
+    m.ncell_cap = a.ncell_capacity > 0 ? a.ncell_capacity : 2 * P0.ncell;
+    // context scratch: [acc 64 B][stats 64 B][pad][McbMove 512 B at +256][q0 | q1 | xs4: n float4 each]
+    //                  [cell_of n][count cap+1][start cap+1][order n]
+    static_assert(sizeof(McbMove) <= 512, "McbMove must fit its scratch slot");
+    const size_t n4 = (size_t)a.n * sizeof(float4);
+    const size_t bytes = 768 + 3 * n4 + sizeof(int) * (2 * (size_t)a.n + 2 * ((size_t)m.ncell_cap + 1));
+    unsigned char* scratch = (unsigned char*)chx_scratch(ctx, bytes);
+    if (!scratch) return CHX_CUDA_ERROR;
+    m.acc = (double*)scratch;
+    m.stats = (int*)(scratch + 64);
+    m.mv = (McbMove*)(scratch + 256);
+    m.q0 = (float4*)(scratch + 768);
+    m.q1 = m.q0 + a.n;
+    m.xs4 = m.q1 + a.n;
+    m.cell_of = (int*)(m.xs4 + a.n);
+    m.count = m.cell_of + a.n;
+    m.start = m.count + m.ncell_cap + 1;
+    m.order = m.start + m.ncell_cap + 1;
+    cudaStream_t st = ctx->stream;
+    state_host->halt = 0;
+    state_host->moves_done = 0;
+    CHX_CUDA(cudaMemcpyAsync(state_dev, state_host, sizeof(chx_mc_baro_state), cudaMemcpyHostToDevice, st));
+    CHX_CUDA(cudaMemsetAsync(scratch, 0, 768, st));
+    int rc = CHX_OK;
+    if (!state_host->have_u) {
+        k_mcb_current<<<1, 1, 0, st>>>(a.cutoff, state_dev, m.mv);
+        CHX_LAUNCHED(ctx);
+        k_mcb_pack<<<chx_div_up(a.n, 256), 256, 0, st>>>(a.n, x0, x1, m.q0, m.q1, state_dev);
+        CHX_LAUNCHED(ctx);
+        rc = mcb_launch_energy(ctx, m, 0);
+        if (rc != CHX_OK) return rc;
+        k_mcb_init<<<1, 1, 0, st>>>(a.beta, a.pressure, state_dev, m.mv, m.acc);
+        CHX_LAUNCHED(ctx);
+    }
+    // a move is ~0.4 ms of device time: plain launches (9 per move), no graph
+    for (int k = 0; k < n_moves && rc == CHX_OK; ++k) rc = mcb_launch_move(ctx, m, wshift, warps, smem);
+    if (rc != CHX_OK) return rc;
+    CHX_CUDA(cudaMemcpyAsync(state_host, state_dev, sizeof(chx_mc_baro_state), cudaMemcpyDeviceToHost, st));
     CHX_CUDA(cudaStreamSynchronize(st));
     return CHX_OK;
 }

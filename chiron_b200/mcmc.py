@@ -482,6 +482,118 @@ class MonteCarloBarostatMove(MCMove):
         elif acceptance_ratio > 0.75:
             self.volume_max_scale = min(self.volume_max_scale * 1.1, 0.3)
 
+    def _device_plan(self, sampler_state, thermodynamic_state, nbr_list):
+        """The barostat loop `chx_mc_barostat_run` covers LJPotential over a periodic NeighborListNsqrd."""
+        from .neighbors import NeighborListNsqrd
+        from .potential import LJPotential
+        ts = thermodynamic_state
+        if ts.temperature is None or ts.pressure is None or not torch.cuda.is_available():
+            return None
+        x = sampler_state.positions
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and x.shape[1] == 3):
+            return None
+        if type(ts.potential) is not LJPotential or not isinstance(nbr_list, NeighborListNsqrd):
+            return None
+        if not (nbr_list.is_built and nbr_list.space.periodic) or sampler_state.box_vectors is None:
+            return None
+        if nbr_list._cutoff_md() != ts.potential.cutoff or nbr_list.ref_positions.shape[0] != x.shape[0]:
+            return None
+        box = sampler_state.box_lengths_host()
+        if tuple(np.float32(v) for v in nbr_list._box_args()[:3]) != tuple(np.float32(v) for v in box):
+            return None
+        if min(box) < 3.0 * nbr_list._cutoff_plus_skin_md() * (1.0 + 1e-5) or x.shape[0] > 400_000:
+            return None
+        return True
+
+    def _update_device(self, plan, sampler_state, thermodynamic_state, nbr_list):
+        """`update()` on `chx_mc_barostat_run` (include/chiron_b200.h): positions, box and the two list
+        sets stay on the device; a move whose list would outgrow `n_max_neighbors` (or whose box gets too
+        small for the cell list) is made by `_step`."""
+        import ctypes as C
+        from .utils import kT_md
+        ts = thermodynamic_state
+        pot = ts.potential
+        remaining = self.number_of_moves
+        while remaining > 0:
+            x = _lib.as_device_f32(sampler_state.positions)
+            n, dev = x.shape[0], x.device
+            ctx = _lib.get_context(dev)
+            # set 0 = a private copy of the current list (the loop overwrites whichever set is not current)
+            sets = [tuple(t.clone() for t in (nbr_list.neighbor_list, nbr_list.neighbor_mask, nbr_list.n_neighbors))]
+            sets.append(tuple(torch.empty_like(t) for t in sets[0]))
+            a = _lib.McBarostatArgs()
+            a.n, a.M = n, int(sets[0][0].shape[1])
+            a.sigma, a.epsilon, a.cutoff = pot.sigma, pot.epsilon, pot.cutoff
+            a.cutoff_plus_skin = nbr_list._cutoff_plus_skin_md()
+            for k in range(2):
+                a.neighbor_list[k] = sets[k][0].data_ptr()
+                a.neighbor_mask[k] = sets[k][1].data_ptr()
+                a.n_neighbors[k] = sets[k][2].data_ptr()
+            a.beta = 1.0 / kT_md(ts.temperature)
+            a.pressure = float((ts.pressure * (1.0 * unit.nanometer ** 3) * unit.AVOGADRO_CONSTANT_NA)
+                               .value_in_unit_system(unit.md_unit_system))
+            a.ncell_capacity = 0
+            bufs = [x.clone(), torch.empty_like(x)]
+            st_dev = torch.zeros(16, dtype=torch.int32, device=dev)
+            st = _lib.McBaroState()
+            key = sampler_state._current_PRNG_key
+            st.key[0], st.key[1] = int(key[0]), int(key[1])
+            st.n_accepted, st.n_proposed = int(self.n_accepted), int(self.n_proposed)
+            st.box[0], st.box[1], st.box[2] = sampler_state.box_lengths_host()
+            accepted_before = int(self.n_accepted)
+            halted = False
+            moved = 0
+            while remaining > 0 and not halted:
+                seg = remaining
+                if self.autotune:
+                    seg = min(seg, self.autotune_interval - self._number_of_attempts_made % self.autotune_interval)
+                st.volume_max_scale = float(self.volume_max_scale)
+                ctx.call("chx_mc_barostat_run", C.byref(a), _lib.ptr(bufs[0]), _lib.ptr(bufs[1]),
+                         _lib.ptr(st_dev), C.byref(st), int(seg))
+                done = int(st.moves_done)
+                moved += done
+                remaining -= done
+                self._number_of_attempts_made += done
+                self.n_accepted, self.n_proposed = int(st.n_accepted), int(st.n_proposed)
+                halted = bool(st.halt)
+                if self.autotune and done > 0 and self._number_of_attempts_made % self.autotune_interval == 0:
+                    self._autotune()
+            if self.n_accepted != accepted_before:
+                sel = int(st.sel)
+                out = _shallow_state_copy(sampler_state)
+                out.positions = bufs[sel]
+                old_box = sampler_state.box_vectors
+                new_box = torch.zeros((3, 3), dtype=old_box.dtype, device=old_box.device)
+                for k in range(3):
+                    new_box[k, k] = float(st.box[k])
+                out.box_vectors = new_box
+                sampler_state = out
+                new_list = _copy_nbr_list(nbr_list)
+                new_list.ref_positions = bufs[sel]
+                new_list.box_vectors = new_box
+                new_list._arrays = sets[sel]
+                new_list.n_builds = nbr_list.n_builds + (self.n_accepted - accepted_before)
+                nbr_list = new_list
+            sampler_state._current_PRNG_key = np.array([st.key[0], st.key[1]], dtype=np.uint32)
+            if moved > 0:
+                ts.volume = float(st.last_volume) * unit.nanometer ** 3    # states.py:313-316, last evaluation
+            if halted:
+                self._current_reduced_potential = None
+                sampler_state, thermodynamic_state, nbr_list = self._step(sampler_state, thermodynamic_state, nbr_list)
+                self._number_of_attempts_made += 1
+                remaining -= 1
+                if self.autotune and self._number_of_attempts_made % self.autotune_interval == 0:
+                    self._autotune()
+                if remaining > 0 and self._device_plan(sampler_state, thermodynamic_state, nbr_list) is None:
+                    for _ in range(remaining):
+                        sampler_state, thermodynamic_state, nbr_list = self._step(
+                            sampler_state, thermodynamic_state, nbr_list)
+                        self._number_of_attempts_made += 1
+                    remaining = 0
+        self._current_reduced_potential = None
+        self._move_iteration += 1
+        return sampler_state, thermodynamic_state, nbr_list
+
     def _propose(self, current_sampler_state, current_thermodynamic_state, current_reduced_potential,
                  current_nbr_list=None):
         key = current_sampler_state.new_PRNG_key

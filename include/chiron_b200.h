@@ -210,6 +210,46 @@ typedef struct {
 int chx_mc_displace_run(chx_ctx* ctx, const chx_mc_displace_args* args, float* x0, float* x1,
                         chx_mc_state* state_dev, chx_mc_state* state_host, int n_moves);
 
+/* n_moves Monte Carlo BAROSTAT steps (chiron/mcmc.py:913-1009 MonteCarloBarostatMove._propose + :357-463
+ * _step) for LJPotential over a periodic NeighborListNsqrd, without a host round trip per step.  Per
+ * move: split the key; V1 = V0 + uniform(subkey,-1,1) * volume_max_scale * V0 and s = (V1/V0)^(1/3) in
+ * fp32 like mcmc.py:956-974; x' = x * s, box' = box * s; the neighbour list is REBUILT on (x', box') into
+ * the list set that is not current (cell grid of the proposed box, computed on the device; arrays
+ * identical to chx_nlist_build_cell); u' = beta (U(x') + P V'); accept iff the reference's test on
+ * -(u' - u) + N log(V1/V0) passes.  x[state.sel] / list set state.sel / state.box are the current
+ * configuration.  The loop stops BEFORE a move (state.halt = 1, key not advanced) when the proposed box
+ * has fewer than 3 cells per edge or more cells than `ncell_capacity`, or when a row reaches M
+ * neighbours (the reference's growth trigger, neighbors.py:709): the caller makes that move through
+ * the building blocks and re-enters. */
+typedef struct {
+    int n;                          /* particles */
+    float sigma, epsilon, cutoff;   /* LJ, md units */
+    float cutoff_plus_skin;         /* list radius, summed in double and rounded once like neighbors.py:674 */
+    int M;                          /* n_max_neighbors of both list sets */
+    uint32_t* neighbor_list[2];     /* device (n,M) each; set state.sel holds the current list on entry */
+    int32_t* neighbor_mask[2];      /* device (n,M) */
+    int32_t* n_neighbors[2];        /* device (n) */
+    double beta;                    /* mol/kJ */
+    double pressure;                /* P N_A in kJ/mol/nm^3 */
+    int ncell_capacity;             /* 0 = 2 x the cells of the entry box */
+} chx_mc_barostat_args;
+typedef struct {
+    uint32_t key[2];
+    int32_t sel;                    /* position buffer AND list set of the current configuration */
+    int32_t have_u;
+    float u_current;
+    float volume_max_scale;
+    int32_t n_accepted, n_proposed;
+    int32_t moves_done;
+    int32_t halt;
+    int32_t nan_seen;
+    float box[3];                   /* current box lengths (in/out) */
+    float last_volume;              /* volume of the last evaluated proposal (ThermodynamicState.volume) */
+    int32_t reserved;
+} chx_mc_baro_state;
+int chx_mc_barostat_run(chx_ctx* ctx, const chx_mc_barostat_args* args, float* x0, float* x1,
+                        chx_mc_baro_state* state_dev, chx_mc_baro_state* state_host, int n_moves);
+
 /* ---- Fused LJ Langevin engine (integrators.py:110-218 + neighbors.py + potential.py) -------------- */
 /* Runs whole trajectories on the device: cell-sorted particles, counting-sort cell list,
  * tiled neighbour structure, ONE kernel per Langevin step (forces over the tiles, then the BAOAB

@@ -28,7 +28,7 @@ def main(n_side=32, quiet=False):
     from loguru import logger
     if quiet:
         logger.remove()
-    out = {"api": "MCMCSampler.run (device-resident Metropolis loop for displacement moves, step-by-step barostat)"}
+    out = {"api": "MCMCSampler.run (device-resident Metropolis loops: chx_mc_displace_run, chx_mc_barostat_run)"}
     # ---- config 3 ----
     sigma, eps, rc, skin = 0.373, 0.2941, 1.4, 0.5
     n = n_side ** 3

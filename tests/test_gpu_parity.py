@@ -822,3 +822,66 @@ def test_mc_device_loop_lj_all_pairs(cuda_device, with_pairlist):
     a, b = out[True], out[False]
     assert a[0] == b[0] and 0 < a[0]["n_accepted"] < 40
     assert np.allclose(a[1], b[1], rtol=0, atol=1e-6) and np.array_equal(a[2], b[2])
+
+
+# ---------------------------------------------------------------------------------------------------
+# barostat loop on the device (csrc/mc.cu, chx_mc_barostat_run) == the step-by-step path
+# ---------------------------------------------------------------------------------------------------
+def _run_barostat_both_ways(skin, n_moves, scale, autotune=False):
+    from chiron_b200 import unit
+    from chiron_b200.mcmc import MonteCarloBarostatMove
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.utils import PRNG
+    out = {}
+    for loop in (True, False):
+        lj_sys, x, box = _lj_system(12, 0.8, seed=91)
+        potential = LJPotential(lj_sys.topology, lj_sys.sigma, lj_sys.epsilon, 1.02 * unit.nanometer)
+        PRNG.set_seed(1234)
+        state = SamplerState(positions=lj_sys.positions, current_PRNG_key=PRNG.get_random_key(),
+                             box_vectors=lj_sys.box_vectors)
+        ts = ThermodynamicState(potential=potential, temperature=300 * unit.kelvin, pressure=2000.0 * unit.atmosphere)
+        nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.02 * unit.nanometer, skin=skin * unit.nanometer,
+                               n_max_neighbors=180, builder="cell")
+        nl.build_from_state(state)
+        move = MonteCarloBarostatMove(volume_max_scale=scale, number_of_moves=n_moves, autotune=autotune,
+                                      autotune_interval=10)
+        move.device_loop = loop
+        s, ts_out, nl_out = move.update(state, ts, nl)
+        out[loop] = dict(stats=move.statistics, x=_np(s.positions), key=np.asarray(s._current_PRNG_key).copy(),
+                         box=_np(s.box_vectors), scale=move.volume_max_scale, nl=nl_out,
+                         volume=float(ts_out.volume.value_in_unit(unit.nanometer ** 3)),
+                         u=float(ts_out.get_reduced_potential(s, nl_out)), x0=x, box0=box)
+    return out
+
+
+def test_mc_barostat_device_loop_matches_stepwise(cuda_device):
+    """Same decisions, key and autotuned scale; positions and box equal to fp32 rounding (the loop takes
+    the cube root with CUDA's powf, the host path with NumPy's); the list handed back is the reference
+    list of the final configuration."""
+    out = _run_barostat_both_ways(skin=0.3, n_moves=30, scale=0.002, autotune=True)
+    a, b = out[True], out[False]
+    assert a["stats"] == b["stats"] and 0 < a["stats"]["n_accepted"] < 30
+    assert np.array_equal(a["key"], b["key"]) and a["scale"] == b["scale"]
+    assert np.allclose(a["box"], b["box"], rtol=1e-6) and not np.allclose(a["box"], a["box0"], rtol=1e-5)
+    assert np.allclose(a["x"], b["x"], rtol=2e-6, atol=1e-6)
+    assert np.isclose(a["volume"], b["volume"], rtol=1e-6) and np.isclose(a["u"], b["u"], rtol=1e-5)
+    # the list of the loop == a fresh reference build on the loop's final state
+    L = np.diag(a["box"])
+    ref = pairs.build_neighborlist(a["x"], a["box"], 1.02, 0.3, int(a["nl"].n_max_neighbors))
+    assert np.array_equal(_np(a["nl"].n_neighbors), ref["n_neighbors"])
+    assert np.array_equal(_np(a["nl"].neighbor_list).astype(np.uint32), ref["neighbor_list"])
+    assert np.array_equal(_np(a["nl"].ref_positions), a["x"]) and L.min() > 3.9
+
+
+def test_mc_barostat_device_loop_halts_when_the_cell_grid_breaks(cuda_device):
+    """List radius just under a third of the box: every compression leaves fewer than 3 cells per edge,
+    the loop stops before those moves and they run through the building blocks (O(N^2) builder)."""
+    lj_sys, x, box = _lj_system(12, 0.8, seed=91)
+    skin = float(box[0, 0]) / 3.0005 - 1.02
+    out = _run_barostat_both_ways(skin=skin, n_moves=16, scale=0.002)
+    a, b = out[True], out[False]
+    assert a["stats"] == b["stats"] and 0 < a["stats"]["n_accepted"] < 16
+    assert np.array_equal(a["key"], b["key"])
+    assert np.allclose(a["box"], b["box"], rtol=1e-6) and np.allclose(a["x"], b["x"], rtol=2e-6, atol=1e-6)
