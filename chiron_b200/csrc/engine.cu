@@ -466,7 +466,8 @@ k_md_cand(const float4* __restrict__ xs_all, const int2* __restrict__ range_all,
             qn += __popc(bal);
         }
     }
-    ovf = __any_sync(FULL, ovf);
+    const bool q_ovf = __any_sync(FULL, ovf);     // candidate queue too small (shared memory only)
+    ovf = false;
     if (qn > qcap) qn = qcap;
     __syncwarp();
 
@@ -568,6 +569,7 @@ k_md_cand(const float4* __restrict__ xs_all, const int2* __restrict__ range_all,
         generic_all[rb] = gen ? 1 : 0;
         bcenter_all[rb] = make_float4(bcx, bcy, bcz, 0.f);
         if (ovf) atomicOr(&rep[r].overflow, 1);
+        if (q_ovf) atomicOr(&rep[r].overflow, 4);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(FULL, pairs, o);
@@ -1421,7 +1423,19 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
             return rc;
         }
         // grow and rebuild the flagged replicas again (their sorted state is already in place):
-        // bit 0 = candidate queue / list too small, bit 1 = the deal ran out of tiles or of list words
+        // bit 0 = candidate list of a block too small, bit 1 = the deal ran out of tiles or of list words,
+        // bit 2 = candidate QUEUE (shared memory of k_md_cand) too small: no device array depends on it
+        if (ovf & 4) md->qcap = (md->qcap + md->qcap / 2 + 31) & ~31;
+        if (!(ovf & 3)) {
+            for (int r = 0; r < R; ++r) {
+                md->rep_host[r].overflow = 0;
+                md->rep_host[r].cand_pairs2 = 0;
+                md->rep_host[r].trip_slots = 0;
+            }
+            rc = md_upload_rep(md);
+            if (rc != CHX_OK) return rc;
+            continue;
+        }
         if (ovf & 1) { md->tcap *= 2; md->qcap *= 2; }
         if (ovf & 2) {
             if (md->lw < 6) md->lw += 2;
@@ -1562,7 +1576,15 @@ int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
         if (e && atoi(e) > 0) lw = atoi(e);
         md->lw = lw <= 2 ? 2 : (lw <= 4 ? 4 : 6);   // even: the force loop reads list words in pairs
     }
-    md->qcap = ((int)(2.5 * cand) + 256 + 31) & ~31;
+    {
+        // candidate queue per block in units of the expected candidate count: the bounding-box prefilter
+        // passes ~1.4x (it grows on overflow); a smaller queue lets more warps of k_md_cand share an SM
+        // (measured: step 74.7 / 73.6 / 73.4 / 72.9 us for 2.5 / 2.0 / 1.7 / 1.5)
+        double qf = 1.6;
+        const char* e = getenv("CHX_MD_QCAP");
+        if (e && atof(e) > 0.5) qf = atof(e);
+        md->qcap = ((int)(qf * cand) + 256 + 31) & ~31;
+    }
     md->rebuilds = 0; md->steps = 0; md->have_state = false; md->forces_valid = false;
     { const char* e = getenv("CHX_MD_NOGRAPH"); md->no_graph = e && e[0] == '1'; }
     md->launches0 = ctx->launches;
