@@ -885,3 +885,30 @@ def test_mc_barostat_device_loop_halts_when_the_cell_grid_breaks(cuda_device):
     assert a["stats"] == b["stats"] and 0 < a["stats"]["n_accepted"] < 16
     assert np.array_equal(a["key"], b["key"])
     assert np.allclose(a["box"], b["box"], rtol=1e-6) and np.allclose(a["x"], b["x"], rtol=2e-6, atol=1e-6)
+
+
+def test_mc_device_loop_nan_energy_is_rejected_with_one_key_split(cuda_device):
+    """Two particles on top of each other: every proposal has a NaN energy, which the reference rejects
+    WITHOUT drawing the acceptance uniform (mcmc.py:417-430), so the key advances by one split per move."""
+    from chiron_b200 import unit
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import _topology
+    from chiron_b200.utils import PRNG
+
+    def make():
+        x = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 0.0], [0.5, 0.1, 0.0], [0.0, 0.6, 0.2]], f32)
+        potential = LJPotential(_topology(4), 0.34 * unit.nanometer, 0.238 * unit.kilocalories_per_mole,
+                                1.02 * unit.nanometer)
+        PRNG.set_seed(1234)
+        state = SamplerState(positions=x * unit.nanometer, current_PRNG_key=PRNG.get_random_key())
+        return state, ThermodynamicState(potential=potential, temperature=300 * unit.kelvin), None
+    out = _run_move_both_ways(make, 12, displacement_sigma=0.01 * unit.nanometer, atom_subset=[2])
+    a, b = out[True], out[False]
+    assert a[0] == b[0] == dict(n_accepted=0, n_proposed=12)
+    assert np.array_equal(a[2], b[2])
+    key = jr.PRNGKey(1234)
+    key = jr.split(key)[1]                       # PRNG.get_random_key() hands out the subkey
+    for _ in range(12):
+        key = jr.split(key)[0]
+    assert np.array_equal(a[2], key)
