@@ -54,6 +54,7 @@ static __global__ void k_count_stats(const int32_t* nn, int n, int M, int* __res
 struct CellGrid {
     int nx, ny, nz;
     float inv_cx, inv_cy, inv_cz;  // 1 / cell edge
+    int S;                         // stencil radius: cells of edge >= (cutoff+skin) / S, (2S+1)^3 cells swept
 };
 
 struct SweepConst {
@@ -73,18 +74,24 @@ struct CellParams {
     int valid;             // 0: the build is skipped (grid unusable: the caller falls back)
 };
 
-// nx, ny, nz >= 3 cells of edge >= (cutoff+skin)(1+1e-5) (binning uses a rounded wrapped coordinate, the
-// margin keeps every pair inside the predicate within the 27-cell stencil), at most 256 per edge
+// Cells of edge >= (cutoff+skin)(1+1e-5) / S (binning uses a rounded wrapped coordinate, the margin keeps
+// every pair inside the predicate within the (2S+1)^3 stencil), at least 2S+1 and at most 256 per edge.
+// S = 2 (half-size cells, 125 of them: 2.2x less volume to search than 27 full-size ones) when the box and
+// the cell capacity allow it, else S = 1.
 __host__ __device__ inline bool make_cell_params(float lx, float ly, float lz, float cutoff_plus_skin,
                                                  int ncell_cap, CellParams& P) {
-    const double rc = (double)cutoff_plus_skin * (1.0 + 1e-5);
-    int nx = (int)floor((double)lx / rc), ny = (int)floor((double)ly / rc), nz = (int)floor((double)lz / rc);
     P.valid = 0;
-    if (nx < 3 || ny < 3 || nz < 3) return false;
-    nx = nx > 256 ? 256 : nx; ny = ny > 256 ? 256 : ny; nz = nz > 256 ? 256 : nz;
-    if (ncell_cap > 0 && nx * ny * nz > ncell_cap) return false;
+    int nx = 0, ny = 0, nz = 0, S = 0;
+    for (int s = 2; s >= 1 && S == 0; --s) {
+        const double rc = (double)cutoff_plus_skin * (1.0 + 1e-5) / s;
+        nx = (int)floor((double)lx / rc); ny = (int)floor((double)ly / rc); nz = (int)floor((double)lz / rc);
+        nx = nx > 256 ? 256 : nx; ny = ny > 256 ? 256 : ny; nz = nz > 256 ? 256 : nz;
+        const int need = 2 * s + 1;
+        if (nx >= need && ny >= need && nz >= need && (ncell_cap <= 0 || nx * ny * nz <= ncell_cap)) S = s;
+    }
+    if (S == 0) return false;
     P.box = make_box(lx, ly, lz);
-    P.g.nx = nx; P.g.ny = ny; P.g.nz = nz;
+    P.g.nx = nx; P.g.ny = ny; P.g.nz = nz; P.g.S = S;
     P.g.inv_cx = (float)(nx / (double)lx); P.g.inv_cy = (float)(ny / (double)ly); P.g.inv_cz = (float)(nz / (double)lz);
     P.ncell = nx * ny * nz;
     P.sc.c = cutoff_plus_skin;
@@ -206,36 +213,42 @@ k_build_cell_bm(const float* x, const float4* __restrict__ xs4, int n,
     const float xw = ref_wrap(xi, box.lx), yw = ref_wrap(yi, box.ly), zw = ref_wrap(zi, box.lz);
     const int ci = cell_of[i];
     const int cz = ci % g.nz, cy = (ci / g.nz) % g.ny, cx = ci / (g.nz * g.ny);
-    for (int dx = -1; dx <= 1; ++dx) {
+    const int S = g.S;
+    for (int dx = -S; dx <= S; ++dx) {
         int ax = cx + dx;
         float xs = xw;                       // row particle shifted into the neighbour cell's image
         if (ax < 0) { ax += g.nx; xs = xw + box.lx; } else if (ax >= g.nx) { ax -= g.nx; xs = xw - box.lx; }
-        for (int dy = -1; dy <= 1; ++dy) {
+        for (int dy = -S; dy <= S; ++dy) {
             int ay = cy + dy;
             float ys = yw;
             if (ay < 0) { ay += g.ny; ys = yw + box.ly; } else if (ay >= g.ny) { ay -= g.ny; ys = yw - box.ly; }
-            for (int dz = -1; dz <= 1; ++dz) {
-                int az = cz + dz;
-                float zs = zw;
-                if (az < 0) { az += g.nz; zs = zw + box.lz; } else if (az >= g.nz) { az -= g.nz; zs = zw - box.lz; }
-                const int cc = (ax * g.ny + ay) * g.nz + az;
-                const int s = start[cc], e = start[cc + 1];
-                for (int t = s + lane; t < e; t += 32) {
-                    const float4 p = xs4[t];
-                    const int j = __float_as_int(p.w);
-                    if (j <= i) continue;
-                    const float ddx = xs - p.x, ddy = ys - p.y, ddz = zs - p.z;
-                    const float r2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
-                    if (r2 >= sc.c2_hi) continue;
-                    if (r2 >= sc.c2_lo) {
-                        float rx, ry, rz, d;
-                        ref_displacement<true>(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2], box, rx, ry, rz, d);
-                        if (!(d < sc.c)) continue;
-                    }
-                    const int q = j >> 5;
-                    atomicOr(&bm[q + (q >> wshift)], 1u << (j & 31));
-                }
-            }
+            // the cells cz - S .. cz + S of this column are contiguous in cell order: one run, or two
+            // when the column wraps around the box in z
+            const int col = (ax * g.ny + ay) * g.nz;
+#define CL_SWEEP_RUN(A0, A1, ZS)                                                                          \
+            do {                                                                                          \
+                const float zs = (ZS);                                                                    \
+                const int s = start[col + (A0)], e = start[col + (A1) + 1];                               \
+                for (int t = s + lane; t < e; t += 32) {                                                  \
+                    const float4 p = xs4[t];                                                              \
+                    const int j = __float_as_int(p.w);                                                    \
+                    if (j <= i) continue;                                                                 \
+                    const float ddx = xs - p.x, ddy = ys - p.y, ddz = zs - p.z;                           \
+                    const float r2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));                           \
+                    if (r2 >= sc.c2_hi) continue;                                                         \
+                    if (r2 >= sc.c2_lo) {                                                                 \
+                        float rx, ry, rz, d;                                                              \
+                        ref_displacement<true>(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2], box, rx, ry, rz, d); \
+                        if (!(d < sc.c)) continue;                                                        \
+                    }                                                                                     \
+                    const int q = j >> 5;                                                                 \
+                    atomicOr(&bm[q + (q >> wshift)], 1u << (j & 31));                                     \
+                }                                                                                         \
+            } while (0)
+            CL_SWEEP_RUN(max(cz - S, 0), min(cz + S, g.nz - 1), zw);
+            if (cz - S < 0) CL_SWEEP_RUN(cz - S + g.nz, g.nz - 1, zw + box.lz);
+            if (cz + S >= g.nz) CL_SWEEP_RUN(0, cz + S - g.nz, zw - box.lz);
+#undef CL_SWEEP_RUN
         }
     }
     __syncwarp();

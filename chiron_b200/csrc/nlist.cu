@@ -102,11 +102,11 @@ k_build_cell(const float* __restrict__ x, int n, Box box, CellGrid g, float c, i
     const int ci = cell_of[i];
     const int cz = ci % g.nz, cy = (ci / g.nz) % g.ny, cx = ci / (g.nz * g.ny);
     int count = 0;
-    for (int dx = -1; dx <= 1; ++dx) {
+    for (int dx = -g.S; dx <= g.S; ++dx) {
         int ax = cx + dx; ax = ax < 0 ? ax + g.nx : (ax >= g.nx ? ax - g.nx : ax);
-        for (int dy = -1; dy <= 1; ++dy) {
+        for (int dy = -g.S; dy <= g.S; ++dy) {
             int ay = cy + dy; ay = ay < 0 ? ay + g.ny : (ay >= g.ny ? ay - g.ny : ay);
-            for (int dz = -1; dz <= 1; ++dz) {
+            for (int dz = -g.S; dz <= g.S; ++dz) {
                 int az = cz + dz; az = az < 0 ? az + g.nz : (az >= g.nz ? az - g.nz : az);
                 const int cc = (ax * g.ny + ay) * g.nz + az;
                 const int s = start[cc], e = start[cc + 1];
