@@ -35,7 +35,7 @@ __device__ __forceinline__ void block_add_double(double v, double* target) {
 // classified with the fast test (exact predicate only within a few ulps of the cutoff); energies and
 // forces come from r2 without sqrt / division (relative error ~1e-7).
 template <bool PERIODIC, bool WANT_E, bool WANT_F>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, WANT_F ? 1 : 8)
 k_lj_nlist(const float* __restrict__ x, int n, Box box, FastCut fc, const uint32_t* __restrict__ list,
            const int32_t* __restrict__ nn, int M, float sigma, float eps,
            double* __restrict__ energy, float* __restrict__ force) {
