@@ -94,3 +94,45 @@ def test_metropolis_acceptance_matches_oracle_statistics(cuda_device):
     p = (move.statistics["n_accepted"] + acc) / (n_gpu + n_cpu)
     assert 0.1 < p < 0.9, p
     assert abs(p_gpu - p_cpu) < 3.0 * np.sqrt(p * (1 - p) * (1.0 / n_gpu + 1.0 / n_cpu)), (p_gpu, p_cpu)
+
+
+def test_ideal_gas_npt_volume_distribution(cuda_device):
+    """The reference's (skipped) convergence test and Examples/Idealgas.py:137-150: ideal gas N = 216 at
+    298 K, 1 atm with displacement + barostat moves.  The Metropolis barostat samples
+    p(V) ~ V^N exp(-beta P V): <V> = (N+1) kT / P and sigma_V = sqrt(N+1) kT / P.  The reference asks for
+    5 % on the mean and 10 % on sigma after 1000 iterations; this shorter run (the displacement moves go
+    through the device-resident loop) checks the mean within 5 % and sigma within 30 %."""
+    from chiron_b200 import unit
+    from chiron_b200.mcmc import MCMCSampler, MonteCarloBarostatMove, MonteCarloDisplacementMove, MoveSchedule
+    from chiron_b200.neighbors import OrthogonalPeriodicSpace, PairListNsqrd
+    from chiron_b200.potential import IdealGasPotential
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import _topology
+    from chiron_b200.utils import PRNG
+    n = 216
+    kT_over_P = R_GAS * 298.0 / (1.0 * 101325.0 * 6.02214076e23 * 1e-27 / 1000.0)   # nm^3 (P N_A in kJ/mol/nm^3)
+    v_expected = (n + 1) * kT_over_P
+    L = float(v_expected ** (1.0 / 3.0))
+    rng = np.random.default_rng(7)
+    PRNG.set_seed(1234)
+    state = SamplerState((rng.random((n, 3)) * L).astype(np.float32) * unit.nanometer, PRNG.get_random_key(),
+                         box_vectors=(np.eye(3, dtype=np.float32) * L) * unit.nanometer)
+    ts = ThermodynamicState(IdealGasPotential(_topology(n)), temperature=298 * unit.kelvin,
+                            pressure=1.0 * unit.atmosphere)
+    nl = PairListNsqrd(OrthogonalPeriodicSpace(), cutoff=0 * unit.nanometer)
+    nl.build_from_state(state)
+    disp = MonteCarloDisplacementMove(displacement_sigma=0.1 * unit.nanometer, number_of_moves=20)
+    baro = MonteCarloBarostatMove(volume_max_scale=0.1, number_of_moves=10, autotune=True, autotune_interval=50)
+    sampler = MCMCSampler(MoveSchedule([("displacement", disp), ("barostat", baro)]))
+    volumes = []
+    for it in range(160):
+        state, ts, nl = sampler.run(state, ts, 1, nl)
+        if it >= 30:
+            lx, ly, lz = state.box_lengths_host()
+            volumes.append(lx * ly * lz)
+    volumes = np.array(volumes)
+    assert disp.statistics["n_accepted"] == disp.statistics["n_proposed"]          # U = 0
+    assert 0.2 < baro.statistics["n_accepted"] / baro.statistics["n_proposed"] < 0.95
+    assert abs(volumes.mean() / v_expected - 1.0) < 0.05, (volumes.mean(), v_expected)
+    sigma_expected = np.sqrt(n + 1) * kT_over_P
+    assert abs(volumes.std(ddof=1) / sigma_expected - 1.0) < 0.30, (volumes.std(ddof=1), sigma_expected)
