@@ -912,3 +912,40 @@ def test_mc_device_loop_nan_energy_is_rejected_with_one_key_split(cuda_device):
     for _ in range(12):
         key = jr.split(key)[0]
     assert np.array_equal(a[2], key)
+
+
+def test_mc_loops_at_config3_size(cuda_device):
+    """BASELINE.json config 3 (LJ NPT, N = 32,768, UA-TraPPE methane parameters of Examples/LJ_MCMC.py):
+    a few displacement and barostat moves through the device loops against the step-by-step path."""
+    from chiron_b200 import unit
+    from chiron_b200.mcmc import MonteCarloBarostatMove, MonteCarloDisplacementMove
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import LennardJonesFluid
+    from chiron_b200.utils import PRNG
+    sigma, eps, rc, skin = 0.373, 0.2941, 1.4, 0.5
+    res = {}
+    for loop in (True, False):
+        lj = LennardJonesFluid(nparticles=32 ** 3, reduced_density=14.08 * sigma ** 3, sigma=sigma * unit.nanometer,
+                               epsilon=eps * unit.kilocalories_per_mole, mass=16.04, seed=3, symbol="C")
+        pot_ = LJPotential(lj.topology, lj.sigma, lj.epsilon, rc * unit.nanometer)
+        PRNG.set_seed(1234)
+        state = SamplerState(lj.positions, PRNG.get_random_key(), box_vectors=lj.box_vectors)
+        ts = ThermodynamicState(pot_, temperature=140 * unit.kelvin, pressure=13.00765 * unit.atmosphere)
+        nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=rc * unit.nanometer, skin=skin * unit.nanometer,
+                               n_max_neighbors=400, builder="cell")
+        nl.build_from_state(state)
+        disp = MonteCarloDisplacementMove(displacement_sigma=0.0001 * unit.nanometer, number_of_moves=12)
+        baro = MonteCarloBarostatMove(volume_max_scale=0.0001, number_of_moves=8)
+        disp.device_loop = baro.device_loop = loop
+        state, ts, nl = disp.update(state, ts, nl)
+        state, ts, nl = baro.update(state, ts, nl)
+        res[loop] = (disp.statistics, baro.statistics, _np(state.positions), _np(state.box_vectors),
+                     np.asarray(state._current_PRNG_key).copy(), int(nl.n_neighbors.sum().item()))
+    a, b = res[True], res[False]
+    assert a[0] == b[0] and 0 < a[0]["n_accepted"] < 12
+    assert a[1] == b[1] and a[1]["n_proposed"] == 8, (a[1], b[1])
+    assert np.array_equal(a[4], b[4])
+    assert np.allclose(a[3], b[3], rtol=1e-6) and np.allclose(a[2], b[2], rtol=2e-6, atol=2e-6)
+    assert abs(a[5] - b[5]) <= 2      # list of the final configuration: positions equal to fp32 rounding
