@@ -87,7 +87,8 @@ class McBarostatArgs(C.Structure):
     """chx_mc_barostat_args (include/chiron_b200.h)."""
     _fields_ = [("n", _I), ("sigma", _F), ("epsilon", _F), ("cutoff", _F), ("cutoff_plus_skin", _F), ("M", _I),
                 ("neighbor_list", _P * 2), ("neighbor_mask", _P * 2), ("n_neighbors", _P * 2),
-                ("beta", C.c_double), ("pressure", C.c_double), ("ncell_capacity", _I)]
+                ("beta", C.c_double), ("pressure", C.c_double), ("ncell_capacity", _I),
+                ("superset_list", _P), ("superset_nn", _P)]
 
 
 class McBaroState(C.Structure):

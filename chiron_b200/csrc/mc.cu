@@ -11,6 +11,8 @@
 // A proposal that would make NeighborListNsqrd.check() true (mcmc.py:754-759: rebuild on the
 // proposed positions) stops the loop BEFORE that move (state.halt = 1, key not advanced); the caller
 // performs that one move through the building-block path, which rebuilds the list, and re-enters.
+#include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -620,6 +622,106 @@ static int mcb_launch_energy(chx_ctx* ctx, const McbArgs& m, int which) {
     return CHX_OK;
 }
 
+// List of the proposal by filtering the superset list (built once per call at radius (cutoff+skin)(1+delta)):
+// one warp per row, exact predicate on the scaled positions, ballot compaction keeps the id order, so the
+// arrays equal the ones the 125-cell sweep writes.
+__global__ void __launch_bounds__(256, 6)
+k_mcb_filter(int n, int M, const uint32_t* __restrict__ sup_list, const int32_t* __restrict__ sup_nn,
+             const float4* __restrict__ q0, const float4* __restrict__ q1,
+             const chx_mc_baro_state* __restrict__ st, const McbMove* __restrict__ mv,
+             uint32_t* list0, uint32_t* list1, int32_t* mask0, int32_t* mask1, int32_t* nn0, int32_t* nn1) {
+    if (st->halt) return;
+    const int tgt = (st->sel ^ 1) & 1;
+    const float4* x = tgt ? q1 : q0;
+    uint32_t* list = tgt ? list1 : list0;
+    int32_t* mask = tgt ? mask1 : mask0;
+    int32_t* nn = tgt ? nn1 : nn0;
+    const Box box = make_box(mv->box_new[0], mv->box_new[1], mv->box_new[2]);
+    FastCut fc;
+    fc.c = mv->P.sc.c; fc.c2_lo = mv->P.sc.c2_lo; fc.c2_hi = mv->P.sc.c2_hi;
+    fc.inv_lx = mv->P.sc.inv_lx; fc.inv_ly = mv->P.sc.inv_ly; fc.inv_lz = mv->P.sc.inv_lz;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float4 xi = x[i];
+    int cnt = sup_nn[i];
+    cnt = cnt < M ? cnt : M;
+    int count = 0;
+    uint32_t first = 0u;
+    const uint32_t* row = sup_list + (size_t)i * M;
+    // four chunks of 32 entries in flight: the index loads and the position gathers are issued before
+    // any test, so the two dependent memory latencies per entry overlap
+    for (int k0 = 0; k0 < cnt; k0 += 128) {
+        uint32_t j[4];
+        float4 p[4];
+        bool hit[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + 32 * u + lane;
+            j[u] = k < cnt ? row[k] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[u] = x[j[u] != 0xffffffffu ? j[u] : (uint32_t)i];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float r2, dx, dy, dz;
+            hit[u] = j[u] != 0xffffffffu &&
+                     fast_within<true>(xi.x, xi.y, xi.z, p[u].x, p[u].y, p[u].z, box, fc, r2, dx, dy, dz);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned b = __ballot_sync(0xffffffffu, hit[u]);
+            if (b) {
+                if (count == 0) first = __shfl_sync(0xffffffffu, j[u], __ffs(b) - 1);
+                if (hit[u]) {
+                    const int pos = count + __popc(b & ((1u << lane) - 1u));
+                    if (pos < M) list[(size_t)i * M + pos] = j[u];
+                }
+                count += __popc(b);
+            }
+        }
+    }
+    // Incremental row finalisation (neighbors.py:606-609 semantics as in finish_row): the target set holds
+    // a complete, valid row from an earlier build (both sets start as copies of the current list), so
+    // only what differs is written -- the pad mask between the old and the new count, and the padding ids
+    // where entries turned into padding or when the fill value changed.  Saves the 2 x N x M words a full
+    // rewrite moves per proposal.
+    const int old_count = nn[i];
+    uint32_t fill = count > 0 ? first : 0u;
+    if (fill == (uint32_t)i) fill += 1u;
+    const int stored = count < M ? count : M;
+    const int old_stored = old_count < M ? old_count : M;
+    const bool had_pad = old_stored < M;
+    const uint32_t old_fill = had_pad ? list[(size_t)i * M + M - 1] : fill;
+    __syncwarp();
+    const int pad_to = (had_pad && old_fill == fill) ? (old_stored > stored ? old_stored : stored) : M;
+    for (int k = stored + lane; k < pad_to; k += 32) list[(size_t)i * M + k] = fill;
+    const int lo = count < old_count ? count : old_count, hi = count < old_count ? old_count : count;
+    for (int k = lo + lane; k < (hi < M ? hi : M); k += 32) mask[(size_t)i * M + k] = (k < count) ? 1 : 0;
+    if (lane == 0) nn[i] = count;
+}
+
+static int mcb_launch_move_filtered(chx_ctx* ctx, const McbArgs& m) {
+    const chx_mc_barostat_args& a = m.a;
+    cudaStream_t st = ctx->stream;
+    const int* flip = &m.st->sel;
+    k_mcb_propose<<<chx_div_up(a.n, 256), 256, 0, st>>>(a.n, a.cutoff, a.cutoff_plus_skin, m.ncell_cap, m.x0, m.x1,
+                                                        m.q0, m.q1, m.st, m.mv);
+    CHX_LAUNCHED(ctx);
+    k_mcb_filter<<<chx_div_up(a.n, 8), 256, 0, st>>>(a.n, a.M, a.superset_list, a.superset_nn, m.q0, m.q1, m.st, m.mv,
+                                                     a.neighbor_list[0], a.neighbor_list[1], a.neighbor_mask[0],
+                                                     a.neighbor_mask[1], a.n_neighbors[0], a.n_neighbors[1]);
+    CHX_LAUNCHED(ctx);
+    k_count_stats<<<chx_div_up(a.n, 256), 256, 0, st>>>(a.n_neighbors[1], a.n, a.M, m.stats, a.n_neighbors[0], flip,
+                                                        &m.st->halt);
+    CHX_LAUNCHED(ctx);
+    int rc = mcb_launch_energy(ctx, m, 1);
+    if (rc != CHX_OK) return rc;
+    k_mcb_decide<<<1, 1, 0, st>>>(a.M, a.beta, a.pressure, m.st, m.mv, m.acc, m.stats);
+    CHX_LAUNCHED(ctx);
+    return CHX_OK;
+}
+
 static int mcb_launch_move(chx_ctx* ctx, const McbArgs& m, int wshift, int warps, size_t smem) {
     const chx_mc_barostat_args& a = m.a;
     cudaStream_t st = ctx->stream;
@@ -702,8 +804,44 @@ int chx_mc_barostat_run(chx_ctx* ctx, const chx_mc_barostat_args* args, float* x
         k_mcb_init<<<1, 1, 0, st>>>(a.beta, a.pressure, state_dev, m.mv, m.acc);
         CHX_LAUNCHED(ctx);
     }
-    // a move is ~0.4 ms of device time: plain launches (9 per move), no graph
-    for (int k = 0; k < n_moves && rc == CHX_OK; ++k) rc = mcb_launch_move(ctx, m, wshift, warps, smem);
+    // superset list: one sweep at a slightly larger radius now, a filter pass per move
+    bool filtered = false;
+    if (a.superset_list && a.superset_nn && n_moves > 0 && state_host->volume_max_scale < 0.5f) {
+        static int use_sup = -1;
+        if (use_sup < 0) { const char* e = getenv("CHX_MC_NO_SUPERSET"); use_sup = (e && e[0] == '1') ? 0 : 1; }
+        const double delta = pow(1.0 - (double)state_host->volume_max_scale, -(double)n_moves / 3.0) - 1.0 + 1e-4;
+        CellParams Ps;
+        const float r_sup = (float)((double)a.cutoff_plus_skin * (1.0 + delta));
+        if (use_sup && delta <= 0.03 &&
+            make_cell_params(state_host->box[0], state_host->box[1], state_host->box[2], r_sup, m.ncell_cap, Ps)) {
+            // the superset build reuses the geometry slot of the moves (k_mcb_propose overwrites it later)
+            CellParams* Ps_dev = &m.mv->P;
+            memcpy(ctx->host_pinned + 8, &Ps, sizeof(Ps));
+            CHX_CUDA(cudaMemcpyAsync(Ps_dev, ctx->host_pinned + 8, sizeof(Ps), cudaMemcpyHostToDevice, st));
+            const int cur = state_host->sel & 1;
+            const float* xc = cur ? x1 : x0;
+            CHX_CUDA(cudaMemsetAsync(m.count, 0, sizeof(int) * ((size_t)m.ncell_cap + 1), st));
+            k_cell_count<<<chx_div_up(a.n, 256), 256, 0, st>>>(xc, a.n, Ps_dev, m.cell_of, m.count);
+            CHX_LAUNCHED(ctx);
+            k_cell_scan<<<1, 1024, 0, st>>>(m.count, m.start, Ps_dev);
+            CHX_LAUNCHED(ctx);
+            k_cell_fill<<<chx_div_up(a.n, 256), 256, 0, st>>>(xc, m.cell_of, a.n, Ps_dev, m.start, m.count, m.order, m.xs4);
+            CHX_LAUNCHED(ctx);
+            // ids and counts go to the superset arrays, the pad mask to the list set that is not current
+            rc = cell_bm_launch(ctx, xc, m.xs4, a.n, Ps_dev, a.M, wshift, warps, smem, m.cell_of, m.start,
+                                a.superset_list, a.neighbor_mask[1 - cur], a.superset_nn);
+            if (rc != CHX_OK) return rc;
+            k_count_stats<<<chx_div_up(a.n, 256), 256, 0, st>>>(a.superset_nn, a.n, a.M, m.stats);
+            CHX_LAUNCHED(ctx);
+            CHX_CUDA(cudaMemcpyAsync(ctx->host_pinned, m.stats, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CHX_CUDA(cudaMemsetAsync(m.stats, 0, 2 * sizeof(int), st));
+            CHX_CUDA(cudaStreamSynchronize(st));
+            filtered = ctx->host_pinned[0] < a.M;      // every superset row fits
+        }
+    }
+    // a move is ~0.1 ms (filtered) / ~0.3 ms (sweep) of device time: plain launches, no graph
+    for (int k = 0; k < n_moves && rc == CHX_OK; ++k)
+        rc = filtered ? mcb_launch_move_filtered(ctx, m) : mcb_launch_move(ctx, m, wshift, warps, smem);
     if (rc != CHX_OK) return rc;
     CHX_CUDA(cudaMemcpyAsync(state_host, state_dev, sizeof(chx_mc_baro_state), cudaMemcpyDeviceToHost, st));
     CHX_CUDA(cudaStreamSynchronize(st));

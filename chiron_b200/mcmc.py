@@ -520,7 +520,7 @@ class MonteCarloBarostatMove(MCMove):
             ctx = _lib.get_context(dev)
             # set 0 = a private copy of the current list (the loop overwrites whichever set is not current)
             sets = [tuple(t.clone() for t in (nbr_list.neighbor_list, nbr_list.neighbor_mask, nbr_list.n_neighbors))]
-            sets.append(tuple(torch.empty_like(t) for t in sets[0]))
+            sets.append(tuple(t.clone() for t in sets[0]))     # both sets start valid: rows are updated incrementally
             a = _lib.McBarostatArgs()
             a.n, a.M = n, int(sets[0][0].shape[1])
             a.sigma, a.epsilon, a.cutoff = pot.sigma, pot.epsilon, pot.cutoff
@@ -533,6 +533,8 @@ class MonteCarloBarostatMove(MCMove):
             a.pressure = float((ts.pressure * (1.0 * unit.nanometer ** 3) * unit.AVOGADRO_CONSTANT_NA)
                                .value_in_unit_system(unit.md_unit_system))
             a.ncell_capacity = 0
+            superset = (torch.empty_like(sets[0][0]), torch.empty_like(sets[0][2]))
+            a.superset_list, a.superset_nn = superset[0].data_ptr(), superset[1].data_ptr()
             bufs = [x.clone(), torch.empty_like(x)]
             st_dev = torch.zeros(16, dtype=torch.int32, device=dev)
             st = _lib.McBaroState()

@@ -226,12 +226,21 @@ typedef struct {
     float sigma, epsilon, cutoff;   /* LJ, md units */
     float cutoff_plus_skin;         /* list radius, summed in double and rounded once like neighbors.py:674 */
     int M;                          /* n_max_neighbors of both list sets */
-    uint32_t* neighbor_list[2];     /* device (n,M) each; set state.sel holds the current list on entry */
+    uint32_t* neighbor_list[2];     /* device (n,M) each; set state.sel holds the current list on entry and the
+                                       other set a complete valid list too (a copy): rows are updated in place */
     int32_t* neighbor_mask[2];      /* device (n,M) */
     int32_t* n_neighbors[2];        /* device (n) */
     double beta;                    /* mol/kJ */
     double pressure;                /* P N_A in kJ/mol/nm^3 */
     int ncell_capacity;             /* 0 = 2 x the cells of the entry box */
+    /* Optional superset list (device (n,M) ids and (n) counts, caller-allocated scratch): when given, one
+     * list of radius (cutoff+skin)(1+delta) is built at the start of the call, delta bounding the
+     * compression n_moves moves can produce, and every proposal's list is obtained by FILTERING it with the
+     * exact predicate on the scaled positions (rows stay in id order, so the arrays are the ones a fresh
+     * build gives) instead of a 125-cell sweep.  Falls back to the sweep when delta > 3 % or a superset row
+     * does not fit M. */
+    uint32_t* superset_list;
+    int32_t* superset_nn;
 } chx_mc_barostat_args;
 typedef struct {
     uint32_t key[2];
