@@ -70,8 +70,12 @@ k_mcl_propose(int n, const float* __restrict__ mask, Box box, const float* __res
         float xn[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float d = __fmul_rn(normal_from_bits(random_bits_elem(s0, s1, 3ull * i + c, total)), sigma);
-            if (mask) d = __fmul_rn(d, m);
+            // a zero mask multiplies the (finite) noise to +-0, and x + (+-0) == x: no need to draw it
+            float d = 0.0f;
+            if (m != 0.0f) {
+                d = __fmul_rn(normal_from_bits(random_bits_elem(s0, s1, 3ull * i + c, total)), sigma);
+                if (mask) d = __fmul_rn(d, m);
+            }
             float v = __fadd_rn(xc[3 * i + c], d);
             if (WRAP) v = ref_wrap(v, c == 0 ? box.lx : (c == 1 ? box.ly : box.lz));
             xp[3 * i + c] = v;
@@ -383,6 +387,190 @@ static int mc_graph_get(chx_ctx* ctx, const McArgs& m, cudaGraphExec_t* out) {
     return CHX_OK;
 }
 
+// ---- small systems: the whole loop in ONE launch --------------------------------------------------------
+// For n <= MC_SMALL_MAX_N a move is far too little work for three launches (the loop above runs at the
+// graph-node latency floor, ~2 us per node).  One CTA keeps both position buffers in shared memory and
+// runs all n_moves moves back to back: propose (+wrap, +check), energy, decision by thread 0, swap of the
+// buffer roles.  Same PRNG stream, same arithmetic per term, so the trajectory equals the multi-launch
+// path's (sums differ in the order of fp64 additions only).
+#define MC_SMALL_MAX_N 2048
+#define MC_SMALL_THREADS 512
+
+__device__ __forceinline__ double mc_cta_sum(double v, double* sh) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();                 // sh may still be read from the previous call
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < (MC_SMALL_THREADS >> 5); ++k) t += sh[k];   // same order in every thread
+    return t;
+}
+
+template <int POT, bool PERIODIC>
+__device__ __forceinline__ double mc_small_energy(const chx_mc_displace_args& a, const Box& box, const FastCut& fc,
+                                                  const float* xa, const float* xb, double* sh) {
+    // U of xb (HO, list LJ) or U(xb) - U(xa) (subset delta); xa / xb live in shared memory
+    double e = 0.0;
+    const int n = a.n;
+    if (POT == CHX_MC_HO) {
+        for (int i = threadIdx.x; i < n; i += MC_SMALL_THREADS) {
+            const int r = a.n0 == 1 ? 0 : i;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float dx = __fsub_rn(xb[3 * i + c], a.x0[3 * r + c]);
+                e += (double)__fmul_rn(dx, dx);
+            }
+        }
+    } else if (POT == CHX_MC_LJ_NLIST) {
+        const int lane = threadIdx.x & 31;
+        for (int i = threadIdx.x >> 5; i < n; i += MC_SMALL_THREADS >> 5) {
+            int cnt = a.n_neighbors[i];
+            cnt = cnt < a.M ? cnt : a.M;
+            e += (double)lj_nlist_row_energy<PERIODIC>(Pos3{xb}, i, lane, box, fc, a.neighbor_list + (size_t)i * a.M,
+                                                       cnt, a.sigma * a.sigma, a.epsilon);
+        }
+    } else if (POT == CHX_MC_LJ_SUBSET_DELTA) {
+        for (int s = 0; s < a.n_subset; ++s) {
+            const int m = (int)a.subset_ids[s];
+            const float ox = xa[3 * m], oy = xa[3 * m + 1], oz = xa[3 * m + 2];
+            const float nx = xb[3 * m], ny = xb[3 * m + 1], nz = xb[3 * m + 2];
+            for (int j = threadIdx.x; j < n; j += MC_SMALL_THREADS) {
+                if (j == m) continue;
+                const double w = a.subset_mask[j] != 0.0f ? 0.5 : 1.0;
+                float rx, ry, rz, d, ee;
+                if (m < j) ref_displacement<PERIODIC>(nx, ny, nz, xb[3 * j], xb[3 * j + 1], xb[3 * j + 2], box, rx, ry, rz, d);
+                else ref_displacement<PERIODIC>(xb[3 * j], xb[3 * j + 1], xb[3 * j + 2], nx, ny, nz, box, rx, ry, rz, d);
+                if (d < a.cutoff) { lj_pair_e(d, a.sigma, a.epsilon, ee); e += w * (double)ee; }
+                if (m < j) ref_displacement<PERIODIC>(ox, oy, oz, xa[3 * j], xa[3 * j + 1], xa[3 * j + 2], box, rx, ry, rz, d);
+                else ref_displacement<PERIODIC>(xa[3 * j], xa[3 * j + 1], xa[3 * j + 2], ox, oy, oz, box, rx, ry, rz, d);
+                if (d < a.cutoff) { lj_pair_e(d, a.sigma, a.epsilon, ee); e -= w * (double)ee; }
+            }
+        }
+    }
+    return mc_cta_sum(e, sh);
+}
+
+template <int POT, bool PERIODIC, bool CHECK>
+__global__ void __launch_bounds__(MC_SMALL_THREADS)
+k_mcl_small(chx_mc_displace_args a, McThermo th, FastCut fc, float* __restrict__ x0, float* __restrict__ x1,
+            chx_mc_state* __restrict__ st, int n_moves) {
+    extern __shared__ float sm_pos[];
+    __shared__ double sh[MC_SMALL_THREADS >> 5];
+    __shared__ chx_mc_state s_st;
+    __shared__ int s_accept;
+    const int n = a.n;
+    float* xa = sm_pos;
+    float* xb = sm_pos + 3 * n;
+    const Box box = make_box(a.lx, a.ly, a.lz);
+    if (threadIdx.x == 0) s_st = *st;
+    __syncthreads();
+    float* xg = s_st.sel ? x1 : x0;
+    for (int t = threadIdx.x; t < 3 * n; t += MC_SMALL_THREADS) { xa[t] = xg[t]; xb[t] = xg[t]; }
+    __syncthreads();
+    if (!s_st.have_u) {
+        double u0 = 0.0;
+        if (POT != CHX_MC_LJ_SUBSET_DELTA && POT != CHX_MC_IDEAL) u0 = mc_small_energy<POT, PERIODIC>(a, box, fc, xa, xa, sh);
+        if (threadIdx.x == 0) { s_st.u_current = mc_reduced(th, u0); s_st.have_u = 1; }
+        __syncthreads();
+    }
+    const float half_skin = 0.5f * a.skin;
+    for (int mv = 0; mv < n_moves; ++mv) {
+        uint32_t c0, c1, s0, s1;
+        threefry_split(s_st.key[0], s_st.key[1], c0, c1, s0, s1);
+        const float sigma = s_st.sigma_disp;
+        const unsigned long long total = 3ull * (unsigned long long)n;
+        bool moved = false;
+        for (int i = threadIdx.x; i < n; i += MC_SMALL_THREADS) {
+            const float msk = a.subset_mask ? a.subset_mask[i] : 1.0f;
+            float xn[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                // a zero mask multiplies the (finite) noise to +-0, and x + (+-0) == x: no need to draw it
+                float d = 0.0f;
+                if (msk != 0.0f) {
+                    d = __fmul_rn(normal_from_bits(random_bits_elem(s0, s1, 3ull * i + c, total)), sigma);
+                    if (a.subset_mask) d = __fmul_rn(d, msk);
+                }
+                float v = __fadd_rn(xa[3 * i + c], d);
+                if (PERIODIC) v = ref_wrap(v, c == 0 ? box.lx : (c == 1 ? box.ly : box.lz));
+                xb[3 * i + c] = v;
+                xn[c] = v;
+            }
+            if (CHECK) {
+                float rx, ry, rz, d;
+                ref_displacement<PERIODIC>(xn[0], xn[1], xn[2], a.ref_positions[3 * i], a.ref_positions[3 * i + 1],
+                                           a.ref_positions[3 * i + 2], box, rx, ry, rz, d);
+                moved = moved || d >= half_skin;
+            }
+        }
+        const int any_moved = __syncthreads_or(CHECK && moved);     // also publishes xb
+        if (any_moved) {
+            if (threadIdx.x == 0) s_st.halt = 1;
+            break;
+        }
+        double acc = 0.0;
+        if (POT != CHX_MC_IDEAL) acc = mc_small_energy<POT, PERIODIC>(a, box, fc, xa, xb, sh);
+        if (threadIdx.x == 0) {
+            const float u_cur = s_st.u_current;
+            float u_new;
+            if (POT == CHX_MC_LJ_SUBSET_DELTA) u_new = __fadd_rn(u_cur, (float)(acc * th.beta));
+            else u_new = mc_reduced(th, acc);
+            const float lr = __fadd_rn(-u_new, u_cur);
+            bool accept = false;
+            if (u_new != u_new) {
+                s_st.nan_seen += 1;
+            } else {
+                uint32_t d0, d1, t0, t1;
+                threefry_split(c0, c1, d0, d1, t0, t1);
+                c0 = d0; c1 = d1;
+                const float uni = uniform_from_bits(random_bits_elem(t0, t1, 0ull, 1ull), 0.0f, 1.0f);
+                accept = (-lr <= 0.0f) || (uni < expf(lr));
+            }
+            s_st.key[0] = c0; s_st.key[1] = c1;
+            if (accept) { s_st.u_current = u_new; s_st.n_accepted += 1; }
+            s_st.n_proposed += 1;
+            s_st.moves_done += 1;
+            s_accept = accept ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_accept) { float* t = xa; xa = xb; xb = t; }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 3 * n; t += MC_SMALL_THREADS) xg[t] = xa[t];
+    if (threadIdx.x == 0) *st = s_st;
+}
+
+static int mc_launch_small(chx_ctx* ctx, const McArgs& m, int n_moves) {
+    const chx_mc_displace_args& a = m.a;
+    const McThermo th = mc_thermo(a);
+    const FastCut fc = make_fast_cut(a.cutoff > 0.f ? a.cutoff : 1.f, a.lx, a.ly, a.lz, a.periodic != 0);
+    const size_t smem = (size_t)6 * a.n * sizeof(float);
+    const bool chk = a.ref_positions != nullptr;
+#define SMALL_LAUNCH(POT, P, C)                                                                              \
+    do {                                                                                                     \
+        CHX_CUDA(cudaFuncSetAttribute(k_mcl_small<POT, P, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_mcl_small<POT, P, C><<<1, MC_SMALL_THREADS, smem, ctx->stream>>>(a, th, fc, m.x0, m.x1, m.st, n_moves); \
+    } while (0)
+#define SMALL_POT(POT)                                                                                       \
+    do {                                                                                                     \
+        if (a.periodic) { if (chk) SMALL_LAUNCH(POT, true, true); else SMALL_LAUNCH(POT, true, false); }      \
+        else { if (chk) SMALL_LAUNCH(POT, false, true); else SMALL_LAUNCH(POT, false, false); }               \
+    } while (0)
+    switch (a.potential) {
+    case CHX_MC_HO: SMALL_POT(CHX_MC_HO); break;
+    case CHX_MC_IDEAL: SMALL_POT(CHX_MC_IDEAL); break;
+    case CHX_MC_LJ_NLIST: SMALL_POT(CHX_MC_LJ_NLIST); break;
+    case CHX_MC_LJ_SUBSET_DELTA: SMALL_POT(CHX_MC_LJ_SUBSET_DELTA); break;
+    default: chx_set_error("potential kind %d has no single-CTA loop", a.potential); return CHX_BAD_ARG;
+    }
+#undef SMALL_POT
+#undef SMALL_LAUNCH
+    CHX_LAUNCHED(ctx);
+    return CHX_OK;
+}
+
 // chx_context_destroy: the graphs captured for this context go with it (a later context may reuse
 // the address)
 void chx_mc_forget_context(chx_ctx* ctx) {
@@ -421,6 +609,21 @@ int chx_mc_displace_run(chx_ctx* ctx, const chx_mc_displace_args* args, float* x
     state_host->halt = 0;
     state_host->moves_done = 0;
     CHX_CUDA(cudaMemcpyAsync(state_dev, state_host, sizeof(chx_mc_state), cudaMemcpyHostToDevice, st));
+    {
+        // small systems: the whole loop in one single-CTA launch (CHX_MC_NO_SMALL=1 keeps the launches per move)
+        static int use_small = -1;
+        if (use_small < 0) { const char* e = getenv("CHX_MC_NO_SMALL"); use_small = (e && e[0] == '1') ? 0 : 1; }
+        const bool small_pot = a.potential == CHX_MC_HO || a.potential == CHX_MC_IDEAL ||
+                               a.potential == CHX_MC_LJ_SUBSET_DELTA ||
+                               (a.potential == CHX_MC_LJ_NLIST && (long long)a.n * a.M <= 16384);   // one CTA: tiny lists only
+        if (use_small && small_pot && a.n <= MC_SMALL_MAX_N && n_moves > 0) {
+            int rc = mc_launch_small(ctx, m, n_moves);
+            if (rc != CHX_OK) return rc;
+            CHX_CUDA(cudaMemcpyAsync(state_host, state_dev, sizeof(chx_mc_state), cudaMemcpyDeviceToHost, st));
+            CHX_CUDA(cudaStreamSynchronize(st));
+            return CHX_OK;
+        }
+    }
     CHX_CUDA(cudaMemsetAsync(m.acc, 0, sizeof(double), st));
     k_mcl_pack<<<chx_div_up(a.n, 256), 256, 0, st>>>(a.n, x0, x1, m.q0, m.q1, state_dev);
     CHX_LAUNCHED(ctx);
