@@ -206,7 +206,10 @@ typedef struct {
     int32_t reserved[5];
 } chx_mc_state;
 /* x0/x1: device (n,3) buffers; state_dev: device scratch of sizeof(chx_mc_state); state_host is
- * uploaded first and holds the final state on return.  Synchronises once, at the end. */
+ * uploaded first and holds the final state on return.  Synchronises once, at the end.
+ * Large systems: three launches per move (propose, energy, decide) replayed as a cached CUDA graph of
+ * 10 moves.  n <= 2048 with a cheap energy (harmonic oscillator, ideal gas, subset delta, tiny lists):
+ * the whole call is ONE single-CTA launch with both position buffers in shared memory. */
 int chx_mc_displace_run(chx_ctx* ctx, const chx_mc_displace_args* args, float* x0, float* x1,
                         chx_mc_state* state_dev, chx_mc_state* state_host, int n_moves);
 
