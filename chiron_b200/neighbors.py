@@ -183,6 +183,19 @@ class NeighborListNsqrd(PairsBase):
         self.is_built = False
         self.n_builds = 0
 
+    def __deepcopy__(self, memo):
+        """`MCMCSampler.run` deep-copies its inputs (mcmc.py:1134-1136) so that the caller's objects are
+        never touched.  The list arrays are immutable here -- `build` replaces them wholesale and the
+        device loops write into their own copies -- so a deep copy shares the (N, M) tensors instead of
+        moving 2 x N x M words per call; everything else is copied."""
+        import copy as _copy
+        new = _copy.copy(self)
+        shared = ("_arrays", "ref_positions", "box_vectors", "particle_ids")
+        for k, v in self.__dict__.items():
+            if k not in shared:
+                new.__dict__[k] = _copy.deepcopy(v, memo)
+        return new
+
     @property
     def cutoff(self) -> unit.Quantity:
         return self._cutoff
