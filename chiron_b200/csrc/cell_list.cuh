@@ -17,7 +17,8 @@ static __device__ __forceinline__ void finish_row(int i, int count, uint32_t fir
     if (fill == (uint32_t)i) fill += 1u;
     const int stored = count < M ? count : M;
     for (int k = stored + lane; k < M; k += 32) list[(size_t)i * M + k] = fill;
-    for (int k = lane; k < M; k += 32) mask[(size_t)i * M + k] = (k < count) ? 1 : 0;
+    if (mask != nullptr)   // the barostat loop's superset build keeps ids and counts only
+        for (int k = lane; k < M; k += 32) mask[(size_t)i * M + k] = (k < count) ? 1 : 0;
     if (lane == 0) nn[i] = count;
 }
 

@@ -1030,9 +1030,10 @@ int chx_mc_barostat_run(chx_ctx* ctx, const chx_mc_barostat_args* args, float* x
             CHX_LAUNCHED(ctx);
             k_cell_fill<<<chx_div_up(a.n, 256), 256, 0, st>>>(xc, m.cell_of, a.n, Ps_dev, m.start, m.count, m.order, m.xs4);
             CHX_LAUNCHED(ctx);
-            // ids and counts go to the superset arrays, the pad mask to the list set that is not current
+            // ids and counts go to the superset arrays; no pad mask is written (both list sets stay valid
+            // rows of an earlier build, which k_mcb_filter's incremental row update relies on)
             rc = cell_bm_launch(ctx, xc, m.xs4, a.n, Ps_dev, a.M, wshift, warps, smem, m.cell_of, m.start,
-                                a.superset_list, a.neighbor_mask[1 - cur], a.superset_nn);
+                                a.superset_list, nullptr, a.superset_nn);
             if (rc != CHX_OK) return rc;
             k_count_stats<<<chx_div_up(a.n, 256), 256, 0, st>>>(a.superset_nn, a.n, a.M, m.stats);
             CHX_LAUNCHED(ctx);

@@ -166,7 +166,10 @@ k_nlist_calculate(const float* __restrict__ x, int n, Box box, float cutoff, int
     int cnt = 0;
     for (int k = lane; k < M; k += 32) {
         const size_t o = (size_t)i * M + k;
-        const uint32_t j = list[o];
+        uint32_t j = list[o];
+        // padding ids can point one past the end (a row without neighbours pads with 0, bumped to 1 when
+        // i == 0: neighbors.py:606-609 on a single particle); JAX clamps the gather index
+        j = j < (uint32_t)n ? j : (uint32_t)(n - 1);
         float rx, ry, rz, d;
         ref_displacement<PERIODIC>(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2], box, rx, ry,
                                    rz, d);

@@ -135,8 +135,15 @@ class MCMove(MCMCMove):
             x = _lib.as_device_f32(sampler_state.positions)
             dev = x.device
             ctx = _lib.get_context(dev)
-            bufs = [x.clone(), torch.empty_like(x)]
-            st_dev = torch.zeros(16, dtype=torch.int32, device=dev)
+            # persistent work buffers: the device loop caches its captured graph by argument addresses,
+            # so the same buffers must come back on every update() (results are copied out below)
+            cache = getattr(self, "_dev_bufs", None)
+            if cache is None or cache[0].shape != x.shape or cache[0].device != dev:
+                cache = (torch.empty_like(x), torch.empty_like(x), torch.zeros(16, dtype=torch.int32, device=dev))
+                self._dev_bufs = cache
+            bufs, st_dev = [cache[0], cache[1]], cache[2]
+            bufs[0].copy_(x)
+            st_dev.zero_()
             st = _lib.McState()
             key = sampler_state._current_PRNG_key
             st.key[0], st.key[1] = int(key[0]), int(key[1])
@@ -161,7 +168,7 @@ class MCMove(MCMCMove):
             if self.n_accepted != accepted_before:
                 # accept returns a new state object, reject the same one with the advanced key (mcmc.py:441-463)
                 out = _shallow_state_copy(sampler_state)
-                out.positions = bufs[int(st.sel)]
+                out.positions = bufs[int(st.sel)].clone()
                 sampler_state = out
             sampler_state._current_PRNG_key = new_key
             if halted:
@@ -420,20 +427,25 @@ class MonteCarloDisplacementMove(MCMove):
         delta = self._delta_reduced_potential(x, xp, current_sampler_state, current_thermodynamic_state,
                                               current_nbr_list)
         if delta is not None:
+            # the acceptance uses -delta itself (as the device loop does), not the rounded difference of
+            # two totals
             proposed_reduced_potential = current_reduced_potential + delta
+            log_proposal_ratio = -delta
         else:
             proposed_reduced_potential = current_thermodynamic_state.get_reduced_potential(
                 proposed_sampler_state, proposed_nbr_list)
-        log_proposal_ratio = -proposed_reduced_potential + current_reduced_potential
+            log_proposal_ratio = -proposed_reduced_potential + current_reduced_potential
         return (proposed_sampler_state, current_thermodynamic_state, proposed_reduced_potential,
                 log_proposal_ratio, proposed_nbr_list)
 
     def _delta_reduced_potential(self, x, xp, sampler_state, thermodynamic_state, nbr_list):
         """beta * (U(new) - U(old)) from the subset delta-energy kernel, or None if not applicable."""
+        from .neighbors import NeighborListNsqrd
         from .potential import LJPotential
         pot = thermodynamic_state.potential
+        # only for lists whose energy is truncated at pot.cutoff (a PairListNsqrd(cutoff=None) is not)
         if not (self.use_delta_energy and self.atom_subset is not None and isinstance(pot, LJPotential)
-                and nbr_list is not None and nbr_list.space.periodic
+                and isinstance(nbr_list, NeighborListNsqrd) and nbr_list.space.periodic
                 and thermodynamic_state.temperature is not None):
             return None
         n, dev = x.shape[0], x.device
