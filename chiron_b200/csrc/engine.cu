@@ -60,6 +60,8 @@ struct MdGeom {
     int n, np, nblk, ncell;       // particles, padded, blocks, cells
 };
 
+struct MdCtl;
+
 struct chx_ljmd {
     chx_ctx* ctx;
     chx_ljmd_params p;
@@ -95,6 +97,20 @@ struct chx_ljmd {
     double timed_ms;                 // device time of the replays in which no replica halted
     long long timed_steps;
     bool no_graph;                   // CHX_MD_NOGRAPH=1: launch every kernel directly
+    // persistent step kernel (engine v5)
+    bool persist;                    // CHX_MD_PERSIST=0 falls back to one launch per step
+    int coop_grid, Wmax;             // CTAs of k_md_steps (one per SM), warps = plan pieces at most
+    int deal_tpl;                    // tiles per lane of k_md_deal2 (2, 4, 8; larger: k_md_deal)
+    bool deal_tpl_auto_grow;
+    int q_full, q_P, q_units;        // unit queue of a step: q_full whole blocks, then the rest cut into q_P pieces
+    float4* pbuf;                    // [(R * nblk - q_full) * q_P][32] partial forces of cut blocks
+    int* part_cnt;                   // [R * nblk] arrival counters (zero between steps)
+    MdCtl* ctl;
+    cudaEvent_t pev0, pev1;          // bracket every k_md_steps launch (chx_ljmd_step_timing)
+    // look-ahead of the per-launch step loop: two chunks in flight, each with its own events and a pinned copy
+    // of the control blocks taken right behind it
+    cudaEvent_t pipe_e0[2], pipe_e1[2], pipe_ed[2];
+    MdRep* pipe_rep[2];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -218,64 +234,72 @@ __global__ void k_md_cellcount(const float4* __restrict__ xs, MdGeom g, const in
 }
 
 // one CTA per replica: exclusive scan over the cells in Hilbert order.  Warp w owns a chunk of 1024
-// consecutive cells (32 coalesced rows of 32); chunk totals are scanned across the block.
+// consecutive cells (32 coalesced rows of 32) whose counts it keeps in registers: one load per cell, no
+// load behind a store (27 -> ~6 us at 32,768 cells); the per-cell ranges are written by k_md_ranges.
 __global__ void __launch_bounds__(1024)
-k_md_scan(int* __restrict__ count, int* __restrict__ start, int2* __restrict__ range,
-          const int* __restrict__ h2lin, int ncell, const MdRep* __restrict__ rep) {
+k_md_scan(const int* __restrict__ count, int* __restrict__ start, int ncell, const MdRep* __restrict__ rep) {
     __shared__ int wsum[32];
     __shared__ int carry;
     const int r = blockIdx.x;
     if (!rep[r].flag) return;
     count += (size_t)r * (ncell + 1);
     start += (size_t)r * (ncell + 1);
-    range += (size_t)r * ncell;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (t == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < ncell; base += 32768) {
         const int c0 = base + w * 1024;
+        int v[32];
         int mine = 0;
-#pragma unroll 8
+#pragma unroll
         for (int k = 0; k < 32; ++k) {
             const int c = c0 + k * 32 + lane;
-            mine += c < ncell ? count[c] : 0;
+            v[k] = c < ncell ? count[c] : 0;
+            mine += v[k];
         }
         mine = warp_sum(mine);
         if (lane == 0) wsum[w] = mine;
         __syncthreads();
         if (w == 0) {
-            const int v = wsum[lane];
-            int s = v;
+            const int u0 = wsum[lane];
+            int s = u0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int u = __shfl_up_sync(FULL, s, o);
                 if (lane >= o) s += u;
             }
-            wsum[lane] = s - v + carry;            // exclusive offset of chunk `lane`
+            wsum[lane] = s - u0 + carry;            // exclusive offset of chunk `lane`
             if (lane == 31) carry += s;
         }
         __syncthreads();
         int running = wsum[w];
+#pragma unroll
         for (int k = 0; k < 32; ++k) {
             const int c = c0 + k * 32 + lane;
-            const int v = c < ncell ? count[c] : 0;
-            int inc = v;
+            int inc = v[k];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int u = __shfl_up_sync(FULL, inc, o);
                 if (lane >= o) inc += u;
             }
-            const int excl = running + inc - v;
-            if (c < ncell) {
-                start[c] = excl;
-                count[c] = 0;
-                range[h2lin[c]] = make_int2(excl, excl + v);
-            }
+            if (c < ncell) start[c] = running + inc - v[k];
             running += __shfl_sync(FULL, inc, 31);
         }
         __syncthreads();
     }
     if (t == 0) start[ncell] = carry;
+}
+
+// per (x,y,z)-linear cell: [begin, end) in sorted order; clears the counters for k_md_place's cursors
+__global__ void k_md_ranges(int* __restrict__ count, const int* __restrict__ start, int2* __restrict__ range,
+                            const int* __restrict__ h2lin, int ncell, const MdRep* __restrict__ rep) {
+    const int r = blockIdx.y;
+    if (!rep[r].flag) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const size_t cb = (size_t)r * (ncell + 1);
+    count[cb + c] = 0;
+    range[(size_t)r * ncell + h2lin[c]] = make_int2(start[cb + c], start[cb + c + 1]);
 }
 
 __global__ void k_md_place(const int* __restrict__ cell_of, MdGeom g, const int* __restrict__ start,
@@ -479,7 +503,9 @@ k_md_cand(const float4* __restrict__ xs_all, const int2* __restrict__ range_all,
             me.y -= g.box.ly * rintf((me.y - bcy) * g.inv_ly);
             me.z -= g.box.lz * rintf((me.z - bcz) * g.inv_lz);
         }
-        stage[lane] = me;
+        // SoA: x[32] | y[32] | z[32], so that an 8-byte read yields the same coordinate of two particles
+        float* st_ = reinterpret_cast<float*>(stage);
+        st_[lane] = me.x; st_[32 + lane] = me.y; st_[64 + lane] = me.z;
     }
     const unsigned validmask = __ballot_sync(FULL, valid);
     __syncwarp();
@@ -495,17 +521,31 @@ k_md_cand(const float4* __restrict__ xs_all, const int2* __restrict__ range_all,
             xj.z -= g.box.lz * rintf((xj.z - bcz) * g.inv_lz);
         }
         uint32_t col = 0u;   // bit k: particle k of the block is within Rm of this candidate
+        if (gen) {
 #pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const float4 xk = stage[k];
-            float dx = xk.x - xj.x, dy = xk.y - xj.y, dz = xk.z - xj.z;
-            if (gen) {
+            for (int k = 0; k < 32; ++k) {
+                const float* st_ = reinterpret_cast<const float*>(stage);
+                float dx = st_[k] - xj.x, dy = st_[32 + k] - xj.y, dz = st_[64 + k] - xj.z;
                 dx -= g.box.lx * rintf(dx * g.inv_lx);
                 dy -= g.box.ly * rintf(dy * g.inv_ly);
                 dz -= g.box.lz * rintf(dz * g.inv_lz);
+                const float r2 = dx * dx + dy * dy + dz * dz;
+                col |= (r2 < Rm2 ? 1u : 0u) << k;
             }
-            const float r2 = dx * dx + dy * dy + dz * dz;
-            col |= (r2 < Rm2 ? 1u : 0u) << k;
+        } else {
+            // two particles of the block per iteration on packed fp32 pairs (FFMA2 / FMUL2)
+            const float2 jx = make_float2(xj.x, xj.x), jy = make_float2(xj.y, xj.y), jz = make_float2(xj.z, xj.z);
+            const float2 m1 = make_float2(-1.f, -1.f);
+#pragma unroll 8
+            const float2* sx2 = reinterpret_cast<const float2*>(stage);
+            for (int k = 0; k < 32; k += 2) {
+                const float2 dx = __ffma2_rn(jx, m1, sx2[k >> 1]);
+                const float2 dy = __ffma2_rn(jy, m1, sx2[16 + (k >> 1)]);
+                const float2 dz = __ffma2_rn(jz, m1, sx2[32 + (k >> 1)]);
+                const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                col |= (r2.x < Rm2 ? 1u : 0u) << k;
+                col |= (r2.y < Rm2 ? 2u : 0u) << k;
+            }
         }
         col &= validmask;
         const unsigned self = (unsigned)(p - b * 32);
@@ -807,6 +847,117 @@ k_md_emit(const uint32_t* __restrict__ cand_idx_all, const uint32_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// table build, part 2, latency-optimised (k_md_deal2): the same greedy deal as k_md_deal -- identical
+// tables -- with one HALF-WARP per block and one lane per tile (TPL tiles per lane: tile t lives in lane
+// t % 16, register set t / 16).  The per-particle counters of a tile are BIT-SLICED: plane k holds bit k
+// of the 32 counters, so adding a candidate's column word is a ripple carry over NPL words and "which
+// particles sit at the tile's max" is NPL bitwise compares -- ~15 instructions instead of the ~90 of
+// byte counters.  The winning tile is found with two REDUX.MIN (one per half-warp, full mask).
+// Per candidate the dependent chain is key -> REDUX -> update: ~150 cycles instead of ~1500, which is
+// what matters on small grids (8 x 8,192 particles: 360 -> ~45 us), and half the warp instructions of
+// the 8-lane variant on large ones.
+// ---------------------------------------------------------------------------------------------
+#define DEAL2_BPC 8                   // blocks per CTA of 128 threads (two per warp)
+
+template <int TPL, int NPL>
+__global__ void __launch_bounds__(128)
+k_md_deal2(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ cand_n_all, MdGeom g, int ccap,
+           int tcap, int lw, uint16_t* __restrict__ memb_all, uint16_t* __restrict__ tmeta_all,
+           int* __restrict__ ntiles_all, MdRep* __restrict__ rep) {
+    const int r = blockIdx.y;
+    if (!rep[r].flag) return;
+    const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+    const int b = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 2 + half;
+    const bool exists = b < g.nblk;                // control flow below is warp-uniform
+    const size_t rb = (size_t)r * g.nblk + (exists ? b : 0);
+    const uint32_t* in_col = cand_col_all + rb * ccap;
+    uint16_t* memb = memb_all + rb * (size_t)tcap * 32;
+    const int K = exists ? cand_n_all[rb] : 0;
+    const uint32_t cap = 6u * (uint32_t)lw;
+    const int tmax = tcap < 16 * TPL ? tcap : 16 * TPL;
+    int T = (K + TILE_SLOTS - 1) / TILE_SLOTS;
+    bool ovf = T > tmax;
+    if (ovf) T = tmax;
+    const int ovf_bit = tcap > 16 * TPL ? 8 : 2;   // 8: this instantiation ran out of lanes, not the table of tiles
+    uint32_t pl[TPL][NPL], at[TPL], cs[TPL];       // counter bit planes, at-max mask, max << 8 | fill
+#pragma unroll
+    for (int j = 0; j < TPL; ++j) {
+        at[j] = 0xffffffffu; cs[j] = 0u;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) pl[j][k] = 0u;
+    }
+    const int Kw = __reduce_max_sync(FULL, K);
+    uint32_t c_next = K > 0 ? in_col[0] : 0u;
+    for (int q = 0; q < Kw; ++q) {
+        const bool active = q < K && !ovf;
+        const uint32_t c = c_next;
+        if (q + 1 < K) c_next = in_col[q + 1];
+        uint32_t best;
+        bool again;
+        do {
+            uint32_t key = 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < TPL; ++j) {
+                const int t = j * 16 + hl;
+                const uint32_t nm = (cs[j] >> 8) + ((c & at[j]) != 0u ? 1u : 0u);
+                const uint32_t kj = (t < T && (cs[j] & 0xffu) < TILE_SLOTS && nm <= cap)
+                                        ? (nm << 18 | (cs[j] & 0xffu) << 12 | (uint32_t)t) : 0xffffffffu;
+                key = min(key, kj);
+            }
+            const uint32_t k0 = __reduce_min_sync(FULL, half ? 0xffffffffu : key);
+            const uint32_t k1 = __reduce_min_sync(FULL, half ? key : 0xffffffffu);
+            best = half ? k1 : k0;
+            again = false;
+            if (active && best == 0xffffffffu) {
+                if (T < tmax) { ++T; again = true; }   // open one more tile
+                else ovf = true;
+            }
+        } while (__any_sync(FULL, again));
+        {
+            const bool place = active && !ovf;
+            const int tw = (int)(best & 0xfffu), slot = (int)((best >> 12) & 0x3fu);
+            const uint32_t newmax = best >> 18;
+            // every lane runs the update of all its tiles with the candidate's column masked to zero unless
+            // the tile is the winner: straight-line code, all array indices compile-time constants
+#pragma unroll
+            for (int j = 0; j < TPL; ++j) {
+                const bool hit = place && tw == j * 16 + hl;
+                uint32_t carry = hit ? c : 0u, eq = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    const uint32_t p = pl[j][k];
+                    const uint32_t np_ = p ^ carry;
+                    carry &= p;
+                    pl[j][k] = np_;
+                    eq &= ((newmax >> k) & 1u) ? np_ : ~np_;
+                }
+                at[j] = hit ? eq : at[j];
+                cs[j] = hit ? (newmax << 8 | (uint32_t)(slot + 1)) : cs[j];
+            }
+            if (place && (tw & 15) == hl) memb[tw * 32 + slot] = (uint16_t)q;
+        }
+    }
+    if (!exists) return;
+    uint16_t* tmeta = tmeta_all + rb * (size_t)tcap;
+    if (!ovf) {
+#pragma unroll
+        for (int j = 0; j < TPL; ++j)
+            if (j * 16 + hl < T) tmeta[j * 16 + hl] = (uint16_t)cs[j];     // max << 8 | fill
+    }
+    if (hl == 0) {
+        ntiles_all[rb] = ovf ? 0 : T;
+        if (ovf) atomicOr(&rep[r].overflow, ovf_bit);
+    }
+}
+
+// control block of the persistent step kernel (k_md_steps)
+struct MdCtl {
+    unsigned bar;        // grid barrier counter (zeroed before every launch)
+    int qhead[4];        // work-queue heads: step s draws its units from qhead[s & 3]
+    int error;           // 1 = a grid barrier timed out (never expected; keeps a bug from hanging the GPU)
+};
+
+// ---------------------------------------------------------------------------------------------
 // force / energy over the tiles
 // ---------------------------------------------------------------------------------------------
 struct LjConst {
@@ -848,12 +999,22 @@ __device__ __forceinline__ int tile_slot(const uint32_t* __restrict__ tp, uint32
     return (int)((wv >> (5 * (e - 6 * wi))) & 31u);
 }
 
+// x, y, z of a float4 position as an 8-byte and a 4-byte load.  A 16-byte gather would leave its .w (the
+// particle id, unused in the pair loop) dead, and ptxas recycles a dead destination register at once: the
+// next writer of that register then waits for the gather in flight (write-after-write), which exposed the
+// full L2 latency once per tile (10 % of all stall samples, profiles/r02_step_kernel_ncu.md).
+__device__ __forceinline__ float3 md_gather3(const float4* xs, uint32_t idx) {
+    const float2 xy = *reinterpret_cast<const float2*>(xs + idx);
+    const float z = reinterpret_cast<const float*>(xs + idx)[2];
+    return make_float3(xy.x, xy.y, z);
+}
+
 // xs: positions of ALL replicas (the tiles hold replica-absolute indices).  LW2: two list words per
 // tile (at most 12 partners per lane and tile), the common case, with the list kept in registers.
 // The loop visits tiles tp, tp + tadv, ... (nt of them): tadv = SPLIT * tstride when SPLIT warps share a
 // block, each taking every SPLIT-th tile.
 template <bool ENERGY, bool GEN, bool LW2, int SPLIT>
-__device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, const uint32_t* __restrict__ tp,
+__device__ __forceinline__ void md_tile_loop(const float4* xs, const uint32_t* __restrict__ tp,
                                              int nt, int tstride_arg, const float4 xi0, const float4 xi,
                                              const float4 bc, const MdGeom& g, const LjConst& lj, int lane,
                                              float& fx, float& fy, float& fz, float& e_acc, unsigned& npair) {
@@ -867,10 +1028,12 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
     const float FAR = 1.0e18f;
     const bool sentinel = lane == 31;
     const uint32_t* pf = tp + lane;            // this lane's word of the tile being prefetched
-    uint32_t code_n = pf[0], la_n = pf[32], lb_n = pf[64];
-    float4 xj_n = xs[code_n & 0xffffffu];
+    // pipeline state at the top of iteration t: (code, la, lb, xj) = tile t, (code_n, la_n, lb_n) = the words
+    // of tile t + 1 -- all of them loaded at least one tile ago
+    uint32_t code = pf[0], la = pf[32], lb = pf[64];
+    float3 xj = md_gather3(xs, code & 0xffffffu);
     pf += tadv;
-    uint32_t code_nn = pf[0], la_nn = pf[32], lb_nn = pf[64];
+    uint32_t code_n = pf[0], la_n = pf[32], lb_n = pf[64];
     pf += tadv;
 #if CHX_TILE_PREFETCH
     const int nlines = tstride >> 5;            // 128-byte lines per tile
@@ -887,11 +1050,13 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
     const float czl = -bc.z * g.inv_lz;
     const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
     for (int t = 0; t < nt; ++t, tp += tadv) {
-        const uint32_t code = code_n, la = la_n, lb = lb_n;
-        float4 xj = xj_n;
-        code_n = code_nn; la_n = la_nn; lb_n = lb_nn;
-        xj_n = xs[code_n & 0xffffffu];
-        code_nn = pf[0]; la_nn = pf[32]; lb_nn = pf[64];
+        // issue the loads of the look-ahead into FRESH registers: the positions of tile t + 1 and the words
+        // of tile t + 2.  They are consumed by the rotation at the bottom of the iteration, one tile of
+        // arithmetic later.  (With the rotation at the top ptxas copied them into the loop-carried
+        // registers right behind the loads and parked the dead .w of the float4 gather under a live
+        // value: both waited for the load -- 12 % of all stall samples, profiles/r02_step_kernel_ncu.md.)
+        float3 xg = md_gather3(xs, code_n & 0xffffffu);
+        uint32_t code_g = pf[0], la_g = pf[32], lb_g = pf[64];
         pf += tadv;
 #if CHX_TILE_PREFETCH
         // the tables are streamed from HBM once per step: pull the lines of the tile after next into
@@ -1036,9 +1201,98 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
                 }
             }
         }
+        // Rotate the pipeline.  The words just loaded (code_g, la_g, lb_g) move into registers that are dead
+        // during the trips, and ptxas hoists such a copy to right behind its load, where it waits for the
+        // full L2 latency once per tile (9 % of all stall samples, profiles/r02_step_kernel_ncu.md).  So the
+        // copy is an add of a zero that only exists once the trip loop has finished: |accumulator|, clamped
+        // to 1 (also for inf / NaN), times 0.0f is +0.0f = 0x0 and cannot be evaluated, or folded, any earlier.
+        float zf;
+        asm("{ .reg .f32 t; abs.f32 t, %1; min.f32 t, t, 0f3F800000; mul.f32 %0, t, 0f00000000; }"
+            : "=f"(zf) : "f"(GEN ? fx : fx2.x));
+        const uint32_t z = __float_as_uint(zf);
+        code = code_n; la = la_n; lb = lb_n;
+        xj = xg;
+        code_n = code_g + z; la_n = la_g + z; lb_n = lb_g + z;
     }
     fx += fx2.x + fx2.y; fy += fy2.x + fy2.y; fz += fz2.x + fz2.y;
     if (ENERGY) e_acc += e2.x + e2.y;
+}
+
+struct MdStepConst {
+    float h, a, b;               // dt/2, exp(-gamma dt), sqrt(1 - exp(-2 gamma dt))
+    float half_skin_user;        // reference rebuild condition d >= skin/2 (exact predicate)
+    float half_skin_int2;        // (internal skin / 2)^2
+};
+
+// BAOAB update of one block's 32 particles, x_step -> x_{step+1} (written to xn_all, the OTHER position
+// buffer), with the forces (fx, fy, fz) of x_step in registers: the trailing B of step - 1, B-A-O-A of
+// step (integrators.py:174-195), wrap, the reference's rebuild condition and the engine's own.  One
+// thread per replica also advances the key chain: (key(s+2), subkey(s+1)) = split(key(s+1)).
+// Returns true in every lane when this block is the first to invalidate the tables in this step.
+__device__ __forceinline__ bool md_block_update(int r, int b, int lane, size_t o, int step, const float4 xi0,
+                                                float fx, float fy, float fz, bool took_ref, float4* xn_all,
+                                                float4* vs_all, float4* refu_all, const float4* refi_all,
+                                                const MdGeom& g, const MdStepConst& sc, MdRep* rep) {
+    // the noise key of this step was prepared by the previous step; one thread prepares the next --
+    // nobody in this step reads the slots it writes
+    const uint32_t sk0 = *((volatile uint32_t*)&rep[r].sub[step & 1][0]);
+    const uint32_t sk1 = *((volatile uint32_t*)&rep[r].sub[step & 1][1]);
+    if (b == 0 && lane == 0) {
+        uint32_t c0, c1, s0, s1;
+        threefry_split(*((volatile uint32_t*)&rep[r].key[(step + 1) & 1][0]),
+                       *((volatile uint32_t*)&rep[r].key[(step + 1) & 1][1]), c0, c1, s0, s1);
+        rep[r].key[step & 1][0] = c0; rep[r].key[step & 1][1] = c1;
+        rep[r].sub[(step + 1) & 1][0] = s0; rep[r].sub[(step + 1) & 1][1] = s1;
+    }
+    const int id = __float_as_int(xi0.w);
+    bool moved_int = false, moved_user = false;
+    if (id < 0) {
+        xn_all[o] = xi0;                      // padding slot: present in both buffers
+    } else {
+        float4 v = vs_all[o];
+        const float m = v.w;
+        const float kT = rep[r].kT;
+        const float bs = __fmul_rn(sc.b, __fsqrt_rn(__fdiv_rn(kT, m)));
+        const unsigned long long total = 3ull * (unsigned long long)g.n;
+        const bool trailing = step > 0;
+        float xc[3] = {xi0.x, xi0.y, xi0.z}, vc[3] = {v.x, v.y, v.z};
+        const float fc[3] = {fx, fy, fz};
+        const float L[3] = {g.box.lx, g.box.ly, g.box.lz};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float kick = __fdiv_rn(__fmul_rn(sc.h, fc[c]), m);
+            if (trailing) vc[c] = __fadd_rn(vc[c], kick);                      // B of step - 1
+            vc[c] = __fadd_rn(vc[c], kick);                                    // B
+            xc[c] = __fadd_rn(xc[c], __fmul_rn(sc.h, vc[c]));                  // A
+            const float xi_n = normal_from_bits(random_bits_elem(sk0, sk1, 3ull * id + c, total));
+            vc[c] = __fadd_rn(__fmul_rn(sc.a, vc[c]), __fmul_rn(bs, xi_n));    // O
+            xc[c] = __fadd_rn(xc[c], __fmul_rn(sc.h, vc[c]));                  // A
+            xc[c] = ref_wrap(xc[c], L[c]);
+        }
+        xn_all[o] = make_float4(xc[0], xc[1], xc[2], xi0.w);
+        vs_all[o] = make_float4(vc[0], vc[1], vc[2], m);
+        // reference rebuild condition (exact, neighbors.py:864-868)
+        const float4 ru = took_ref ? xi0 : refu_all[o];
+        float rx, ry, rz, d;
+        ref_displacement<true>(xc[0], xc[1], xc[2], ru.x, ru.y, ru.z, g.box, rx, ry, rz, d);
+        moved_user = d >= sc.half_skin_user;
+        // engine's own list validity (fast min-image)
+        const float4 ri = refi_all[o];
+        float dx = xc[0] - ri.x, dy = xc[1] - ri.y, dz = xc[2] - ri.z;
+        dx -= g.box.lx * rintf(dx * g.inv_lx);
+        dy -= g.box.ly * rintf(dy * g.inv_ly);
+        dz -= g.box.lz * rintf(dz * g.inv_lz);
+        moved_int = dx * dx + dy * dy + dz * dz >= sc.half_skin_int2;
+    }
+    // rare events (a rebuild every few dozen steps): warp vote, then straight to the control block.
+    // halt = first step that must not run on these tables; user_step[] is read by the NEXT step
+    const unsigned ev = __reduce_or_sync(FULL, (moved_int ? 1u : 0u) | (moved_user ? 2u : 0u));
+    int old = 0;
+    if (lane == 0 && ev) {
+        if (ev & 1u) old = atomicMin(&rep[r].halt, step + 1);
+        if (ev & 2u) rep[r].user_step[step & 1] = step;
+    }
+    return (ev & 1u) != 0u && __shfl_sync(FULL, old, 0) > step + 1;
 }
 
 // The step kernel.  One launch = one Langevin step: forces of the current positions x_s over the
@@ -1051,11 +1305,6 @@ __device__ __forceinline__ void md_tile_loop(const float4* __restrict__ xs, cons
 // SPLIT warps of a CTA share one block: warp w takes tiles w, w + SPLIT, ... and the partial forces
 // are summed through shared memory in warp order (deterministic).  SPLIT = 1 is one warp per block;
 // 4 gives small systems (few blocks per SM) enough warps to hide latency.
-struct MdStepConst {
-    float h, a, b;               // dt/2, exp(-gamma dt), sqrt(1 - exp(-2 gamma dt))
-    float half_skin_user;        // reference rebuild condition d >= skin/2 (exact predicate)
-    float half_skin_int2;        // (internal skin / 2)^2
-};
 
 #define MD_FORCE_MAX_SPLIT 4
 template <bool ENERGY, int SPLIT, bool UPDATE>
@@ -1156,64 +1405,217 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
         }
     }
     if (!UPDATE || w != 0) return;
+    md_block_update(r, b, lane, o, step, xi0, fx, fy, fz, took_ref, const_cast<float4*>(odd ? xs_a : xs_b), vs_all,
+                    refu_all, refi_all, g, sc, rep);
+}
 
-    // ---- BAOAB update of the warp's own particles: x_step -> x_{step+1} (other buffer) ----
-    // the noise key of this step was prepared by the previous launch; one thread prepares the next:
-    // (key(s+2), subkey(s+1)) = split(key(s+1)) -- nobody in this launch reads the slots it writes
-    const uint32_t sk0 = rep[r].sub[step & 1][0], sk1 = rep[r].sub[step & 1][1];
-    if (b == 0 && lane == 0) {
-        uint32_t c0, c1, s0, s1;
-        threefry_split(rep[r].key[(step + 1) & 1][0], rep[r].key[(step + 1) & 1][1], c0, c1, s0, s1);
-        rep[r].key[step & 1][0] = c0; rep[r].key[step & 1][1] = c1;
-        rep[r].sub[(step + 1) & 1][0] = s0; rep[r].sub[(step + 1) & 1][1] = s1;
-    }
-    float4* xn_all = const_cast<float4*>(odd ? xs_a : xs_b);
-    const int id = __float_as_int(xi0.w);
-    bool moved_int = false, moved_user = false;
-    if (id < 0) {
-        xn_all[o] = xi0;                      // padding slot: present in both buffers
-    } else {
-        float4 v = vs_all[o];
-        const float m = v.w;
-        const float kT = rep[r].kT;
-        const float bs = __fmul_rn(sc.b, __fsqrt_rn(__fdiv_rn(kT, m)));
-        const unsigned long long total = 3ull * (unsigned long long)g.n;
-        const bool trailing = step > 0;
-        float xc[3] = {xi0.x, xi0.y, xi0.z}, vc[3] = {v.x, v.y, v.z};
-        const float fc[3] = {fx, fy, fz};
-        const float L[3] = {g.box.lx, g.box.ly, g.box.lz};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float kick = __fdiv_rn(__fmul_rn(sc.h, fc[c]), m);
-            if (trailing) vc[c] = __fadd_rn(vc[c], kick);                      // B of step - 1
-            vc[c] = __fadd_rn(vc[c], kick);                                    // B
-            xc[c] = __fadd_rn(xc[c], __fmul_rn(sc.h, vc[c]));                  // A
-            const float xi_n = normal_from_bits(random_bits_elem(sk0, sk1, 3ull * id + c, total));
-            vc[c] = __fadd_rn(__fmul_rn(sc.a, vc[c]), __fmul_rn(bs, xi_n));    // O
-            xc[c] = __fadd_rn(xc[c], __fmul_rn(sc.h, vc[c]));                  // A
-            xc[c] = ref_wrap(xc[c], L[c]);
+// ---------------------------------------------------------------------------------------------
+// The persistent step kernel (engine v5).  ONE cooperative launch runs Langevin steps s0 .. s_end - 1
+// (and, optionally, the force evaluation of x_{s_end} that closes a run) until the tables go stale:
+//   * one CTA of 32 warps per SM.  The work of a step is a queue of UNITS drawn with one atomic per unit
+//     (the next unit is fetched while the current one is processed): first `n_full` whole blocks, then the
+//     remaining blocks cut into P pieces of consecutive tiles each.  Whole blocks first and small pieces
+//     last keep every warp of the machine busy until the end of the step: 8192 blocks on 4736 resident
+//     warps are 1 + 3 x 1/4 rounds instead of 2, and 2048 blocks (8 replicas x 8192 particles) fill the
+//     machine as 4096 halves;
+//   * a whole block is finished straight from registers; the pieces of a cut block write their partial
+//     force to `pbuf` and bump the block's arrival counter, and the LAST piece to arrive sums the partials
+//     in piece order (deterministic) and does the BAOAB update;
+//   * steps are separated by a grid barrier (one atomic per CTA): no launch, no host round trip, no
+//     no-op launches after a halt; the kernel returns as soon as every replica it serves has halted
+//     (tables stale) or at s_end.
+// The per-step work (tile loop, BAOAB update, PRNG stream, rebuild bookkeeping) is the same code the
+// per-launch kernel k_md_force<UPDATE> runs; only the order in which the partial forces of a cut block are
+// added differs.
+// ---------------------------------------------------------------------------------------------
+#define MD_FINAL_NONE 0    // steps only
+#define MD_FINAL_KICK 1    // + forces of x_{s_end}, trailing B of the last step (integrators.py:195), step bookkeeping
+#define MD_FINAL_FORCE 2   // forces only (set_state), no bookkeeping
+
+struct MdStepsArgs {
+    float4 *xs_a, *xs_b, *fs, *vs, *refu;
+    const float4* refi;
+    const uint32_t* tiles;
+    const int* ntiles;
+    const uint8_t* generic;
+    const float4* bcenter;
+    float4* pbuf;        // [(NB - n_full) * P][32] partial forces of cut blocks
+    int* cnt;            // [NB] pieces of a cut block that have arrived in the current step
+    MdRep* rep;
+    MdCtl* ctl;
+    MdGeom g;
+    LjConst lj;
+    MdStepConst sc;
+    int tcap, tstride, NB, R, s0, s_end, final_mode;
+    int n_full, P, n_units;
+};
+
+__device__ __forceinline__ int ld_volatile_i(const int* p) {   // L2 load (another SM may have written it this step)
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_u(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+#define MD_STEPS_WARPS 32
+__global__ void __launch_bounds__(MD_STEPS_WARPS * 32, 1)
+k_md_steps(const __grid_constant__ MdStepsArgs A) {
+    __shared__ int s_cont;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const MdGeom& g = A.g;
+    unsigned bar_target = 0;
+    for (int s = A.s0; s <= A.s_end; ++s) {
+        const bool fin = s == A.s_end;
+        if (fin && A.final_mode == MD_FINAL_NONE) break;
+        const bool odd = A.final_mode != MD_FINAL_FORCE && (s & 1);
+        float4* xs_cur = odd ? A.xs_b : A.xs_a;
+        float4* xs_nxt = odd ? A.xs_a : A.xs_b;
+        int* qh = &A.ctl->qhead[s & 3];
+        if (blockIdx.x == 0 && threadIdx.x == 0) A.ctl->qhead[(s + 2) & 3] = 0;   // idle since step s - 2
+        // the first unit of a warp is static (no burst of 4736 atomics on one address at the step start),
+        // the following ones are drawn from the queue head
+        const int n_warps = gridDim.x * MD_STEPS_WARPS;
+        int u_next = blockIdx.x * MD_STEPS_WARPS + wid;
+        while (u_next < A.n_units) {
+            const int u = u_next;
+            // fetch the next unit now: the atomic is in flight while this unit is processed
+            if (lane == 0) {
+                // (atom.inc, not atom.add: ptxas turns a uniform-address add into its warp-aggregation idiom,
+                // which shuffles the result out at once and so waits for the atomic right here)
+                unsigned got;
+                asm volatile("atom.relaxed.gpu.global.inc.u32 %0, [%1], 2147483647;" : "=r"(got) : "l"(qh) : "memory");
+                u_next = (int)got;      // + n_warps after the unit: nothing may touch the result before
+            }
+            // unit -> (block, piece)
+            int rb = u, part = 0;
+            const bool cut = u >= A.n_full;
+            if (cut) {
+                const int k = u - A.n_full;
+                rb = A.n_full + k / A.P;
+                part = k - (rb - A.n_full) * A.P;
+            }
+            const int r = rb / g.nblk, b = rb - r * g.nblk;
+            MdRep* rp = A.rep + r;
+            // tables valid for x_lo .. x_{halt-1}; a halt raised by another warp in THIS step is s + 1
+            const bool active = ld_volatile_i(&rp->lo) <= s && s < ld_volatile_i(&rp->halt);
+            if (active) {
+                const int nt_real = __ldg(&A.ntiles[rb]);
+                int ta = 0, tb = nt_real;
+                if (cut) {
+                    ta = (int)(((long long)nt_real * part) / A.P);
+                    tb = (int)(((long long)nt_real * (part + 1)) / A.P);
+                }
+                const int i = b * 32 + lane;
+                const size_t o = (size_t)r * g.np + i;
+                const float4 xi0 = xs_cur[o];
+                float fx = 0.f, fy = 0.f, fz = 0.f, e_acc = 0.f;
+                unsigned npair = 0;
+                bool finish = !cut;
+                if (!fin && s == 0 && ld_volatile_i(&rp->fs_valid)) {
+                    // first step of a run: set_state / the previous run left F(x_0) in fs
+                    if (part == 0) {
+                        const float4 f0 = A.fs[o];
+                        fx = f0.x; fy = f0.y; fz = f0.z;
+                        finish = true;
+                    }
+                } else {
+                    const uint32_t* tp = A.tiles + (size_t)rb * (size_t)(A.tcap + TILE_PAD) * A.tstride +
+                                         (size_t)ta * A.tstride;
+                    const bool gen = __ldg(&A.generic[rb]) != 0;
+                    const float4 bc = __ldg(&A.bcenter[rb]);
+                    float4 xi = xi0;
+                    if (gen) {
+                        md_tile_loop<false, true, false, 1>(xs_cur, tp, tb - ta, A.tstride, xi0, xi, bc, g, A.lj, lane,
+                                                            fx, fy, fz, e_acc, npair);
+                    } else {
+                        xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
+                        xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
+                        xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
+                        if (A.tstride == 96)
+                            md_tile_loop<false, false, true, 1>(xs_cur, tp, tb - ta, A.tstride, xi0, xi, bc, g, A.lj,
+                                                                lane, fx, fy, fz, e_acc, npair);
+                        else
+                            md_tile_loop<false, false, false, 1>(xs_cur, tp, tb - ta, A.tstride, xi0, xi, bc, g, A.lj,
+                                                                 lane, fx, fy, fz, e_acc, npair);
+                    }
+                    if (cut) {
+                        // publish the partial; the last piece to arrive adds them up in piece order
+                        float4* blockbuf = A.pbuf + (size_t)(rb - A.n_full) * A.P * 32;
+                        __stcg(&blockbuf[part * 32 + lane], make_float4(fx, fy, fz, 0.f));
+                        __syncwarp();      // orders the 32 stores before lane 0's release (cumulative)
+                        int old = 0;
+                        // release only (MEMBAR + ATOMG): an acquire fence would flush this SM's L1 (CCTL.IVALL)
+                        // under the other warps' position gathers; the partials are read back from L2 instead
+                        if (lane == 0)
+                            asm volatile("atom.add.release.gpu.global.s32 %0, [%1], 1;"
+                                         : "=r"(old) : "l"(A.cnt + rb) : "memory");
+                        old = __shfl_sync(FULL, old, 0);
+                        if (old == A.P - 1) {
+                            if (lane == 0) A.cnt[rb] = 0;      // next use: the next step, behind the grid barrier
+                            fx = fy = fz = 0.f;
+                            for (int q = 0; q < A.P; ++q) {
+                                const float4 pq = __ldcg(&blockbuf[q * 32 + lane]);
+                                fx += pq.x; fy += pq.y; fz += pq.z;
+                            }
+                            finish = true;
+                        }
+                    }
+                }
+                if (finish) {
+                    // reference rebuild (neighbors.py:903-905 -> build): the update of step s - 1 found a
+                    // particle skin/2 away from the reference positions, so x_s becomes the new reference
+                    bool took_ref = false;
+                    if ((A.final_mode != MD_FINAL_FORCE || !fin) && s >= 1 &&
+                        ld_volatile_i(&rp->user_step[(s - 1) & 1]) == s - 1) {
+                        took_ref = true;
+                        A.refu[o] = xi0;
+                        if (b == 0 && lane == 0) rp->user_rebuilds++;
+                    }
+                    if (fin) {
+                        A.fs[o] = make_float4(fx, fy, fz, 0.f);
+                        if (A.final_mode == MD_FINAL_KICK) {
+                            float4 v = A.vs[o];
+                            v.x = __fadd_rn(v.x, __fdiv_rn(__fmul_rn(A.sc.h, fx), v.w));
+                            v.y = __fadd_rn(v.y, __fdiv_rn(__fmul_rn(A.sc.h, fy), v.w));
+                            v.z = __fadd_rn(v.z, __fdiv_rn(__fmul_rn(A.sc.h, fz), v.w));
+                            A.vs[o] = v;
+                        }
+                    } else {
+                        md_block_update(r, b, lane, o, s, xi0, fx, fy, fz, took_ref, xs_nxt, A.vs, A.refu, A.refi, g,
+                                        A.sc, A.rep);
+                    }
+                }
+            }
+            u_next = __shfl_sync(FULL, u_next, 0) + n_warps;
         }
-        xn_all[o] = make_float4(xc[0], xc[1], xc[2], xi0.w);
-        vs_all[o] = make_float4(vc[0], vc[1], vc[2], m);
-        // reference rebuild condition (exact, neighbors.py:864-868)
-        const float4 ru = took_ref ? xi0 : refu_all[o];
-        float rx, ry, rz, d;
-        ref_displacement<true>(xc[0], xc[1], xc[2], ru.x, ru.y, ru.z, g.box, rx, ry, rz, d);
-        moved_user = d >= sc.half_skin_user;
-        // engine's own list validity (fast min-image)
-        const float4 ri = refi_all[o];
-        float dx = xc[0] - ri.x, dy = xc[1] - ri.y, dz = xc[2] - ri.z;
-        dx -= g.box.lx * rintf(dx * g.inv_lx);
-        dy -= g.box.ly * rintf(dy * g.inv_ly);
-        dz -= g.box.lz * rintf(dz * g.inv_lz);
-        moved_int = dx * dx + dy * dy + dz * dz >= sc.half_skin_int2;
-    }
-    // rare events (a rebuild every few dozen steps): warp vote, then straight to the control block.
-    // halt = first step that must not run on these tables; user_step[] is read by the NEXT launch
-    const unsigned ev = __reduce_or_sync(FULL, (moved_int ? 1u : 0u) | (moved_user ? 2u : 0u));
-    if (lane == 0 && ev) {
-        if (ev & 1u) atomicMin(&rep[r].halt, step + 1);
-        if (ev & 2u) rep[r].user_step[step & 1] = step;
+        if (fin) break;
+        // ---- grid barrier: x_{s+1}, v, the key chain and the halts of this step become visible ----
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&A.ctl->bar, 1u);
+            bar_target += gridDim.x;
+            for (unsigned spin = 0; ld_acquire_u(&A.ctl->bar) < bar_target; ++spin)
+                if (spin > (1u << 22)) { A.ctl->error = 1; break; }   // ~seconds: fail loudly instead of hanging
+        }
+        if (wid == 0) {
+            __syncwarp();
+            // does any replica still have work at step s + 1 or later?  (A halt raised during step s + 1 by
+            // a faster CTA has the value s + 2 and does not change the answer.)
+            bool any = false;
+            for (int r = lane; r < A.R; r += 32) {
+                const int lo = ld_volatile_i(&A.rep[r].lo), halt = ld_volatile_i(&A.rep[r].halt);
+                any = any || (halt > (lo > s + 1 ? lo : s + 1) && lo <= A.s_end);
+            }
+            any = __any_sync(FULL, any);
+            if (lane == 0) s_cont = any ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_cont) break;
     }
 }
 
@@ -1231,12 +1633,29 @@ __global__ void k_md_sync_odd(MdGeom g, const MdRep* __restrict__ rep, const flo
     dst[o] = src[o];
 }
 
-__global__ void k_md_scale_v(float4* __restrict__ vs, int np, float sc) {
+// per-replica host scalars travel as kernel arguments (no staging buffer, no synchronisation)
+#define MD_ARG_CHUNK 256
+struct MdFloatChunk { float v[MD_ARG_CHUNK]; };
+
+// v *= scale[r] for the replicas r0 .. r0 + count - 1 (blockIdx.y); 1.0 leaves a replica untouched
+__global__ void k_md_scale_v(float4* __restrict__ vs_all, int np, int r0, const __grid_constant__ MdFloatChunk sc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= np) return;
+    const float f = sc.v[blockIdx.y];
+    if (i >= np || f == 1.0f) return;
+    float4* vs = vs_all + (size_t)(r0 + blockIdx.y) * np;
     float4 v = vs[i];
-    v.x *= sc; v.y *= sc; v.z *= sc;
+    v.x *= f; v.y *= f; v.z *= f;
     vs[i] = v;
+}
+
+__global__ void k_md_set_kt(MdRep* __restrict__ rep, int r0, int count, const __grid_constant__ MdFloatChunk kt) {
+    const int k = threadIdx.x;
+    if (k < count) rep[r0 + k].kT = kt.v[k];
+}
+
+__global__ void k_md_reset_pairs(MdRep* __restrict__ rep, int R) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) rep[r].int_pairs2 = 0ull;
 }
 
 __global__ void k_md_kick(float4* __restrict__ vs_all, const float4* __restrict__ fs_all, MdGeom g,
@@ -1298,6 +1717,42 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->bcenter, nb * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->rep, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMalloc(&md->step_base, sizeof(int)));
+    {
+        // persistent step kernel: one CTA of 32 warps per SM, all co-resident (cooperative launch)
+        int per_sm = 0;
+        CHX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_steps, MD_STEPS_WARPS * 32, 0));
+        md->coop_grid = md->ctx->sm_count * (per_sm > 0 ? 1 : 0);
+        if (md->coop_grid == 0) md->persist = false;
+        md->Wmax = (md->coop_grid > 0 ? md->coop_grid : 1) * MD_STEPS_WARPS;
+        // unit queue: whole blocks for the full rounds, the remainder cut into P pieces so that the last
+        // round is P times finer (P in {1, 2, 4, 8}: fewest pieces that minimise rounds / P)
+        {
+            const long long NBt = (long long)nb, W = md->Wmax;
+            long long nfull = (NBt / W) * W;
+            int P = 1;
+            const long long rem = NBt - nfull;
+            if (rem > 0) {
+                double best = 1e30;
+                for (int p = 1; p <= 8; p *= 2) {
+                    const double rounds = (double)((rem * p + W - 1) / W) / p * (1.0 + 0.03 * (p - 1));
+                    if (rounds < best - 1e-9) { best = rounds; P = p; }
+                }
+            }
+            { const char* e = getenv("CHX_MD_PIECES"); if (e && atoi(e) > 0) { P = atoi(e); } }
+            { const char* e = getenv("CHX_MD_NFULL"); if (e && atoi(e) >= 0 && atoi(e) <= NBt) nfull = atoi(e); }
+            md->q_full = (int)nfull; md->q_P = P; md->q_units = (int)(nfull + (NBt - nfull) * P);
+        }
+        CHX_CUDA(cudaMalloc(&md->pbuf, ((size_t)(nb - md->q_full) * md->q_P + 1) * 32 * sizeof(float4)));
+        CHX_CUDA(cudaMalloc(&md->part_cnt, nb * sizeof(int)));
+        CHX_CUDA(cudaMemset(md->part_cnt, 0, nb * sizeof(int)));
+        CHX_CUDA(cudaMalloc(&md->ctl, sizeof(MdCtl)));
+        CHX_CUDA(cudaMemset(md->ctl, 0, sizeof(MdCtl)));
+        md->pev0 = md->pev1 = nullptr;
+        for (int k = 0; k < 2; ++k) {
+            md->pipe_e0[k] = md->pipe_e1[k] = md->pipe_ed[k] = nullptr;
+            CHX_CUDA(cudaMallocHost(&md->pipe_rep[k], md->R * sizeof(MdRep)));
+        }
+    }
     md->tev0 = md->tev1 = nullptr; md->timed_ms = 0.0; md->timed_steps = 0;
     md->chunk_graph = nullptr; md->chunk_graph_tcap = -1; md->chunk_graph_lw = -1; md->cap_stream = nullptr;
     CHX_CUDA(cudaMallocHost(&md->rep_host, md->R * sizeof(MdRep)));
@@ -1368,7 +1823,10 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
     }
     k_md_cellcount<<<gp, 256, 0, st>>>(md->xs, g, md->lin2h, md->rep, md->cell_of, md->cell_count);
     CHX_LAUNCHED(ctx);
-    k_md_scan<<<R, 1024, 0, st>>>(md->cell_count, md->cell_start, md->cell_range, md->h2lin, g.ncell, md->rep);
+    k_md_scan<<<R, 1024, 0, st>>>(md->cell_count, md->cell_start, g.ncell, md->rep);
+    CHX_LAUNCHED(ctx);
+    k_md_ranges<<<dim3(chx_div_up(g.ncell, 256), R), 256, 0, st>>>(md->cell_count, md->cell_start, md->cell_range,
+                                                                   md->h2lin, g.ncell, md->rep);
     CHX_LAUNCHED(ctx);
     k_md_place<<<gp, 256, 0, st>>>(md->cell_of, g, md->cell_start, md->rep, md->cell_count, md->order);
     CHX_LAUNCHED(ctx);
@@ -1401,9 +1859,31 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
             md->xs, md->cell_range, g, R_list, md->internal_skin, md_ccap(md), md->qcap, md->cand_idx,
             md->cand_col, md->cand_n, md->generic, md->bcenter, md->rep);
         CHX_LAUNCHED(ctx);
-        CHX_CUDA(cudaFuncSetAttribute(k_md_deal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
-        k_md_deal<<<dim3(chx_div_up(g.nblk, DEAL_BPC), R), 128, smem_d, st>>>(
-            md->cand_col, md->cand_n, g, md_ccap(md), md->tcap, md->lw, md->memb, md->tmeta, md->ntiles, md->rep);
+        static int old_deal = -2;   // CHX_MD_OLD_DEAL = 1 / 0 forces k_md_deal / k_md_deal2; unset: by grid size
+        if (old_deal == -2) { const char* e = getenv("CHX_MD_OLD_DEAL"); old_deal = e ? (e[0] == '1' ? 1 : 0) : -1; }
+        if (md->deal_tpl < 2) md->deal_tpl = 2;
+        while (16 * md->deal_tpl < md->tcap && md->deal_tpl_auto_grow) md->deal_tpl *= 2;
+        // measured on B200 (profiles/r02_launches_*.csv): 8 x 8,192 particles (2048 blocks) 360 -> 160 us with
+        // k_md_deal2, N = 262,144 (8192 blocks) 242 -> 336 us: the half-warp variant wins while the grid is
+        // too small to hide the latency of the sequential greedy, the 8-lane variant once it is instruction bound
+        const bool small_grid = (long long)R * g.nblk <= 16LL * ctx->sm_count * 2;
+        if (md->deal_tpl <= 8 && (old_deal < 0 ? small_grid : !old_deal)) {
+            // half-warp per block, bit-sliced counters (k_md_deal2); 16 * TPL tiles per block at most: the
+            // smallest instantiation that has held every block so far (it grows on overflow bit 8)
+            const dim3 gd(chx_div_up(g.nblk, DEAL2_BPC), R);
+#define MD_DEAL2(TPL, NPL)                                                                              \
+            k_md_deal2<TPL, NPL><<<gd, 128, 0, st>>>(md->cand_col, md->cand_n, g, md_ccap(md), md->tcap, md->lw, \
+                                                     md->memb, md->tmeta, md->ntiles, md->rep)
+            const bool p4 = md->lw <= 2;   // counters up to 6 * lw: 4 bit planes for lw = 2, else 6
+            if (md->deal_tpl == 2) { if (p4) MD_DEAL2(2, 4); else MD_DEAL2(2, 6); }
+            else if (md->deal_tpl == 4) { if (p4) MD_DEAL2(4, 4); else MD_DEAL2(4, 6); }
+            else { if (p4) MD_DEAL2(8, 4); else MD_DEAL2(8, 6); }
+#undef MD_DEAL2
+        } else {
+            CHX_CUDA(cudaFuncSetAttribute(k_md_deal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+            k_md_deal<<<dim3(chx_div_up(g.nblk, DEAL_BPC), R), 128, smem_d, st>>>(
+                md->cand_col, md->cand_n, g, md_ccap(md), md->tcap, md->lw, md->memb, md->tmeta, md->ntiles, md->rep);
+        }
         CHX_LAUNCHED(ctx);
         k_md_emit<<<dim3(chx_div_up(g.nblk, 4), R), 128, 0, st>>>(
             md->cand_idx, md->cand_col, md->memb, md->tmeta, md->ntiles, g, md_ccap(md), md->tcap, md->lw,
@@ -1426,6 +1906,7 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
         // bit 0 = candidate list of a block too small, bit 1 = the deal ran out of tiles or of list words,
         // bit 2 = candidate QUEUE (shared memory of k_md_cand) too small: no device array depends on it
         if (ovf & 4) md->qcap = (md->qcap + md->qcap / 2 + 31) & ~31;
+        if (ovf & 8) md->deal_tpl *= 2;    // k_md_deal2 needs more tiles per lane (beyond 8: the shared-memory k_md_deal)
         if (!(ovf & 3)) {
             for (int r = 0; r < R; ++r) {
                 md->rep_host[r].overflow = 0;
@@ -1524,6 +2005,132 @@ static int md_force(chx_ljmd* md, int mode, int step, bool energy, int report_in
     return CHX_OK;
 }
 
+// One cooperative launch of the persistent step kernel: steps s0 .. s_end - 1 for the replicas with
+// lo <= step < halt, and (final_mode) the closing force evaluation of x_{s_end}.  Asynchronous.
+static int md_launch_persist(chx_ljmd* md, int s0, int s_end, int final_mode) {
+    chx_ctx* ctx = md->ctx;
+    cudaStream_t st = ctx->stream;
+    CHX_CUDA(cudaMemsetAsync(md->ctl, 0, sizeof(MdCtl), st));   // barrier counter, queue heads
+    MdStepsArgs A;
+    A.xs_a = md->xs; A.xs_b = md->xs_b; A.fs = md->fs; A.vs = md->vs; A.refu = md->refu; A.refi = md->refi;
+    A.tiles = md->tiles; A.ntiles = md->ntiles; A.generic = md->generic; A.bcenter = md->bcenter;
+    A.pbuf = md->pbuf; A.cnt = md->part_cnt; A.n_full = md->q_full; A.P = md->q_P; A.n_units = md->q_units;
+    A.rep = md->rep; A.ctl = md->ctl; A.g = md->g; A.lj = md_lj(md); A.sc = md_step_const(md);
+    A.tcap = md->tcap; A.tstride = md_tstride(md); A.NB = md->R * md->g.nblk; A.R = md->R;
+    A.s0 = s0; A.s_end = s_end; A.final_mode = final_mode;
+    void* args[] = {&A};
+    if (!md->pev0) { CHX_CUDA(cudaEventCreate(&md->pev0)); CHX_CUDA(cudaEventCreate(&md->pev1)); }
+    CHX_CUDA(cudaEventRecord(md->pev0, st));
+    CHX_CUDA(cudaLaunchCooperativeKernel((const void*)k_md_steps, dim3(md->coop_grid), dim3(MD_STEPS_WARPS * 32), args, 0, st));
+    CHX_CUDA(cudaEventRecord(md->pev1, st));
+    CHX_LAUNCHED(ctx);
+    return CHX_OK;
+}
+
+// chx_ljmd_run on the persistent step kernel (no energy reports inside the run).  rep_host holds the
+// uploaded per-run control (keys, lo = 0, halt = none).  A launch runs until every replica it serves has
+// gone stale or the chunk ends; the host rebuilds the stale replicas' tables on x_halt and relaunches.
+static int md_run_persist(chx_ljmd* md, int nsteps, uint32_t* keys_host) {
+    chx_ctx* ctx = md->ctx;
+    const MdGeom& g = md->g;
+    cudaStream_t st = ctx->stream;
+    const int R = md->R;
+    auto clear_build_stats = [](MdRep& q) { q.overflow = 0; q.cand_pairs2 = 0; q.trip_slots = 0; };
+    // Batched replicas go stale at different steps; with R > 1 every chunk starts on fresh tables for all
+    // replicas and a halt inside a chunk becomes the exception (CHX_MD_PROACTIVE=0 disables it).  A single
+    // system runs until its tables go stale.
+    bool proactive = R > 1;
+    { const char* e = getenv("CHX_MD_PROACTIVE"); if (e) proactive = e[0] == '1'; }
+    int CH = proactive ? 50 : nsteps;
+    { const char* e = getenv("CHX_MD_CHUNK"); if (e && atoi(e) > 0) CH = atoi(e); }
+    int rc = CHX_OK;
+    // one launch + the bookkeeping of its timing; s0 = first step any replica runs
+    auto launch = [&](int s0, int te, int final_mode) -> int {
+        int rc2 = md_launch_persist(md, s0, te, final_mode);
+        if (rc2 != CHX_OK) return rc2;
+        CHX_CUDA(cudaMemcpyAsync(ctx->host_pinned, md->ctl, sizeof(MdCtl), cudaMemcpyDeviceToHost, st));
+        rc2 = md_download_rep(md);
+        if (rc2 != CHX_OK) return rc2;
+        if (reinterpret_cast<const MdCtl*>(ctx->host_pinned)->error) {
+            chx_set_error("k_md_steps: grid barrier timed out");
+            return CHX_CUDA_ERROR;
+        }
+        int last = s0;
+        for (int r = 0; r < R; ++r) {
+            const MdRep& q = md->rep_host[r];
+            if (q.lo > te) continue;
+            const int end = q.halt < te ? q.halt : te;
+            if (end > last) last = end;
+        }
+        float ems = 0.f;
+        if (last > s0 && cudaEventElapsedTime(&ems, md->pev0, md->pev1) == cudaSuccess) {
+            md->timed_ms += ems;
+            md->timed_steps += last - s0;
+        }
+        return CHX_OK;
+    };
+    int t = 0;
+    while (t < nsteps) {
+        const int te = nsteps - t < CH ? nsteps : t + CH;
+        const int fin = te == nsteps ? MD_FINAL_KICK : MD_FINAL_NONE;
+        if (proactive && !(t == 0 && md->tables_fresh)) {
+            for (int r = 0; r < R; ++r) { md->rep_host[r].flag = 1; clear_build_stats(md->rep_host[r]); }
+            rc = md_upload_rep(md);
+            if (rc != CHX_OK) return rc;
+            rc = md_rebuild(md, (t & 1) != 0);
+            if (rc != CHX_OK) return rc;
+            for (int r = 0; r < R; ++r) md->rep_host[r].flag = 0;
+            rc = md_upload_rep(md);
+            if (rc != CHX_OK) return rc;
+        }
+        md->tables_fresh = false;
+        rc = launch(t, te, fin);
+        if (rc != CHX_OK) return rc;
+        // replicas whose tables went stale inside the chunk (halt = first step that did not run): rebuild
+        // on x_halt and run the rest of the chunk.  halt == te needs tables for the next chunk (a proactive
+        // rebuild at its start covers that) or for the closing force evaluation.
+        for (;;) {
+            int first = HALT_NONE;
+            bool any = false;
+            for (int r = 0; r < R; ++r) {
+                MdRep& q = md->rep_host[r];
+                const bool stale = q.halt <= te && !(q.halt == te && proactive && te < nsteps);
+                if (stale) {
+                    q.flag = 1; q.lo = q.halt; q.halt = HALT_NONE;
+                    clear_build_stats(q);
+                    if (q.lo < first) first = q.lo;
+                    any = true;
+                } else {
+                    q.flag = 0; q.lo = HALT_NONE;   // done with this chunk
+                    if (q.halt <= te) q.halt = HALT_NONE;
+                }
+            }
+            if (!any) break;
+            rc = md_upload_rep(md);
+            if (rc != CHX_OK) return rc;
+            rc = md_rebuild(md, true);
+            if (rc != CHX_OK) return rc;
+            rc = launch(first, te, fin);
+            if (rc != CHX_OK) return rc;
+        }
+        for (int r = 0; r < R; ++r) { md->rep_host[r].lo = te; md->rep_host[r].flag = 0; md->rep_host[r].halt = HALT_NONE; }
+        rc = md_upload_rep(md);
+        if (rc != CHX_OK) return rc;
+        t = te;
+    }
+    if (nsteps & 1)   // x_n is in buffer B: outside a run the current positions live in md->xs
+        CHX_CUDA(cudaMemcpyAsync(md->xs, md->xs_b, (size_t)R * g.np * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    rc = md_download_rep(md);
+    if (rc != CHX_OK) return rc;
+    for (int r = 0; r < R; ++r) {
+        keys_host[2 * r] = md->rep_host[r].key[nsteps & 1][0];
+        keys_host[2 * r + 1] = md->rep_host[r].key[nsteps & 1][1];
+    }
+    md->forces_valid = true;
+    md->steps += nsteps;
+    return CHX_OK;
+}
+
 extern "C" {
 
 int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
@@ -1586,7 +2193,11 @@ int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
         md->qcap = ((int)(qf * cand) + 256 + 31) & ~31;
     }
     md->rebuilds = 0; md->steps = 0; md->have_state = false; md->forces_valid = false;
+    md->deal_tpl = 2; md->deal_tpl_auto_grow = false;
     { const char* e = getenv("CHX_MD_NOGRAPH"); md->no_graph = e && e[0] == '1'; }
+    // the persistent step kernel is opt-in: measured slower than one launch per step on B200
+    // (N = 262,144: 66.8 vs 53.0 us per step; 8 x 8,192: 26.2 vs 22.8 us; profiles/r02_step_kernel_ncu.md)
+    { const char* e = getenv("CHX_MD_PERSIST"); md->persist = e && e[0] == '1'; }
     md->launches0 = ctx->launches;
     int rc = md_alloc(md);
     if (rc != CHX_OK) { delete md; return rc; }
@@ -1605,6 +2216,12 @@ int chx_ljmd_destroy(chx_ljmd* md) {
     cudaFree(md->generic); cudaFree(md->bcenter); cudaFree(md->rep); cudaFree(md->step_base);
     if (md->chunk_graph) cudaGraphExecDestroy(md->chunk_graph);
     cudaFree(md->xs_b);
+    cudaFree(md->pbuf); cudaFree(md->part_cnt); cudaFree(md->ctl);
+    if (md->pev0) { cudaEventDestroy(md->pev0); cudaEventDestroy(md->pev1); }
+    for (int k = 0; k < 2; ++k) {
+        if (md->pipe_e0[k]) { cudaEventDestroy(md->pipe_e0[k]); cudaEventDestroy(md->pipe_e1[k]); cudaEventDestroy(md->pipe_ed[k]); }
+        cudaFreeHost(md->pipe_rep[k]);
+    }
     if (md->cap_stream) cudaStreamDestroy(md->cap_stream);
     if (md->tev0) { cudaEventDestroy(md->tev0); cudaEventDestroy(md->tev1); }
     cudaFreeHost(md->rep_host);
@@ -1633,7 +2250,8 @@ int chx_ljmd_set_state(chx_ljmd* md, const float* x, const float* v, const float
     CHX_LAUNCHED(ctx);
     rc = md_rebuild(md);
     if (rc != CHX_OK) return rc;
-    rc = md_force(md, FMODE_ALL, -2, false, 0, nullptr);
+    // forces of x_0 in the summation order of the step loop (a later run starts from them)
+    rc = md->persist ? md_launch_persist(md, 0, 0, MD_FINAL_FORCE) : md_force(md, FMODE_ALL, -2, false, 0, nullptr);
     if (rc != CHX_OK) return rc;
     md->have_state = true;
     md->tables_fresh = true;
@@ -1683,8 +2301,17 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     if (rc != CHX_OK) return rc;
     if (report) CHX_CUDA(cudaMemsetAsync(energies_dev, 0, sizeof(double) * R * n_reports, st));
     md->forces_valid = false;
+    if (md->persist && !report) return md_run_persist(md, nsteps, keys_host);
 
-    int CH = R > 1 ? 50 : 32;   // steps per graph replay / host check (CHX_MD_CHUNK overrides; even)
+    // Batched replicas go stale at different steps; waiting for each other inside a chunk and then
+    // catching up one by one costs more than the tables themselves.  So with R > 1 every chunk starts
+    // on fresh tables for all replicas and a halt inside a chunk becomes the exception.
+    // CHX_MD_PROACTIVE=0 disables it.
+    bool proactive = R > 1;
+    { const char* e = getenv("CHX_MD_PROACTIVE"); if (e) proactive = e[0] == '1'; }
+    // steps per graph replay / host check (CHX_MD_CHUNK overrides; even).  A single system runs short chunks
+    // with one chunk of look-ahead (below), batched replicas one rebuild per 50-step chunk
+    int CH = proactive ? 50 : 8;
     { const char* e = getenv("CHX_MD_CHUNK"); if (e && atoi(e) > 0) CH = atoi(e); }
     CH += CH & 1;
 
@@ -1700,7 +2327,7 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     // full chunks without energy reports replay one CUDA graph of CH fused steps: the kernels read
     // the chunk's first step (even, so the buffer roles are the captured ones) from device memory
     const bool use_graph = !report && !md->no_graph;
-    auto launch_chunk_graph = [&](int s0) -> int {
+    auto launch_chunk_graph = [&](int s0, cudaEvent_t ev0, cudaEvent_t ev1) -> int {
         if (md->chunk_graph && (md->chunk_graph_tcap != md->tcap || md->chunk_graph_lw != md->lw || md->chunk_graph_ch != CH)) {
             cudaGraphExecDestroy(md->chunk_graph);
             md->chunk_graph = nullptr;
@@ -1727,53 +2354,17 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
         }
         k_md_setbase<<<1, 1, 0, st>>>(md->step_base, s0);
         CHX_LAUNCHED(ctx);
-        if (!md->tev0) { CHX_CUDA(cudaEventCreate(&md->tev0)); CHX_CUDA(cudaEventCreate(&md->tev1)); }
-        CHX_CUDA(cudaEventRecord(md->tev0, st));
+        CHX_CUDA(cudaEventRecord(ev0, st));
         CHX_CUDA(cudaGraphLaunch(md->chunk_graph, st));
-        CHX_CUDA(cudaEventRecord(md->tev1, st));
+        CHX_CUDA(cudaEventRecord(ev1, st));
         ctx->launches += CH;
         return CHX_OK;
     };
     auto clear_build_stats = [](MdRep& q) { q.overflow = 0; q.cand_pairs2 = 0; q.trip_slots = 0; };
 
-    // Batched replicas go stale at different steps; waiting for each other inside a chunk and then
-    // catching up one by one costs more than the tables themselves.  So with R > 1 every chunk starts
-    // on fresh tables for all replicas and a halt inside a chunk becomes the exception.
-    // CHX_MD_PROACTIVE=0 disables it.
-    bool proactive = R > 1;
-    { const char* e = getenv("CHX_MD_PROACTIVE"); if (e) proactive = e[0] == '1'; }
-    int t = 0;
-    while (t < nsteps) {
-        const int te = nsteps - t < CH ? nsteps : t + CH;
-        if (proactive && !(t == 0 && md->tables_fresh)) {
-            for (int r = 0; r < R; ++r) { md->rep_host[r].flag = 1; clear_build_stats(md->rep_host[r]); }
-            rc = md_upload_rep(md);
-            if (rc != CHX_OK) return rc;
-            rc = md_rebuild(md, (t & 1) != 0);
-            if (rc != CHX_OK) return rc;
-            for (int r = 0; r < R; ++r) md->rep_host[r].flag = 0;
-            rc = md_upload_rep(md);
-            if (rc != CHX_OK) return rc;
-        }
-        md->tables_fresh = false;
-        const bool replay = use_graph && te - t == CH && !(t & 1);
-        rc = replay ? launch_chunk_graph(t) : launch_steps(t, te, nullptr);
-        if (rc != CHX_OK) return rc;
-        rc = md_download_rep(md);
-        if (rc != CHX_OK) return rc;
-        if (replay) {
-            // step-kernel timing for the roofline: only replays in which every launch did its full work
-            bool clean = true;
-            for (int r = 0; r < R; ++r) clean = clean && md->rep_host[r].halt >= te;
-            float ems = 0.f;
-            if (clean && cudaEventElapsedTime(&ems, md->tev0, md->tev1) == cudaSuccess) {
-                md->timed_ms += ems;
-                md->timed_steps += CH;
-            }
-        }
-        // replicas whose tables went stale inside the chunk (halt = first step that did not run):
-        // rebuild on x_halt and run the rest of the chunk.  halt == te needs tables for the next chunk
-        // (or for the final force evaluation); a proactive rebuild at the next chunk start covers it.
+    // rebuild the tables of the stale replicas (halt <= te) on x_halt and run them up to te with direct
+    // launches, until nobody is stale; rep_host must hold the downloaded control blocks
+    auto catch_up = [&](int te) -> int {
         for (;;) {
             int first = HALT_NONE;
             bool any = false;
@@ -1790,16 +2381,109 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
                     if (q.halt <= te) q.halt = HALT_NONE;
                 }
             }
-            if (!any) break;
+            if (!any) return CHX_OK;
+            int rc2 = md_upload_rep(md);
+            if (rc2 != CHX_OK) return rc2;
+            rc2 = md_rebuild(md, true);
+            if (rc2 != CHX_OK) return rc2;
+            rc2 = launch_steps(first, te, nullptr);
+            if (rc2 != CHX_OK) return rc2;
+            rc2 = md_download_rep(md);
+            if (rc2 != CHX_OK) return rc2;
+        }
+    };
+    int t = 0;
+    if (!proactive && use_graph) {
+        // LOOK-AHEAD LOOP.  Two chunks are in flight: chunk k + 1 is enqueued before the host looks at the
+        // result of chunk k, so the device never waits for the host between chunks.  This is safe because the
+        // halt lives on the device: once a replica's tables are stale, every later launch returns at once for
+        // it (step >= halt).  When a chunk reports a halt the look-ahead is drained (a handful of no-op
+        // launches), the tables are rebuilt on x_halt and the steps up to the end of the look-ahead are redone
+        // with direct launches.
+        struct Pend { int t0, te; bool replay; int slot; };
+        Pend pend[2];
+        int n_pend = 0, t_enq = 0, next_slot = 0;
+        md->tables_fresh = false;
+        for (int k = 0; k < 2; ++k)
+            if (!md->pipe_e0[k]) {
+                CHX_CUDA(cudaEventCreate(&md->pipe_e0[k]));
+                CHX_CUDA(cudaEventCreate(&md->pipe_e1[k]));
+                CHX_CUDA(cudaEventCreateWithFlags(&md->pipe_ed[k], cudaEventDisableTiming));
+            }
+        while (t < nsteps) {
+            while (n_pend < 2 && t_enq < nsteps) {
+                const int te = nsteps - t_enq < CH ? nsteps : t_enq + CH;
+                const bool replay = te - t_enq == CH && !(t_enq & 1);
+                const int sl = next_slot;
+                next_slot ^= 1;
+                rc = replay ? launch_chunk_graph(t_enq, md->pipe_e0[sl], md->pipe_e1[sl]) : launch_steps(t_enq, te, nullptr);
+                if (rc != CHX_OK) return rc;
+                CHX_CUDA(cudaMemcpyAsync(md->pipe_rep[sl], md->rep, R * sizeof(MdRep), cudaMemcpyDeviceToHost, st));
+                CHX_CUDA(cudaEventRecord(md->pipe_ed[sl], st));
+                pend[n_pend].t0 = t_enq; pend[n_pend].te = te; pend[n_pend].replay = replay; pend[n_pend].slot = sl;
+                ++n_pend;
+                t_enq = te;
+            }
+            const Pend p = pend[0];
+            CHX_CUDA(cudaEventSynchronize(md->pipe_ed[p.slot]));
+            bool halted = false;
+            for (int r = 0; r < R; ++r) halted = halted || md->pipe_rep[p.slot][r].halt <= p.te;
+            if (!halted) {
+                float ems = 0.f;   // step-kernel timing for the roofline: every launch of this replay did its full work
+                if (p.replay && cudaEventElapsedTime(&ems, md->pipe_e0[p.slot], md->pipe_e1[p.slot]) == cudaSuccess) {
+                    md->timed_ms += ems;
+                    md->timed_steps += CH;
+                }
+                pend[0] = pend[1];
+                --n_pend;
+                t = p.te;
+                continue;
+            }
+            rc = md_download_rep(md);      // waits for the look-ahead as well
+            if (rc != CHX_OK) return rc;
+            n_pend = 0;
+            rc = catch_up(t_enq);
+            if (rc != CHX_OK) return rc;
+            for (int r = 0; r < R; ++r) { md->rep_host[r].lo = t_enq; md->rep_host[r].flag = 0; md->rep_host[r].halt = HALT_NONE; }
             rc = md_upload_rep(md);
             if (rc != CHX_OK) return rc;
-            rc = md_rebuild(md, true);
+            t = t_enq;
+        }
+    }
+    while (t < nsteps) {
+        const int te = nsteps - t < CH ? nsteps : t + CH;
+        if (proactive && !(t == 0 && md->tables_fresh)) {
+            for (int r = 0; r < R; ++r) { md->rep_host[r].flag = 1; clear_build_stats(md->rep_host[r]); }
+            rc = md_upload_rep(md);
             if (rc != CHX_OK) return rc;
-            rc = launch_steps(first, te, nullptr);
+            rc = md_rebuild(md, (t & 1) != 0);
             if (rc != CHX_OK) return rc;
-            rc = md_download_rep(md);
+            for (int r = 0; r < R; ++r) md->rep_host[r].flag = 0;
+            rc = md_upload_rep(md);
             if (rc != CHX_OK) return rc;
         }
+        md->tables_fresh = false;
+        const bool replay = use_graph && te - t == CH && !(t & 1);
+        if (replay && !md->tev0) { CHX_CUDA(cudaEventCreate(&md->tev0)); CHX_CUDA(cudaEventCreate(&md->tev1)); }
+        rc = replay ? launch_chunk_graph(t, md->tev0, md->tev1) : launch_steps(t, te, nullptr);
+        if (rc != CHX_OK) return rc;
+        rc = md_download_rep(md);
+        if (rc != CHX_OK) return rc;
+        if (replay) {
+            // step-kernel timing for the roofline: only replays in which every launch did its full work
+            bool clean = true;
+            for (int r = 0; r < R; ++r) clean = clean && md->rep_host[r].halt >= te;
+            float ems = 0.f;
+            if (clean && cudaEventElapsedTime(&ems, md->tev0, md->tev1) == cudaSuccess) {
+                md->timed_ms += ems;
+                md->timed_steps += CH;
+            }
+        }
+        // replicas whose tables went stale inside the chunk (halt = first step that did not run):
+        // rebuild on x_halt and run the rest of the chunk.  halt == te needs tables for the next chunk
+        // (or for the final force evaluation); a proactive rebuild at the next chunk start covers it.
+        rc = catch_up(te);
+        if (rc != CHX_OK) return rc;
         for (int r = 0; r < R; ++r) { md->rep_host[r].lo = te; md->rep_host[r].flag = 0; md->rep_host[r].halt = HALT_NONE; }
         rc = md_upload_rep(md);
         if (rc != CHX_OK) return rc;
@@ -1828,11 +2512,8 @@ int chx_ljmd_energy(chx_ljmd* md, double* energy_dev) {
     CHX_REQUIRE(md && md->have_state && energy_dev, "engine has no state or energy_dev is NULL");
     cudaStream_t st = md->ctx->stream;
     CHX_CUDA(cudaMemsetAsync(energy_dev, 0, sizeof(double) * md->R, st));
-    int rc = md_download_rep(md);
-    if (rc != CHX_OK) return rc;
-    for (int r = 0; r < md->R; ++r) md->rep_host[r].int_pairs2 = 0;
-    rc = md_upload_rep(md);
-    if (rc != CHX_OK) return rc;
+    k_md_reset_pairs<<<chx_div_up(md->R, 128), 128, 0, st>>>(md->rep, md->R);   // no host round trip
+    CHX_LAUNCHED(md->ctx);
     return md_force(md, FMODE_ALL, -2, true, 0, energy_dev);
 }
 
@@ -1860,19 +2541,26 @@ int chx_ljmd_stats(chx_ljmd* md, long long* stats_host) {
 
 int chx_ljmd_set_kt(chx_ljmd* md, const float* kT_per_replica_host) {
     CHX_REQUIRE(md && md->have_state && kT_per_replica_host, "engine has no state or kT is NULL");
-    int rc = md_download_rep(md);
-    if (rc != CHX_OK) return rc;
-    for (int r = 0; r < md->R; ++r) md->rep_host[r].kT = kT_per_replica_host[r];
-    return md_upload_rep(md);
+    for (int r0 = 0; r0 < md->R; r0 += MD_ARG_CHUNK) {
+        MdFloatChunk c;
+        const int cnt = md->R - r0 < MD_ARG_CHUNK ? md->R - r0 : MD_ARG_CHUNK;
+        for (int k = 0; k < cnt; ++k) c.v[k] = kT_per_replica_host[r0 + k];
+        k_md_set_kt<<<1, MD_ARG_CHUNK, 0, md->ctx->stream>>>(md->rep, r0, cnt, c);
+        CHX_LAUNCHED(md->ctx);
+    }
+    return CHX_OK;
 }
 
 int chx_ljmd_scale_velocities(chx_ljmd* md, const float* scale_per_replica_host) {
     CHX_REQUIRE(md && md->have_state && scale_per_replica_host, "engine has no state or scale is NULL");
     const MdGeom& g = md->g;
-    for (int r = 0; r < md->R; ++r) {
-        const float sc = scale_per_replica_host[r];
-        if (sc == 1.0f) continue;
-        k_md_scale_v<<<chx_div_up(g.np, 256), 256, 0, md->ctx->stream>>>(md->vs + (size_t)r * g.np, g.np, sc);
+    for (int r0 = 0; r0 < md->R; r0 += MD_ARG_CHUNK) {
+        MdFloatChunk c;
+        const int cnt = md->R - r0 < MD_ARG_CHUNK ? md->R - r0 : MD_ARG_CHUNK;
+        bool any = false;
+        for (int k = 0; k < cnt; ++k) { c.v[k] = scale_per_replica_host[r0 + k]; any = any || c.v[k] != 1.0f; }
+        if (!any) continue;
+        k_md_scale_v<<<dim3(chx_div_up(g.np, 256), cnt), 256, 0, md->ctx->stream>>>(md->vs, g.np, r0, c);
         CHX_LAUNCHED(md->ctx);
     }
     return CHX_OK;

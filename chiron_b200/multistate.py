@@ -67,6 +67,54 @@ def gather_rows(local_rows: np.ndarray, n_replicas: int, group=None) -> np.ndarr
     return out
 
 
+class _RowGatherer:
+    """All-gather of the per-rank rows of the R x K reduced-potential matrix with the rows ALREADY ON THE
+    DEVICE (NCCL): the batched energy kernel's output is scaled into a persistent send buffer, one
+    `all_gather_into_tensor` runs on the compute stream's NCCL queue, and the only host transfer of the sweep
+    is one D2H copy of the gathered (R, K) matrix into pinned memory.  With gloo (CPU tests) the same calls run
+    on host tensors."""
+
+    def __init__(self, n_replicas: int, K: int, group=None):
+        import torch.distributed as dist
+        self.R, self.K, self.group = n_replicas, K, group
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.world = dist.get_world_size(group) if self.dist else 1
+        self.rank = dist.get_rank(group) if self.dist else 0
+        self.bounds = [shard_bounds(n_replicas, self.world, r) for r in range(self.world)]
+        self.n_max = max(hi - lo for lo, hi in self.bounds)
+        self.send = self.recv = self.host = None
+
+    def _buffers(self, like: torch.Tensor):
+        backend_dev = like.device
+        if self.dist is not None and self.dist.get_backend(self.group) != "nccl":
+            backend_dev = torch.device("cpu")
+        if self.send is None or self.send.device != backend_dev:
+            self.send = torch.zeros((self.n_max, self.K), dtype=torch.float64, device=backend_dev)
+            self.recv = torch.empty((self.world * self.n_max, self.K), dtype=torch.float64, device=backend_dev)
+            self.host = torch.empty((self.world * self.n_max, self.K), dtype=torch.float64,
+                                    pin_memory=torch.cuda.is_available())
+        return backend_dev
+
+    def __call__(self, rows: torch.Tensor) -> np.ndarray:
+        dev = self._buffers(rows)
+        n_local = rows.shape[0]
+        if self.world == 1:
+            self.host[:n_local].copy_(rows, non_blocking=True)
+            if rows.is_cuda:
+                torch.cuda.current_stream(rows.device).synchronize()
+            return self.host[:n_local].numpy().copy()
+        self.send[:n_local].copy_(rows if rows.device == dev else rows.to(dev), non_blocking=True)
+        self.dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        self.host.copy_(self.recv, non_blocking=True)
+        if self.recv.is_cuda:
+            torch.cuda.current_stream(self.recv.device).synchronize()
+        flat = self.host.numpy().reshape(self.world, self.n_max, self.K)
+        out = np.empty((self.R, self.K), dtype=np.float64)
+        for r, (lo, hi) in enumerate(self.bounds):
+            out[lo:hi] = flat[r, :hi - lo]
+        return out
+
+
 def neighbor_swaps(u_rk: np.ndarray, replica_states: np.ndarray, iteration: int, seed: int,
                    n_accepted: Optional[np.ndarray] = None, n_proposed: Optional[np.ndarray] = None) -> np.ndarray:
     """One round of neighbour replica exchange.  State pairs (s, s+1) with s = iteration mod 2, +2, ...;
@@ -127,6 +175,7 @@ class MultiStateSampler:
         self.mcmc_iterations_per_sweep = mcmc_iterations_per_sweep
         self.use_batched_engine = True
         self._batched = None
+        self._row_gatherer = None
         self._rank, self._world = 0, 1
 
     # ---- properties (`multistate.py:86-176`) ----------------------------------------------------------
@@ -148,10 +197,22 @@ class MultiStateSampler:
 
     @property
     def sampler_states(self) -> Optional[List[SamplerState]]:
+        """Copies of the SamplerStates.  In a sharded run (world_size > 1) only the replicas in
+        `local_replica_range` are propagated by this rank; the positions of the others are fetched from their
+        owners here (velocities and PRNG keys of non-local replicas stay as created)."""
         if self._sampler_states is None:
             return None
         self._sync_from_engine()
-        return copy.deepcopy(self._sampler_states)
+        out = copy.deepcopy(self._sampler_states)
+        if self._world > 1:
+            lo, hi = self.local_replica_range
+            xyz = self._report_positions()["positions"]
+            dev = self._sampler_states[lo].positions.device if hi > lo else None
+            for r in range(self.number_of_replicas):
+                if not (lo <= r < hi):
+                    out[r].positions = unit.Quantity(torch.as_tensor(xyz[r], dtype=torch.float32, device=dev),
+                                                     unit.nanometer)
+        return out
 
     @property
     def is_periodic(self):
@@ -267,11 +328,14 @@ class MultiStateSampler:
         K = self.number_of_thermodynamic_states
         batched = self._batched_engine()
         if batched is not None:
-            rows = batched.reduced_potentials()
-        else:
-            rows = np.zeros((hi - lo, K))
-            for replica_id in range(lo, hi):
-                rows[replica_id - lo, :] = self._compute_replica_reduced_potential(replica_id)
+            # rows stay on the device until the gathered matrix comes back (one D2H per sweep)
+            if self._row_gatherer is None or (self._row_gatherer.R, self._row_gatherer.K) != (self.number_of_replicas, K):
+                self._row_gatherer = _RowGatherer(self.number_of_replicas, K)
+            self._energy_thermodynamic_states = self._row_gatherer(batched.reduced_potentials_device())
+            return
+        rows = np.zeros((hi - lo, K))
+        for replica_id in range(lo, hi):
+            rows[replica_id - lo, :] = self._compute_replica_reduced_potential(replica_id)
         self._energy_thermodynamic_states = gather_rows(rows, self.number_of_replicas)
 
     # ---- mixing (`multistate.py:447-495`) ------------------------------------------------------------------
@@ -339,19 +403,26 @@ class MultiStateSampler:
             self._compute_energies()
             self._report_iteration()
             self._update_analysis()
-        self._reporter.flush_buffer()
+        # every rank keeps the (identical) records in memory for the estimator; one rank owns the file
+        if self._rank == 0:
+            self._reporter.flush_buffer()
 
     # ---- reporting / analysis (`multistate.py:601-742`) ------------------------------------------------------
     def _report_energy_matrix(self):
         return {"u_kn": self._energy_thermodynamic_states.T}
 
     def _report_positions(self):
+        """(R, N, 3) positions of ALL replicas: every rank contributes the replicas it propagates
+        (one all-gather when the run is sharded)."""
         self._sync_from_engine()
         lo, hi = self.local_replica_range
-        n_atoms = self._sampler_states[lo].positions.shape[0]
+        n_atoms = self._sampler_states[0].positions.shape[0]
         xyz = np.zeros((self.number_of_replicas, n_atoms, 3))
         for replica_id in range(lo, hi):
             xyz[replica_id] = self._sampler_states[replica_id].positions.detach().cpu().numpy()
+        if self._world > 1:
+            flat = gather_rows(xyz[lo:hi].reshape(hi - lo, n_atoms * 3), self.number_of_replicas)
+            xyz = flat.reshape(self.number_of_replicas, n_atoms, 3)
         return {"positions": xyz}
 
     def _report(self, property: str):
@@ -512,17 +583,28 @@ class _BatchedLJReplicas:
             self.engine.run(self.nsteps, keys)
             self._dirty = True
 
-    def reduced_potentials(self) -> np.ndarray:
-        """(n_local, K): u_kl = beta_l (U_k + p_l V) from one batched energy kernel
-        (`states.py:302-325` evaluated for all states at once)."""
-        U = self.engine.energy().cpu().numpy()               # kJ/mol per local replica
+    def _betas(self):
         if self._beta_mol is None:
             ms = self.ms
             one = unit.Quantity(1.0, unit.kilojoule_per_mole) / unit.AVOGADRO_CONSTANT_NA
             self._beta_mol = np.array([float(ts.beta * one) for ts in ms._thermodynamic_states])
             self._beta_pv = np.array([float(ts.beta * (ts.pressure * (self.volume * unit.nanometer ** 3)))
                                       if ts.pressure is not None else 0.0 for ts in ms._thermodynamic_states])
-        return U[:, None] * self._beta_mol[None, :] + self._beta_pv[None, :]
+            dev = self.engine.device
+            self._beta_mol_dev = torch.from_numpy(self._beta_mol).to(dev)
+            self._beta_pv_dev = torch.from_numpy(self._beta_pv).to(dev)
+        return self._beta_mol, self._beta_pv
+
+    def reduced_potentials_device(self) -> torch.Tensor:
+        """(n_local, K) float64 on the device: u_kl = beta_l (U_k + p_l V) from one batched energy kernel
+        (`states.py:302-325` evaluated for all states at once); nothing touches the host."""
+        self._betas()
+        U = self.engine.energy()                               # kJ/mol per local replica, device
+        return torch.addcmul(self._beta_pv_dev[None, :], U[:, None], self._beta_mol_dev[None, :])
+
+    def reduced_potentials(self) -> np.ndarray:
+        """Host copy of `reduced_potentials_device`."""
+        return self.reduced_potentials_device().cpu().numpy()
 
     def set_states(self, new_states, velocity_scales: dict):
         kts = [self.kT_of_state[new_states[r]] for r in range(self.lo, self.hi)]

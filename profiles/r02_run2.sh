@@ -1,0 +1,7 @@
+python -c "import __graft_entry__ as g; g.build()"
+timeout 300 python profiles/r02_debug_persist.py 2>&1 | grep -v "^$" | tail -30 > gpurun_out/r2_debug1.log
+cat gpurun_out/r2_debug1.log
+( timeout 300 python profiles/tune_split.py; NREP=8 CELLS=16,16,32 timeout 300 python profiles/tune_split.py ) 2>&1 | grep -E "TUNE|rror" > gpurun_out/r2_tune2.log
+cat gpurun_out/r2_tune2.log
+STEPS=200 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_md_steps -s 12 -c 1 -o gpurun_out/r2_steps_v5a python profiles/tune_split.py > gpurun_out/r2_ncu1.log 2>&1
+tail -3 gpurun_out/r2_ncu1.log

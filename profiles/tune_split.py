@@ -46,13 +46,16 @@ def main():
     e0.record(); eng.force_only(100); e1.record(); torch.cuda.synchronize()
     t_force = e0.elapsed_time(e1) / 100 * 1e3
     best = 1e30
+    eng.step_timing(reset=True)
     for _ in range(3):
         e0.record(); keys, _ = eng.run(steps, keys); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / steps * 1e3)
     st = eng.stats()
-    print("TUNE nrep=%d n=%d split=%s chunk=%s skin=%s force_us=%.2f step_us=%.2f lane_util=%.3f rebuilds=%d" % (
-        R, n, os.environ.get("CHX_FORCE_SPLIT", "auto"), os.environ.get("CHX_MD_CHUNK", "-"),
-        os.environ.get("CHX_MD_SKIN", "-"), t_force, best, st["lane_utilisation"], st["table_rebuilds"]))
+    kms, ksteps = eng.step_timing()
+    print("TUNE nrep=%d n=%d persist=%s chunk=%s skin=%s force_us=%.2f step_us=%.2f kernel_us_per_step=%.2f lane_util=%.3f rebuilds=%d" % (
+        R, n, os.environ.get("CHX_MD_PERSIST", "1"), os.environ.get("CHX_MD_CHUNK", "-"),
+        os.environ.get("CHX_MD_SKIN", "-"), t_force, best, kms / max(ksteps, 1) * 1e3, st["lane_utilisation"],
+        st["table_rebuilds"]))
 
 
 if __name__ == "__main__":
