@@ -4,7 +4,8 @@ the cell-list neighbour build (BASELINE.json config 4).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--inner S] [--impl ours|reference]
 
-A bench "step" is one `LangevinIntegrator.run`-sized chunk of S = --inner BAOAB steps (default 100);
+A bench "step" is one `LangevinIntegrator.run`-sized chunk of S = --inner BAOAB steps (default 1000, the
+call Examples/LJ_langevin.py makes);
 `value` is BAOAB steps/s summed over all ranks (one independent system per GPU: the single-system
 path does not shard, SURVEY.md section 8e -> weak scaling, "replicas only").
   value  device-resident: state stays in HBM, K chunks timed with CUDA events on the launch stream
@@ -33,9 +34,32 @@ SIGMA, EPS_KCAL, RC, SKIN = 0.34, 0.238, 1.02, 0.5
 EPS = EPS_KCAL * 4.184
 MASS, TEMP_K, DT_PS, GAMMA = 39.948, 300.0, 0.001, 1.0
 N_SIDE, RHO_STAR = 64, 0.8
-# dram bytes of one step-kernel launch inside the step loop (ncu, profiles/r01_step_kernel_ncu.md)
-NCU_STEP_KERNEL_DRAM_BYTES = 73.0e6
+# dram bytes of one step-kernel launch: read at bench time from the committed ncu export of the same kernel
+NCU_STEP_KERNEL_CSV = os.path.join(ROOT, "profiles", "r02_step_kernel_raw.csv")
+
+
+def ncu_step_kernel_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of k_md_force<UPDATE> from the committed
+    `ncu --set full --clock-control none --cache-control none` export (warm L2: the launch sits inside the step
+    loop, tables and state L2 resident); None if the file is missing."""
+    import csv
+    try:
+        tot, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        with open(NCU_STEP_KERNEL_CSV) as fh:
+            for row in csv.DictReader(fh):
+                if row["metric"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(row["value"]) * unit_scale.get(row["unit"], 1.0)
+        return tot or None
+    except Exception:
+        return None
 WORKLOAD = "LJ argon fluid N=262144 rho*=0.8 rc=3sigma skin=0.5nm T=300K dt=1fs Langevin BAOAB, cell-list build"
+
+
+def bench_config(n_side):
+    """`config` of the JSON line: the workload only, identical in both arms (--impl ours / reference)."""
+    n = n_side ** 3
+    return {"workload": WORKLOAD if n_side == N_SIDE else WORKLOAD.replace("262144", str(n)), "n_particles": n,
+            "parallelism": "1 independent system per GPU (replicas only)"}
 
 
 def parse_args():
@@ -43,7 +67,8 @@ def parse_args():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
-    p.add_argument("--inner", type=int, default=100, help="BAOAB steps per bench step")
+    p.add_argument("--inner", type=int, default=1000,
+                   help="BAOAB steps per bench step = per LangevinIntegrator.run call (Examples/LJ_langevin.py runs 1000)")
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--n-side", type=int, default=N_SIDE)
     p.add_argument("--internal-skin", type=float, default=None)
@@ -66,48 +91,63 @@ def make_system(n_side, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed region: NVML in-process (initialised before the
+    region starts, one sample every 10 ms), `nvidia-smi` as a fallback."""
+
+    _Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.stop, self.index = [], threading.Event(), index
         self.thread = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        # NVML in-process (a sample every 10 ms: the default timed region is ~150 ms); nvidia-smi as a fallback
+        self.nvml = None
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            # torchrun / CUDA_VISIBLE_DEVICES: NVML counts physical devices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
-                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
-                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
-                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
-            while not self.stop.is_set():
-                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                try:
-                    power = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
-                except Exception:
-                    power = float("nan")
-                reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append([str(sm), str(mx), str(power)] +
-                                 ["Active" if reasons & bits[k] else "Not Active"
-                                  for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
-                self.stop.wait(0.01)
-            return
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml = (pynvml, h, mx)
         except Exception:
-            pass
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+            self.nvml = None
+
+    def _nvml_sample(self):
+        pynvml, h, mx = self.nvml
+        bits = (pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap)
+        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        try:
+            power = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            power = float("nan")
+        reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.rows.append([str(sm), str(mx), str(power)] + ["Active" if reasons & b else "Not Active" for b in bits])
+
+    def _smi_sample(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self._Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout
+        row = [c.strip() for c in out.strip().split(",")]
+        if len(row) >= 7:
+            self.rows.append(row)
+
+    def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nvml is not None:
+                    self._nvml_sample()
+                else:
+                    self._smi_sample()
             except Exception:
-                pass
-            self.stop.wait(0.2)
+                self.nvml = None
+            self.stop.wait(0.01 if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.thread.start()
@@ -115,7 +155,14 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self.stop.set()
-        self.thread.join(timeout=6)
+        self.thread.join(timeout=12)
+        if not self.rows:      # nothing during the region: one sample right behind it is better than none
+            for fn in (self._nvml_sample if self.nvml is not None else None, self._smi_sample):
+                try:
+                    if fn is not None and not self.rows:
+                        fn()
+                except Exception:
+                    pass
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -141,44 +188,79 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU baseline: the C/OpenMP restatement of the reference algorithm (oracle/c) on a bounded sample
+# CPU baseline / reference arm: the C/OpenMP restatement of the reference algorithm (oracle/c), all host threads
 # ---------------------------------------------------------------------------------------------------
-REF_REBUILD_INTERVAL = 200.0   # steps between reference rebuild events (`check()` true) at this state point,
-                               # measured by the engine's exact tracker (bench line: reference_rebuild_interval_steps)
+REF_STEPS_PER_BENCH_STEP = 20      # full-size BAOAB steps per bench step of the reference arm
+REF_INTERVAL_PROBE_STEPS = 450     # trajectory length on which the reference arm measures its own rebuild interval
 
 
-def cpu_reference_steps_per_s(x, box, v0, rebuild_interval=REF_REBUILD_INTERVAL, build_stride=24, n_steps=6):
-    """The reference algorithm on the host cores, all threads: per-step cost = `calculate` over the padded
-    (N, M) list + masked LJ energy + the autodiff-equivalent force + BAOAB with in-stream threefry noise +
-    `check` (measured on FULL-size steps as the difference between an (n_steps+2)-step and a 2-step run),
-    plus the O(N^2) build (measured on every `build_stride`-th row of the full system and scaled by the
-    number of pair tests) amortised over the rebuild interval.  The list the timed steps run on is
-    built with the oracle's cell-grid accelerator (not timed: it is not part of the reference)."""
+def cpu_probe_rebuild_interval(x, box, v0, nsteps=REF_INTERVAL_PROBE_STEPS):
+    """Rebuild interval of the REFERENCE list (check(): any particle skin/2 from its reference position,
+    neighbors.py:864-907) on a trajectory of `nsteps` full-size steps of the C port, started from the bench's
+    initial state.  The rebuilds of the probe use the oracle's cell-grid accelerator and are not timed."""
+    from oracle import cport
+    n = x.shape[0]
+    cport.set_build_mode(1)
+    try:
+        xo, vo, key, st = cport.langevin_lj(x, v0, np.full(n, MASS, np.float32), box, SIGMA, EPS, RC, SKIN, 400,
+                                            8.314462618e-3 * TEMP_K, DT_PS, GAMMA, np.array([0, 1234], np.uint32), nsteps)
+    finally:
+        cport.set_build_mode(0)
+    events = int(st["n_builds"]) - 1
+    return (nsteps / events if events > 0 else None), events, (xo, vo, key)
+
+
+def cpu_reference_bench_steps(x, box, v0, k_steps, warmup, interval, n_s=REF_STEPS_PER_BENCH_STEP, state=None):
+    """K bench steps of the reference algorithm on the host cores.  One bench step is executed, not modelled:
+      * `n_s` full-size BAOAB steps of a running trajectory over the padded (N, M) reference list (calculate +
+        masked LJ energy + the autodiff-equivalent force + BAOAB with in-stream threefry noise + check), timed as
+        the difference between an (n_s + 2)-step and a 2-step call from the same state (so the force evaluation
+        that opens a call and the untimed set-up build cancel);
+      * the rows i = k (mod stride) of the reference's O(N^2) list build on the current positions, stride =
+        round(interval / n_s): over `stride` bench steps every row of one complete build has been executed, at the
+        rate at which the reference rebuilds (every `interval` steps).
+    Returns (BAOAB steps/s, detail)."""
     from oracle import cport
     cport.use_all_cores()
     n = x.shape[0]
     kT = 8.314462618e-3 * TEMP_K
     mass = np.full(n, MASS, np.float32)
-    key = np.array([0, 1234], np.uint32)
-    cport.set_build_mode(1)
-    try:
-        _, _, _, st_a = cport.langevin_lj(x, v0, mass, box, SIGMA, EPS, RC, SKIN, 400, kT, DT_PS, GAMMA, key, 2)
-        _, _, _, st_b = cport.langevin_lj(x, v0, mass, box, SIGMA, EPS, RC, SKIN, 400, kT, DT_PS, GAMMA, key, 2 + n_steps)
-    finally:
-        cport.set_build_mode(0)
-    t_step = max(1e-9, (st_b["t_steps_s"] - st_a["t_steps_s"]) / n_steps)
-    t_rows, tests = cport.time_reference_build_rows(x, box, np.float32(RC + SKIN), build_stride)
-    t_build = t_rows * (n * (n - 1) / 2.0) / max(1, tests)
-    per_step = t_step + t_build / rebuild_interval
-    detail = {"t_step_s": t_step, "t_build_s": t_build, "build_rows_timed_s": t_rows, "build_row_stride": build_stride,
-              "full_size_steps_timed": n_steps, "rebuild_interval_steps": rebuild_interval,
-              "n_max_neighbors": int(st_b["M"]), "p_cand": int(st_b["p_cand"]), "threads": cport.num_threads()}
-    return 1.0 / per_step, detail
+    if state is None:
+        state = (x, v0, np.array([0, 1234], np.uint32))
+    xs, vs, key = state
+    stride = max(1, int(round(interval / n_s))) if interval else 0
+    times, t_steps, t_rows_l = [], [], []
+    M = 400
+    for k in range(warmup + k_steps):
+        cport.set_build_mode(1)
+        try:
+            _, _, _, st_a = cport.langevin_lj(xs, vs, mass, box, SIGMA, EPS, RC, SKIN, M, kT, DT_PS, GAMMA, key, 2)
+            xs2, vs2, key2, st_b = cport.langevin_lj(xs, vs, mass, box, SIGMA, EPS, RC, SKIN, M, kT, DT_PS, GAMMA, key, 2 + n_s)
+        finally:
+            cport.set_build_mode(0)
+        t_s = max(1e-9, st_b["t_steps_s"] - st_a["t_steps_s"])
+        t_r = 0.0
+        if stride:
+            t_r, _ = cport.time_reference_build_rows(xs2, box, np.float32(RC + SKIN), stride, row0=k % stride)
+        xs, vs, key = xs2, vs2, key2
+        M = int(st_b["M"])
+        if k >= warmup:
+            times.append(t_s + t_r); t_steps.append(t_s); t_rows_l.append(t_r)
+    total = float(np.sum(times))
+    detail = {"bench_steps_timed": k_steps, "baoab_steps_per_bench_step": n_s, "build_row_stride": stride,
+              "rebuild_interval_steps": interval, "t_steps_s_per_bench_step": float(np.mean(t_steps)),
+              "t_build_rows_s_per_bench_step": float(np.mean(t_rows_l)),
+              "t_full_build_s": float(np.mean(t_rows_l)) * stride if stride else None,
+              "full_builds_executed": (k_steps / stride) if stride else 0.0,
+              "n_max_neighbors": M, "p_cand": int(st_b["p_cand"]), "threads": cport.num_threads(), "extrapolated": False}
+    return k_steps * n_s / total, total / k_steps, detail, (xs, vs, key)
 
 
-CPU_SAMPLE = ("%d full-size BAOAB steps over the padded (N,M) reference list (calculate + masked LJ energy/force + "
-              "threefry noise + check) + every %d-th row of the O(N^2) build scaled by pair tests and amortised over "
-              "%g steps; C/OpenMP restatement of the reference algorithm (oracle/c), JAX not installable offline")
+CPU_SAMPLE = ("%d bench steps EXECUTED at full size (N=%d): each = %d BAOAB steps of a running trajectory over the padded "
+              "(N,M) reference list (calculate + masked LJ energy/force + threefry noise + check) + the rows i = k mod %d of "
+              "the reference's O(N^2) build (one complete build per %d bench steps = the measured rebuild interval of %s "
+              "steps); C/OpenMP restatement of the reference algorithm (oracle/c) on all host threads -- chiron's JAX path "
+              "cannot run this size (N x N mask) and jax is not installable offline")
 
 
 def run_reference(args):
@@ -188,22 +270,25 @@ def run_reference(args):
     import __graft_entry__ as ge
     ge.build_oracle()
     from oracle import cport, jax_random as jr, dynamics as dyn
+    cport.use_all_cores()
     lj, x, box = make_system(args.n_side, seed=4)
-    v0 = dyn.maxwell_boltzmann(jr.PRNGKey(11), np.full(x.shape[0], MASS), TEMP_K)
-    vals, detail = [], None
-    reps = max(1, min(args.steps, 2))
-    for _ in range(reps):
-        v, detail = cpu_reference_steps_per_s(x, box, v0)
-        vals.append(v)
-    value = float(np.median(vals))
-    sample = CPU_SAMPLE % (detail["full_size_steps_timed"], detail["build_row_stride"], detail["rebuild_interval_steps"])
+    n = x.shape[0]
+    v0 = dyn.maxwell_boltzmann(jr.PRNGKey(11), np.full(n, MASS), TEMP_K)
+    t0 = time.perf_counter()
+    interval, events, state = cpu_probe_rebuild_interval(x, box, v0)
+    t_probe = time.perf_counter() - t0
+    value, t_bench_step, detail, _ = cpu_reference_bench_steps(x, box, v0, args.steps, args.warmup, interval, state=state)
+    detail.update(interval_probe_steps=REF_INTERVAL_PROBE_STEPS, interval_probe_events=events, interval_probe_wall_s=t_probe)
+    sample = CPU_SAMPLE % (args.steps, n, detail["baoab_steps_per_bench_step"], max(1, detail["build_row_stride"]),
+                           max(1, detail["build_row_stride"]), ("%.0f" % interval) if interval else "no event in the probe: never")
     line = {
         "impl": "reference", "metric": "LJ Langevin steps/s at N=262144", "value": value, "unit": "steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.inner / value,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_bench_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "baoab_steps_per_bench_step": args.inner,
-                   "note": "reference ALGORITHM restated in C/OpenMP on the host cores (chiron's JAX code cannot be "
-                           "installed offline: jax, openmm, openmmtools absent); %d repetitions of the bounded sample" % reps},
+        "config": bench_config(args.n_side),
+        "bench_step": {"baoab_steps": detail["baoab_steps_per_bench_step"],
+                       "note": "reference ALGORITHM restated in C/OpenMP on the host cores; a bench step is a bounded, "
+                               "fully executed sample (see cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": detail["threads"], "kind": "port",
                          "sample": sample, **detail},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -215,7 +300,8 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # replica exchange: BASELINE.json config 5 (64 temperatures x LJ N=8192), replicas sharded over the ranks
 # ---------------------------------------------------------------------------------------------------
-def bench_remd(dev, rank, world, sweeps=20, warmup=3, n_replicas=64, steps_per_sweep=100):
+def bench_remd(dev, rank, world, sweeps=20, warmup=3, n_replicas=64, steps_per_sweep=100, cpu_baseline=False):
+    import hashlib
     import torch
     import torch.distributed as dist
     from chiron_b200 import unit
@@ -227,13 +313,15 @@ def bench_remd(dev, rank, world, sweeps=20, warmup=3, n_replicas=64, steps_per_s
     from chiron_b200.states import SamplerState, ThermodynamicState
     from chiron_b200.testsystems import LennardJonesFluid
     from chiron_b200 import random as crandom
-    lj = LennardJonesFluid(cells=(16, 16, 32), reduced_density=RHO_STAR, sigma=SIGMA * unit.nanometer,
-                           epsilon=EPS_KCAL * unit.kilocalories_per_mole, seed=5)
+    # replica k starts from its own jittered lattice (seed 5 + k)
+    ljs = [LennardJonesFluid(cells=(16, 16, 32), reduced_density=RHO_STAR, sigma=SIGMA * unit.nanometer,
+                             epsilon=EPS_KCAL * unit.kilocalories_per_mole, seed=5 + k) for k in range(n_replicas)]
+    lj = ljs[0]
     potential = LJPotential(lj.topology, lj.sigma, lj.epsilon, RC * unit.nanometer)
     temps = [TEMP_K * 2.0 ** (k / (n_replicas - 1.0)) for k in range(n_replicas)]
     thermo = [ThermodynamicState(potential, temperature=t * unit.kelvin) for t in temps]
     keys = crandom.split(crandom.PRNGKey(99), n_replicas)
-    states = [SamplerState(lj.positions, keys[k], box_vectors=lj.box_vectors) for k in range(n_replicas)]
+    states = [SamplerState(ljs[k].positions, keys[k], box_vectors=lj.box_vectors) for k in range(n_replicas)]
     nbrs = [NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=RC * unit.nanometer, skin=SKIN * unit.nanometer,
                               n_max_neighbors=400, builder="cell") for _ in range(n_replicas)]
     move = LangevinDynamicsMove(timestep=DT_PS * unit.picosecond, collision_rate=GAMMA / unit.picosecond,
@@ -248,6 +336,11 @@ def bench_remd(dev, rank, world, sweeps=20, warmup=3, n_replicas=64, steps_per_s
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    ms.reset_phase_timers()
+    eng = ms._batched.engine if ms._batched else None
+    if eng is not None:
+        eng.step_timing(reset=True)
+        st0 = eng.stats()
     t0 = time.perf_counter()
     ms.run(warmup + sweeps)
     torch.cuda.synchronize()
@@ -260,12 +353,59 @@ def bench_remd(dev, rank, world, sweeps=20, warmup=3, n_replicas=64, steps_per_s
     dt = float(t.item())
     acc, prop = int(ms._n_accepted_matrix.sum()), int(ms._n_proposed_matrix.sum())
     batched = bool(ms._batched)
-    return {"sweeps_per_s": sweeps / dt, "ms_per_sweep": 1e3 * dt / sweeps, "replicas": n_replicas,
-            "particles_per_replica": lj.n_particles, "baoab_steps_per_sweep": steps_per_sweep,
-            "replica_steps_per_s": sweeps * n_replicas * steps_per_sweep / dt,
-            "exchange": "even/odd neighbour swaps, one all_gather of the 64x64 reduced-potential matrix per sweep",
-            "last_sweep_swaps_accepted": acc, "last_sweep_swaps_proposed": prop, "batched_engine": batched,
-            "sweeps": sweeps, "api": "MultiStateSampler.run"}
+    # per-phase breakdown of a sweep on this rank (host wall time; every phase ends with a host read)
+    ph = ms.phase_seconds
+    per = 1e3 / max(1, ph["sweeps"])
+    phases = {"mix_ms": ph["mix"] * per, "propagate_ms": ph["propagate"] * per,
+              "energies_and_exchange_ms": ph["energies_and_exchange"] * per,
+              "report_ms": ph["report_and_analysis"] * per}
+    if eng is not None:
+        kms, ksteps = eng.step_timing()
+        st1 = eng.stats()
+        phases["step_kernels_ms"] = (kms / ksteps * steps_per_sweep) if ksteps else None
+        phases["table_builds_per_sweep"] = (st1["table_rebuilds"] - st0["table_rebuilds"]) / max(1, sweeps)
+        if phases["step_kernels_ms"] is not None:
+            phases["builds_and_host_in_propagate_ms"] = phases["propagate_ms"] - phases["step_kernels_ms"]
+        phases["local_replicas"] = eng.R
+    # fixed-seed fingerprint: state indices after the run (swap decisions are taken identically on every rank from a
+    # shared counter key) and the energy matrix rounded to 1e-6 relative (a replica's trajectory does not depend on
+    # the rank that runs it beyond fp32 summation order): compare the fingerprints of runs at different N
+    u = np.asarray(ms._energy_thermodynamic_states, dtype=np.float64)
+    fp_states = hashlib.sha1(np.asarray(ms._replica_thermodynamic_states, dtype=np.int64).tobytes()).hexdigest()[:12]
+    out = {"sweeps_per_s": sweeps / dt, "ms_per_sweep": 1e3 * dt / sweeps, "replicas": n_replicas,
+           "particles_per_replica": lj.n_particles, "baoab_steps_per_sweep": steps_per_sweep,
+           "replica_steps_per_s": sweeps * n_replicas * steps_per_sweep / dt,
+           "exchange": "even/odd neighbour swaps; rows of the reduced-potential matrix stay on the device, one NCCL "
+                       "all_gather_into_tensor + one D2H copy of the 64x64 matrix per sweep",
+           "last_sweep_swaps_accepted": acc, "last_sweep_swaps_proposed": prop, "batched_engine": batched,
+           "sweeps": sweeps, "api": "MultiStateSampler.run", "phases_rank0": phases,
+           "fingerprint": {"state_indices_sha1": fp_states, "state_indices": [int(v) for v in ms._replica_thermodynamic_states],
+                           "u_diag_sum": float(np.trace(u)), "u_sum": float(u.sum())}}
+    if cpu_baseline and rank == 0:
+        # the reference algorithm (C/OpenMP port, all host threads): 2 replicas x one sweep, scaled to 64 replicas
+        try:
+            from oracle import cport, dynamics as dyn, jax_random as jr
+            cport.use_all_cores()
+            x = np.asarray(lj.positions.value_in_unit(unit.nanometer), dtype=np.float32)
+            box = np.asarray(lj.box_vectors.value_in_unit(unit.nanometer), dtype=np.float32)
+            n = x.shape[0]
+            v0 = dyn.maxwell_boltzmann(jr.PRNGKey(11), np.full(n, MASS), TEMP_K)
+            tt = []
+            for rep in range(2):
+                tc = time.perf_counter()
+                cport.langevin_lj(x, v0, np.full(n, MASS, np.float32), box, SIGMA, EPS, RC, SKIN, 400,
+                                  8.314462618e-3 * temps[rep * (n_replicas - 1)], DT_PS, GAMMA,
+                                  np.array([0, 99 + rep], np.uint32), steps_per_sweep)
+                tt.append(time.perf_counter() - tc)
+            t_sweep = float(np.mean(tt)) * n_replicas
+            out["cpu_baseline"] = {"value": 1.0 / t_sweep, "unit": "sweeps/s", "cores": cport.num_threads(), "kind": "port",
+                                   "sample": "2 replicas (coldest, hottest) x %d full BAOAB steps incl. the reference O(N^2) "
+                                             "list builds at N=%d, scaled to %d replicas run one after the other (the "
+                                             "reference propagates replicas serially, multistate.py:497-510); energy matrix "
+                                             "and swaps not included" % (steps_per_sweep, n, n_replicas)}
+        except Exception as exc:
+            out["cpu_baseline"] = {"error": repr(exc)}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -372,7 +512,7 @@ def run_ours(args):
     if step_kernel_launches:
         step_kernel_ms = step_kernel_ms_total / step_kernel_launches
     else:
-        # fewer than one 32-step chunk per call (--inner < 32): no graph replay was timed; the whole-step
+        # fewer than one chunk per call (--inner < 8): no graph replay was timed; the whole-step
         # time is an upper bound of the kernel's duration
         step_kernel_ms = ms_max / (K * S)
     achieved_tflops = step_flops / (step_kernel_ms * 1e-3) / 1e12
@@ -437,7 +577,7 @@ def run_ours(args):
         del eng
         torch.cuda.empty_cache()
         try:
-            remd = bench_remd(dev, rank, world, sweeps=args.remd_sweeps)
+            remd = bench_remd(dev, rank, world, sweeps=args.remd_sweeps, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
         except Exception as exc:   # the headline number must survive a failure of the secondary workload
             remd = {"error": repr(exc)}
 
@@ -447,7 +587,7 @@ def run_ours(args):
         try:
             sys.path.insert(0, os.path.join(ROOT, "profiles"))
             import bench_mc
-            mc = bench_mc.main(32, quiet=True)
+            mc = bench_mc.main(32, quiet=True, cpu_baselines=not args.no_cpu_baseline)
         except Exception as exc:
             mc = {"error": repr(exc)}
 
@@ -458,10 +598,16 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import __graft_entry__ as ge
         ge.build_oracle()
-        v, detail = cpu_reference_steps_per_s(x, box, v0, rebuild_interval=ref_interval or REF_REBUILD_INTERVAL)
+        # bounded sample (~15 s): 4 executed bench steps of the reference arm; the rebuild interval is the one the
+        # engine's exact tracker of the reference condition measured in the timed region above
+        from oracle import cport
+        cport.use_all_cores()
+        v, _, detail, _ = cpu_reference_bench_steps(x, box, v0, 4, 1, ref_interval)
         cpu = {"value": v, "unit": "steps/s", "cores": detail["threads"], "kind": "port",
-               "sample": CPU_SAMPLE % (detail["full_size_steps_timed"], detail["build_row_stride"],
-                                       detail["rebuild_interval_steps"]), **detail}
+               "sample": CPU_SAMPLE % (4, n, detail["baoab_steps_per_bench_step"], max(1, detail["build_row_stride"]),
+                                       max(1, detail["build_row_stride"]),
+                                       ("%.0f" % ref_interval) if ref_interval else "no event in the timed region: never"),
+               **detail}
 
     if rank == 0:
         rebuilds = st1["table_rebuilds"] - st0["table_rebuilds"]
@@ -469,12 +615,12 @@ def run_ours(args):
             "metric": "LJ Langevin steps/s at N=262144", "value": steps_per_s, "unit": "steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.n_side == N_SIDE else WORKLOAD.replace("262144", str(n)),
-                       "baoab_steps_per_bench_step": S, "n_particles": n,
-                       "parallelism": "1 independent system per GPU (replicas only)",
-                       "l2": "working set (tiles %.0f MB + state) exceeds nothing to flush: inputs are produced by the previous step"
-                             % (st_e["blocks"] * st_e["tile_capacity"] * 256 / 1e6),
-                       "internal_skin_nm": args.internal_skin or round(0.35 * SIGMA, 4)},
+            "config": bench_config(args.n_side),
+            "bench_step": {"baoab_steps": S,
+                           "l2": "no flush between steps: the inputs of a step are produced by the previous one; tables "
+                                 "(%.0f MB) + state are L2 resident inside the loop, which is the steady state of this workload"
+                                 % (st_e["blocks"] * st_e["tile_capacity"] * st_e["tile_bytes"] / 1e6),
+                           "internal_skin_nm": args.internal_skin or round(0.35 * SIGMA, 4)},
             "pair_interactions_per_s": p_int * steps_per_s / world * world,
             "pair_tests_per_s": p_cand * steps_per_s,
             "p_cand": p_cand, "p_int": p_int, "p_cand_internal_tables": p_cand_internal, "potential_energy_kj_mol": e_now,
@@ -491,8 +637,8 @@ def run_ours(args):
                          "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no fp32 figure)",
                          "ffma2_chain_tflops": fp32x2_peak_tflops, "flops_per_launch": step_flops,
                          "kernel_ms": step_kernel_ms, "kernel_launches_timed": int(step_kernel_launches),
-                         "traffic": NCU_STEP_KERNEL_DRAM_BYTES,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch inside the step loop (--cache-control none; tables and state are L2 resident), profiles/r01_step_kernel_ncu.md",
+                         "traffic": ncu_step_kernel_traffic(),
+                         "traffic_source": "profiles/r02_step_kernel_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full --clock-control none --cache-control none (WARM L2: launch 400 of the step loop; tables and state are L2 resident there; a cold-L2 launch reads 70 MB, profiles/r01_step_kernel_ncu.md)",
                          "pair_loop_only": {"kernel": "k_md_force (no update)", "kernel_ms": force_ms, "flops_per_launch": pair_flops,
                                             "achieved": pair_loop_tflops, "frac": pair_loop_tflops / fp32_peak_tflops},
                          "step_flops": step_flops,

@@ -23,6 +23,7 @@ _I = C.c_int
 _L = C.c_longlong
 _F = C.c_float
 _U = C.c_uint32
+_D = C.c_double
 
 
 class ChironB200Error(RuntimeError):
@@ -51,6 +52,7 @@ SIGNATURES = {
     "chx_lj_subset_delta_energy": [_P, _P, _P, _I, _P, _I, _F, _F, _F, _I, _F, _F, _F, _P],
     "chx_threefry_split_host": [C.POINTER(_U), C.POINTER(_U)],
     "chx_random_bits_host": [C.POINTER(_U), _L, C.POINTER(_U)],
+    "chx_threefry_split_host_n": [C.POINTER(_U), _I, C.POINTER(_U)],
     "chx_random_normal": [_P, _U, _U, _L, _P],
     "chx_random_uniform": [_P, _U, _U, _L, _F, _F, _P],
     "chx_baoab_update": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _U, _U, _I, _F, _F, _F, _I, _P, _F, _P],
@@ -60,6 +62,15 @@ SIGNATURES = {
     "chx_scale": [_P, _P, _L, _F, _P],
     "chx_mc_displace_run": [_P, _P, _P, _P, _P, _P, _I],
     "chx_mc_barostat_run": [_P, _P, _P, _P, _P, _P, _I],
+    # x64 variants
+    "chx_displacement_f64": [_P, _P, _P, _L, _D, _D, _D, _I, _P, _P],
+    "chx_wrap_f64": [_P, _P, _L, _D, _D, _D, _P],
+    "chx_nlist_build_nsq_f64": [_P, _P, _I, _D, _D, _D, _I, _D, _I, _P, _P, _P, C.POINTER(_I), C.POINTER(_I)],
+    "chx_nlist_calculate_f64": [_P, _P, _I, _D, _D, _D, _I, _D, _I, _P, _P, _P, _P, _P, _P],
+    "chx_nlist_check_f64": [_P, _P, _P, _I, _D, _D, _D, _I, _D, _P],
+    "chx_lj_nlist_energy_force_f64": [_P, _P, _I, _D, _D, _D, _I, _D, _D, _D, _I, _P, _P, _P, _P],
+    "chx_baoab_update_f64": [_P, _P, _P, _P, _P, _P, _I, _D, _D, _D, _D, _D, _D, _D, _I],
+    "chx_kick_f64": [_P, _P, _P, _P, _I, _D],
 }
 
 
@@ -211,6 +222,16 @@ def split_host(key):
     out = (_U * 4)()
     check(lib.chx_threefry_split_host(k, out))
     return (np.array([out[0], out[1]], dtype=np.uint32), np.array([out[2], out[3]], dtype=np.uint32))
+
+
+def split_host_n(keys):
+    """(n,2) uint32 keys -> (n,4) uint32: [carried key, subkey] of random.split for every row."""
+    lib = load_library()
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    out = np.empty((keys.shape[0], 4), dtype=np.uint32)
+    check(lib.chx_threefry_split_host_n(keys.ctypes.data_as(C.POINTER(_U)), keys.shape[0],
+                                        out.ctypes.data_as(C.POINTER(_U))))
+    return out
 
 
 def random_bits_host(key, n):

@@ -169,6 +169,14 @@ int chx_threefry_split_host(const uint32_t key_host[2], uint32_t out_host[4]) {
     return CHX_OK;
 }
 
+int chx_threefry_split_host_n(const uint32_t* keys_host, int n, uint32_t* out_host) {
+    CHX_REQUIRE(keys_host && out_host && n >= 0, "bad argument");
+    for (int k = 0; k < n; ++k)
+        threefry_split(keys_host[2 * k], keys_host[2 * k + 1], out_host[4 * k], out_host[4 * k + 1], out_host[4 * k + 2],
+                       out_host[4 * k + 3]);
+    return CHX_OK;
+}
+
 int chx_random_bits_host(const uint32_t key_host[2], long long n, uint32_t* out_host) {
     CHX_REQUIRE(key_host && out_host && n >= 0, "bad argument");
     for (long long e = 0; e < n; ++e)

@@ -1961,9 +1961,11 @@ static int md_force_split(const chx_ljmd* md) {
     if (env == 1 || env == 2 || env == 4) return env;
     const long long warps = (long long)md->g.nblk * md->R;
     const long long slots = 32LL * md->ctx->sm_count;       // resident warps at the kernel's register count
-    // measured on B200 (profiles/r01_split_tune.log): splitting costs 7-15 % once every SM is full
-    // (N = 262,144: 46.1 / 49.4 / 53.2 us for 1 / 2 / 4) and gains 14 % on 8 x 8,192 particles
-    return warps >= slots ? 1 : 4;
+    // measured on B200 (profiles/r01_split_tune.log, gpurun r02 tune9): splitting costs 7-15 % once every SM
+    // is full (N = 262,144: 46.1 / 49.4 / 53.2 us for 1 / 2 / 4) and gains 14 % on 8 x 8,192 particles, where
+    // 2 warps per block (86 % of the warp slots, one wave) beat 4 (1.73 waves): 22.1 vs 22.8 us per step
+    if (warps >= slots) return 1;
+    return 5 * 2 * warps >= 4 * slots ? 2 : 4;
 }
 
 static MdStepConst md_step_const(const chx_ljmd* md) {

@@ -126,23 +126,24 @@ def neighbor_swaps(u_rk: np.ndarray, replica_states: np.ndarray, iteration: int,
     K = u_rk.shape[1]
     replica_at = np.empty(K, dtype=int)
     replica_at[states] = np.arange(states.size)
-    pairs = list(range(int(iteration) % 2, K - 1, 2))
-    if not pairs:
+    s = np.arange(int(iteration) % 2, K - 1, 2)
+    if s.size == 0:
         return states
     key = random.PRNGKey((int(seed) << 32) ^ int(iteration))
-    u01 = random.uniform_host_n(key, len(pairs))
-    for p, s in enumerate(pairs):
-        i, j = replica_at[s], replica_at[s + 1]
-        log_p = -(u_rk[i, s + 1] + u_rk[j, s]) + u_rk[i, s] + u_rk[j, s + 1]
-        accept = bool(log_p >= 0.0 or u01[p] < np.exp(log_p))
-        if n_proposed is not None:
-            n_proposed[s, s + 1] += 1
-            n_proposed[s + 1, s] += 1
-        if accept:
-            states[i], states[j] = s + 1, s
-            if n_accepted is not None:
-                n_accepted[s, s + 1] += 1
-                n_accepted[s + 1, s] += 1
+    u01 = random.uniform_host_n(key, s.size)
+    # the pairs of one round are disjoint, so all decisions are taken at once
+    i, j = replica_at[s], replica_at[s + 1]
+    log_p = -(u_rk[i, s + 1] + u_rk[j, s]) + u_rk[i, s] + u_rk[j, s + 1]
+    with np.errstate(over="ignore"):
+        accept = (log_p >= 0.0) | (u01 < np.exp(log_p))
+    if n_proposed is not None:
+        n_proposed[s, s + 1] += 1
+        n_proposed[s + 1, s] += 1
+    sa = s[accept]
+    states[i[accept]], states[j[accept]] = sa + 1, sa
+    if n_accepted is not None:
+        n_accepted[sa, sa + 1] += 1
+        n_accepted[sa + 1, sa] += 1
     return states
 
 
@@ -177,6 +178,14 @@ class MultiStateSampler:
         self._batched = None
         self._row_gatherer = None
         self._rank, self._world = 0, 1
+        # host wall time per phase of `run`, summed over sweeps (the phases end with a host read, so device time
+        # is included); reset with `reset_phase_timers()`
+        self.phase_seconds = {"mix": 0.0, "propagate": 0.0, "energies_and_exchange": 0.0, "report_and_analysis": 0.0,
+                              "sweeps": 0}
+
+    def reset_phase_timers(self):
+        for k in self.phase_seconds:
+            self.phase_seconds[k] = 0 if k == "sweeps" else 0.0
 
     # ---- properties (`multistate.py:86-176`) ----------------------------------------------------------
     @property
@@ -395,14 +404,23 @@ class MultiStateSampler:
         if self._iteration == 0:
             self._compute_energies()
             self._report_iteration()
+        import time
+        ph = self.phase_seconds
         while not self._is_completed(n_iterations):
             self._iteration += 1
             log.info(f"Iteration {self._iteration}/{n_iterations}")
+            t0 = time.perf_counter()
             self._mix_replicas()
-            self._propagate_replicas()
-            self._compute_energies()
+            t1 = time.perf_counter()
+            self._propagate_replicas()          # ends with a host read of the loop keys: device time included
+            t2 = time.perf_counter()
+            self._compute_energies()            # ends with the D2H copy of the gathered matrix
+            t3 = time.perf_counter()
             self._report_iteration()
             self._update_analysis()
+            t4 = time.perf_counter()
+            ph["mix"] += t1 - t0; ph["propagate"] += t2 - t1; ph["energies_and_exchange"] += t3 - t2
+            ph["report_and_analysis"] += t4 - t3; ph["sweeps"] += 1
         # every rank keeps the (identical) records in memory for the estimator; one rank owns the file
         if self._rank == 0:
             self._reporter.flush_buffer()
@@ -564,9 +582,12 @@ class _BatchedLJReplicas:
         from .utils import initialize_velocities
         ms = self.ms
         for _ in range(int(n_mcmc_iterations)):
-            keys = np.zeros((self.hi - self.lo, 2), dtype=np.uint32)
+            # SamplerState.new_PRNG_key of every local replica in one call (states.py:150-154)
+            cur = np.stack([np.asarray(ms._sampler_states[r]._current_PRNG_key, dtype=np.uint32)
+                            for r in range(self.lo, self.hi)])
+            carried, keys = random.split_many(cur)
             for r in range(self.lo, self.hi):
-                keys[r - self.lo] = ms._sampler_states[r].new_PRNG_key
+                ms._sampler_states[r]._current_PRNG_key = carried[r - self.lo]
             if self.refresh or any(self._missing_v):
                 x, v, _, _ = self.engine.get_state()
                 x = x.reshape(self.hi - self.lo, self.n, 3)

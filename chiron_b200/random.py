@@ -34,6 +34,13 @@ def split(key, num: int = 2):
     return np.stack([carried, sub])
 
 
+def split_many(keys):
+    """`random.split(key)` for n keys at once: (carried (n,2), subkeys (n,2)) -- one library call."""
+    keys = np.ascontiguousarray(np.asarray(keys, dtype=np.uint32).reshape(-1, 2))
+    out = _lib.split_host_n(keys)
+    return out[:, 0:2].copy(), out[:, 2:4].copy()
+
+
 def _numel(shape):
     n = 1
     for s in shape:

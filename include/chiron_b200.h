@@ -126,6 +126,8 @@ int chx_lj_subset_delta_energy(chx_ctx* ctx, const float* x_old, const float* x_
 /* ---- jax.random, legacy threefry stream -------------------------------------- */
 /* random.split(key, 2) on the host: out_host[0..1] = carried key, out_host[2..3] = subkey. */
 int chx_threefry_split_host(const uint32_t key_host[2], uint32_t out_host[4]);
+/* the same for n keys: keys_host (n,2) -> out_host (n,4) = [carried key, subkey] per row */
+int chx_threefry_split_host_n(const uint32_t* keys_host, int n, uint32_t* out_host);
 /* random_bits(key, n) on the host (small n: scalar uniforms for the Metropolis test, mcmc.py:544). */
 int chx_random_bits_host(const uint32_t key_host[2], long long n, uint32_t* out_host);
 /* random.normal(key, (n,)) / random.uniform(key, (n,), lo, hi), bit-compatible layout. */
@@ -322,6 +324,34 @@ int chx_ljmd_table_stats(chx_ljmd* md, long long* out4);
  * replay of a chunk of steps in which no replica stopped for a table rebuild (so every launch did its
  * full work): *total_ms_host over *steps_host launches since creation or the last reset. */
 int chx_ljmd_step_timing(chx_ljmd* md, double* total_ms_host, long long* steps_host, int reset);
+
+/* ---- x64 variants (the reference with jax_enable_x64: float64 positions, displacements, energies, forces) -------
+ * Same semantics, argument order and padding rules as the fp32 entry points they mirror, one IEEE float64 rounding
+ * per reference operation (BASELINE.json north_star: pair sets bit-exact, energies / forces within rel 1e-10).
+ *   chx_displacement_f64 / chx_wrap_f64      chiron/neighbors.py:45-112, 116-175
+ *   chx_nlist_build_nsq_f64                  chiron/neighbors.py:595-626, 671-729 (O(N^2) restatement)
+ *   chx_nlist_calculate_f64 / _check_f64     chiron/neighbors.py:773-787, 864-907
+ *   chx_lj_nlist_energy_force_f64            chiron/potential.py:193-300 over the masked half list; energy_dev
+ *                                            (1 double) and force_dev (N,3) are zeroed first, either may be NULL
+ *   chx_baoab_update_f64 / chx_kick_f64      chiron/integrators.py:181-189, 195 with the (N,3) noise handed in
+ *                                            (the float64 jax.random stream is not generated in-kernel) */
+int chx_displacement_f64(chx_ctx* ctx, const double* x1, const double* x2, long long n, double lx, double ly,
+                         double lz, int periodic, double* r_out, double* dist_out);
+int chx_wrap_f64(chx_ctx* ctx, const double* x, long long n, double lx, double ly, double lz, double* out);
+int chx_nlist_build_nsq_f64(chx_ctx* ctx, const double* x, int n, double lx, double ly, double lz, int periodic,
+                            double cutoff_plus_skin, int M, uint32_t* neighbor_list, int32_t* neighbor_mask,
+                            int32_t* n_neighbors, int* max_count_host, int* count_eq_M_host);
+int chx_nlist_calculate_f64(chx_ctx* ctx, const double* x, int n, double lx, double ly, double lz, int periodic,
+                            double cutoff, int M, const uint32_t* neighbor_list, const int32_t* neighbor_mask,
+                            int32_t* n_out, int32_t* mask_out, double* dist_out, double* rij_out);
+int chx_nlist_check_f64(chx_ctx* ctx, const double* x, const double* ref_x, int n, double lx, double ly, double lz,
+                        int periodic, double half_skin, int32_t* flag_dev);
+int chx_lj_nlist_energy_force_f64(chx_ctx* ctx, const double* x, int n, double lx, double ly, double lz, int periodic,
+                                  double sigma, double epsilon, double cutoff, int M, const uint32_t* neighbor_list,
+                                  const int32_t* neighbor_mask, double* energy_dev, double* force_dev);
+int chx_baoab_update_f64(chx_ctx* ctx, double* x, double* v, const double* F, const double* mass, const double* noise,
+                         int n, double half_dt, double a, double b, double kT, double lx, double ly, double lz, int wrap);
+int chx_kick_f64(chx_ctx* ctx, double* v, const double* F, const double* mass, int n, double half_dt);
 
 #ifdef __cplusplus
 }
