@@ -338,9 +338,18 @@ def bench_remd(dev, rank, world, sweeps=20, warmup=3, n_replicas=64, steps_per_s
         dist.barrier()
     ms.reset_phase_timers()
     eng = ms._batched.engine if ms._batched else None
+    run_wall = [0.0]
     if eng is not None:
         eng.step_timing(reset=True)
         st0 = eng.stats()
+        _run = eng.run
+
+        def timed_run(*a, **k):        # wall time inside chx_ljmd_run (it ends with a host read of the keys)
+            tr = time.perf_counter()
+            out_ = _run(*a, **k)
+            run_wall[0] += time.perf_counter() - tr
+            return out_
+        eng.run = timed_run
     t0 = time.perf_counter()
     ms.run(warmup + sweeps)
     torch.cuda.synchronize()
@@ -367,6 +376,8 @@ def bench_remd(dev, rank, world, sweeps=20, warmup=3, n_replicas=64, steps_per_s
         if phases["step_kernels_ms"] is not None:
             phases["builds_and_host_in_propagate_ms"] = phases["propagate_ms"] - phases["step_kernels_ms"]
         phases["local_replicas"] = eng.R
+        phases["engine_run_ms"] = run_wall[0] * per
+        phases["python_in_propagate_ms"] = phases["propagate_ms"] - phases["engine_run_ms"]
     # fixed-seed fingerprint: state indices after the run (swap decisions are taken identically on every rank from a
     # shared counter key) and the energy matrix rounded to 1e-6 relative (a replica's trajectory does not depend on
     # the rank that runs it beyond fp32 summation order): compare the fingerprints of runs at different N

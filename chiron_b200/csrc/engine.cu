@@ -100,6 +100,8 @@ struct chx_ljmd {
     // persistent step kernel (engine v5)
     bool persist;                    // CHX_MD_PERSIST=0 falls back to one launch per step
     int coop_grid, Wmax;             // CTAs of k_md_steps (one per SM), warps = plan pieces at most
+    uint32_t deal_pkey;              // 1: the deal's first criterion is whether the tile's PACKED trip count grows, i.e. its
+                                     // max goes from even to odd (two partners per trip); CHX_MD_DEAL_KEY=0: the new max itself
     int deal_tpl;                    // tiles per lane of k_md_deal2 (2, 4, 8; larger: k_md_deal)
     bool deal_tpl_auto_grow;
     int q_full, q_P, q_units;        // unit queue of a step: q_full whole blocks, then the rest cut into q_P pieces
@@ -648,7 +650,7 @@ __host__ __device__ inline size_t md_deal_smem(int tcap) {
 __global__ void __launch_bounds__(128)
 k_md_deal(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ cand_n_all, MdGeom g,
           int ccap, int tcap, int lw, uint16_t* __restrict__ memb_all, uint16_t* __restrict__ tmeta_all,
-          int* __restrict__ ntiles_all, MdRep* __restrict__ rep) {
+          int* __restrict__ ntiles_all, MdRep* __restrict__ rep, uint32_t pkey) {
     extern __shared__ __align__(16) uint32_t deal_sm[];
     const int r = blockIdx.y;
     if (!rep[r].flag) return;
@@ -688,7 +690,7 @@ k_md_deal(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ can
 #define DEAL_KEY(AT, CS, TI)                                                                              \
                 ({ const uint32_t nm_ = ((CS) >> 8) + ((c & (AT)) != 0u ? 1u : 0u);                            \
                    ((TI) < T && ((CS) & 0xffu) < TILE_SLOTS && nm_ <= (uint32_t)cap)                          \
-                       ? (nm_ << 18 | ((CS) & 0xffu) << 12 | (uint32_t)(TI)) : 0xffffffffu; })
+                       ? ((nm_ & ~((CS) >> 8) & pkey) << 28 | nm_ << 18 | ((CS) & 0xffu) << 12 | (uint32_t)(TI)) : 0xffffffffu; })
                 best = min(min(DEAL_KEY(at0, cs0, w), DEAL_KEY(at1, cs1, w + DEAL_Q)), DEAL_KEY(at2, cs2, w + 2 * DEAL_Q));
 #undef DEAL_KEY
 #pragma unroll
@@ -701,7 +703,7 @@ k_md_deal(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ can
             } while (__any_sync(FULL, again));
             const bool place = active && !ovf;
             const int tw = place ? (int)(best & 0xfffu) : 0, slot = (int)((best >> 12) & 0x3fu);
-            const uint32_t newmax = best >> 18;
+            const uint32_t newmax = (best >> 18) & 0x3fu;
             const uint32_t b4 = place ? (c >> (4 * w)) & 0xfu : 0u;
             const uint32_t cc = cnt[tw * DEAL_Q] + ((b4 * 0x00204081u) & 0x01010101u);
             if (place) cnt[tw * DEAL_Q] = cc;
@@ -735,7 +737,8 @@ k_md_deal(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ can
                     const uint32_t m = cs[t];
                     const uint32_t nm = (m >> 8) + ((c & at[t]) != 0u ? 1u : 0u);
                     const uint32_t key = ((m & 0xffu) < TILE_SLOTS && nm <= (uint32_t)cap)
-                                             ? (nm << 18 | (m & 0xffu) << 12 | (uint32_t)t) : 0xffffffffu;
+                                             ? ((nm & ~(m >> 8) & pkey) << 28 | nm << 18 | (m & 0xffu) << 12 | (uint32_t)t)
+                                             : 0xffffffffu;
                     best = min(best, key);
                 }
             }
@@ -749,7 +752,7 @@ k_md_deal(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ can
         } while (__any_sync(FULL, again));
         const bool place = active && !ovf;
         const int tw = place ? (int)(best & 0xfffu) : 0, slot = (int)((best >> 12) & 0x3fu);
-        const uint32_t newmax = best >> 18;
+        const uint32_t newmax = (best >> 18) & 0x3fu;
         // byte counters of my 4 particles in the winning tile: +1 where the column has a bit
         const uint32_t b4 = place ? (c >> (4 * w)) & 0xfu : 0u;
         const uint32_t cc = cnt[tw * DEAL_Q] + ((b4 * 0x00204081u) & 0x01010101u);
@@ -863,7 +866,7 @@ template <int TPL, int NPL>
 __global__ void __launch_bounds__(128)
 k_md_deal2(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ cand_n_all, MdGeom g, int ccap,
            int tcap, int lw, uint16_t* __restrict__ memb_all, uint16_t* __restrict__ tmeta_all,
-           int* __restrict__ ntiles_all, MdRep* __restrict__ rep) {
+           int* __restrict__ ntiles_all, MdRep* __restrict__ rep, uint32_t pkey) {
     const int r = blockIdx.y;
     if (!rep[r].flag) return;
     const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
@@ -901,7 +904,8 @@ k_md_deal2(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ ca
                 const int t = j * 16 + hl;
                 const uint32_t nm = (cs[j] >> 8) + ((c & at[j]) != 0u ? 1u : 0u);
                 const uint32_t kj = (t < T && (cs[j] & 0xffu) < TILE_SLOTS && nm <= cap)
-                                        ? (nm << 18 | (cs[j] & 0xffu) << 12 | (uint32_t)t) : 0xffffffffu;
+                                        ? ((nm & ~(cs[j] >> 8) & pkey) << 28 | nm << 18 | (cs[j] & 0xffu) << 12 | (uint32_t)t)
+                                        : 0xffffffffu;
                 key = min(key, kj);
             }
             const uint32_t k0 = __reduce_min_sync(FULL, half ? 0xffffffffu : key);
@@ -916,7 +920,7 @@ k_md_deal2(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ ca
         {
             const bool place = active && !ovf;
             const int tw = (int)(best & 0xfffu), slot = (int)((best >> 12) & 0x3fu);
-            const uint32_t newmax = best >> 18;
+            const uint32_t newmax = (best >> 18) & 0x3fu;
             // every lane runs the update of all its tiles with the candidate's column masked to zero unless
             // the tile is the winner: straight-line code, all array indices compile-time constants
 #pragma unroll
@@ -981,7 +985,7 @@ struct LjConst {
 #define CHX_TILE_PREFETCH 0   // L1 prefetch of the tile after next: measured neutral (profiles/r01_flag_tune.log)
 #endif
 #ifndef CHX_TRIP_UNROLL
-#define CHX_TRIP_UNROLL 1
+#define CHX_TRIP_UNROLL 2     // two trips per iteration: 53.3 -> 52.65 us per step (gpurun r02 variants11)
 #endif
 #ifndef CHX_NEAR3
 #define CHX_NEAR3 1           // one FMNMX3 instead of two FMNMX for the cutoff-band tracker
@@ -1224,6 +1228,41 @@ struct MdStepConst {
     float half_skin_int2;        // (internal skin / 2)^2
 };
 
+// random.normal element for the engine's O step: the reference's formula (sqrt(2) * erfinv(u), XLA's fp32 ErfInv
+// polynomial, common.cuh: normal_from_bits) with the polynomial on FMAs and log1p(-u^2) as a fast log of
+// (1 - u)(1 + u) -- 1 - |u| is exact, so the argument carries no cancellation error; the noise differs from the
+// exactly rounded evaluation by < 2e-7 relative (parity tolerance of a BAOAB step: 1e-5), at ~35 instead of ~70
+// instructions per element.  The API-parity kernels (chx_random_normal, chx_baoab_update) keep the exact form.
+__device__ __forceinline__ float normal_from_bits_fast(uint32_t bits) {
+    const float u = uniform_from_bits(bits, -0.99999994f, 1.0f);
+    float w = -__logf((1.0f - u) * (1.0f + u));
+    float p;
+    if (w < 5.0f) {
+        w -= 2.5f;
+        p = 2.81022636e-08f;
+        p = fmaf(p, w, 3.43273939e-07f);
+        p = fmaf(p, w, -3.5233877e-06f);
+        p = fmaf(p, w, -4.39150654e-06f);
+        p = fmaf(p, w, 0.00021858087f);
+        p = fmaf(p, w, -0.00125372503f);
+        p = fmaf(p, w, -0.00417768164f);
+        p = fmaf(p, w, 0.246640727f);
+        p = fmaf(p, w, 1.50140941f);
+    } else {
+        w = sqrtf(w) - 3.0f;
+        p = -0.000200214257f;
+        p = fmaf(p, w, 0.000100950558f);
+        p = fmaf(p, w, 0.00134934322f);
+        p = fmaf(p, w, -0.00367342844f);
+        p = fmaf(p, w, 0.00573950773f);
+        p = fmaf(p, w, -0.0076224613f);
+        p = fmaf(p, w, 0.00943887047f);
+        p = fmaf(p, w, 1.00167406f);
+        p = fmaf(p, w, 2.83297682f);
+    }
+    return 1.41421356f * (p * u);
+}
+
 // BAOAB update of one block's 32 particles, x_step -> x_{step+1} (written to xn_all, the OTHER position
 // buffer), with the forces (fx, fy, fz) of x_step in registers: the trailing B of step - 1, B-A-O-A of
 // step (integrators.py:174-195), wrap, the reference's rebuild condition and the engine's own.  One
@@ -1253,6 +1292,7 @@ __device__ __forceinline__ bool md_block_update(int r, int b, int lane, size_t o
         const float m = v.w;
         const float kT = rep[r].kT;
         const float bs = __fmul_rn(sc.b, __fsqrt_rn(__fdiv_rn(kT, m)));
+        const float h_over_m = __fdiv_rn(sc.h, m);      // (h f) / m of the reference as f * (h / m): <= 1 ulp apart
         const unsigned long long total = 3ull * (unsigned long long)g.n;
         const bool trailing = step > 0;
         float xc[3] = {xi0.x, xi0.y, xi0.z}, vc[3] = {v.x, v.y, v.z};
@@ -1260,11 +1300,11 @@ __device__ __forceinline__ bool md_block_update(int r, int b, int lane, size_t o
         const float L[3] = {g.box.lx, g.box.ly, g.box.lz};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float kick = __fdiv_rn(__fmul_rn(sc.h, fc[c]), m);
+            const float kick = __fmul_rn(fc[c], h_over_m);
             if (trailing) vc[c] = __fadd_rn(vc[c], kick);                      // B of step - 1
             vc[c] = __fadd_rn(vc[c], kick);                                    // B
             xc[c] = __fadd_rn(xc[c], __fmul_rn(sc.h, vc[c]));                  // A
-            const float xi_n = normal_from_bits(random_bits_elem(sk0, sk1, 3ull * id + c, total));
+            const float xi_n = normal_from_bits_fast(random_bits_elem(sk0, sk1, 3ull * id + c, total));
             vc[c] = __fadd_rn(__fmul_rn(sc.a, vc[c]), __fmul_rn(bs, xi_n));    // O
             xc[c] = __fadd_rn(xc[c], __fmul_rn(sc.h, vc[c]));                  // A
             xc[c] = ref_wrap(xc[c], L[c]);
@@ -1307,8 +1347,11 @@ __device__ __forceinline__ bool md_block_update(int r, int b, int lane, size_t o
 // 4 gives small systems (few blocks per SM) enough warps to hide latency.
 
 #define MD_FORCE_MAX_SPLIT 4
+#ifndef CHX_FORCE_WARPS_PER_SM
+#define CHX_FORCE_WARPS_PER_SM 32   // resident warps per SM the step kernel is compiled for (register budget 65536 / (32 * this))
+#endif
 template <bool ENERGY, int SPLIT, bool UPDATE>
-__global__ void __launch_bounds__(SPLIT * 32, 32 / SPLIT)
+__global__ void __launch_bounds__(SPLIT * 32, CHX_FORCE_WARPS_PER_SM / SPLIT)
 k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, float4* __restrict__ fs_all,
            float4* __restrict__ vs_all, float4* __restrict__ refu_all, const float4* __restrict__ refi_all,
            const uint32_t* __restrict__ tiles_all, const int* __restrict__ ntiles_all,
@@ -1579,9 +1622,10 @@ k_md_steps(const __grid_constant__ MdStepsArgs A) {
                         A.fs[o] = make_float4(fx, fy, fz, 0.f);
                         if (A.final_mode == MD_FINAL_KICK) {
                             float4 v = A.vs[o];
-                            v.x = __fadd_rn(v.x, __fdiv_rn(__fmul_rn(A.sc.h, fx), v.w));
-                            v.y = __fadd_rn(v.y, __fdiv_rn(__fmul_rn(A.sc.h, fy), v.w));
-                            v.z = __fadd_rn(v.z, __fdiv_rn(__fmul_rn(A.sc.h, fz), v.w));
+                            const float h_over_m = __fdiv_rn(A.sc.h, v.w);     // the same form as md_block_update
+                            v.x = __fadd_rn(v.x, __fmul_rn(fx, h_over_m));
+                            v.y = __fadd_rn(v.y, __fmul_rn(fy, h_over_m));
+                            v.z = __fadd_rn(v.z, __fmul_rn(fz, h_over_m));
                             A.vs[o] = v;
                         }
                     } else {
@@ -1664,9 +1708,10 @@ __global__ void k_md_kick(float4* __restrict__ vs_all, const float4* __restrict_
     if (o >= (size_t)R * g.np) return;
     float4 v = vs_all[o];
     const float4 f = fs_all[o];
-    v.x = __fadd_rn(v.x, __fdiv_rn(__fmul_rn(h, f.x), v.w));
-    v.y = __fadd_rn(v.y, __fdiv_rn(__fmul_rn(h, f.y), v.w));
-    v.z = __fadd_rn(v.z, __fdiv_rn(__fmul_rn(h, f.z), v.w));
+    const float h_over_m = __fdiv_rn(h, v.w);     // the same form as md_block_update: a split run equals a single one
+    v.x = __fadd_rn(v.x, __fmul_rn(f.x, h_over_m));
+    v.y = __fadd_rn(v.y, __fmul_rn(f.y, h_over_m));
+    v.z = __fadd_rn(v.z, __fmul_rn(f.z, h_over_m));
     vs_all[o] = v;
 }
 
@@ -1873,7 +1918,7 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
             const dim3 gd(chx_div_up(g.nblk, DEAL2_BPC), R);
 #define MD_DEAL2(TPL, NPL)                                                                              \
             k_md_deal2<TPL, NPL><<<gd, 128, 0, st>>>(md->cand_col, md->cand_n, g, md_ccap(md), md->tcap, md->lw, \
-                                                     md->memb, md->tmeta, md->ntiles, md->rep)
+                                                     md->memb, md->tmeta, md->ntiles, md->rep, md->deal_pkey)
             const bool p4 = md->lw <= 2;   // counters up to 6 * lw: 4 bit planes for lw = 2, else 6
             if (md->deal_tpl == 2) { if (p4) MD_DEAL2(2, 4); else MD_DEAL2(2, 6); }
             else if (md->deal_tpl == 4) { if (p4) MD_DEAL2(4, 4); else MD_DEAL2(4, 6); }
@@ -1882,7 +1927,8 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
         } else {
             CHX_CUDA(cudaFuncSetAttribute(k_md_deal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
             k_md_deal<<<dim3(chx_div_up(g.nblk, DEAL_BPC), R), 128, smem_d, st>>>(
-                md->cand_col, md->cand_n, g, md_ccap(md), md->tcap, md->lw, md->memb, md->tmeta, md->ntiles, md->rep);
+                md->cand_col, md->cand_n, g, md_ccap(md), md->tcap, md->lw, md->memb, md->tmeta, md->ntiles, md->rep,
+                md->deal_pkey);
         }
         CHX_LAUNCHED(ctx);
         k_md_emit<<<dim3(chx_div_up(g.nblk, 4), R), 128, 0, st>>>(
@@ -2196,6 +2242,7 @@ int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
     }
     md->rebuilds = 0; md->steps = 0; md->have_state = false; md->forces_valid = false;
     md->deal_tpl = 2; md->deal_tpl_auto_grow = false;
+    { const char* e = getenv("CHX_MD_DEAL_KEY"); md->deal_pkey = (e && e[0] == '0') ? 0u : 1u; }
     { const char* e = getenv("CHX_MD_NOGRAPH"); md->no_graph = e && e[0] == '1'; }
     // the persistent step kernel is opt-in: measured slower than one launch per step on B200
     // (N = 262,144: 66.8 vs 53.0 us per step; 8 x 8,192: 26.2 vs 22.8 us; profiles/r02_step_kernel_ncu.md)
@@ -2414,7 +2461,9 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
             }
         while (t < nsteps) {
             while (n_pend < 2 && t_enq < nsteps) {
-                const int te = nsteps - t_enq < CH ? nsteps : t_enq + CH;
+                // graph replays start at even steps (the buffer roles are the captured ones): after a rebuild at
+                // an odd step one direct launch restores the alignment
+                const int te = (t_enq & 1) ? t_enq + 1 : (nsteps - t_enq < CH ? nsteps : t_enq + CH);
                 const bool replay = te - t_enq == CH && !(t_enq & 1);
                 const int sl = next_slot;
                 next_slot ^= 1;
@@ -2444,6 +2493,23 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
             rc = md_download_rep(md);      // waits for the look-ahead as well
             if (rc != CHX_OK) return rc;
             n_pend = 0;
+            if (R == 1 && md->rep_host[0].halt < nsteps) {
+                // single system: rebuild on x_halt and re-enter the look-ahead loop at the halted step -- the redone
+                // steps are ordinary chunks, nothing waits for them
+                MdRep& q = md->rep_host[0];
+                const int first = q.halt;
+                q.flag = 1; q.lo = first; q.halt = HALT_NONE;
+                clear_build_stats(q);
+                rc = md_upload_rep(md);
+                if (rc != CHX_OK) return rc;
+                rc = md_rebuild(md, true);
+                if (rc != CHX_OK) return rc;
+                md->rep_host[0].flag = 0;
+                rc = md_upload_rep(md);
+                if (rc != CHX_OK) return rc;
+                t = t_enq = first;
+                continue;
+            }
             rc = catch_up(t_enq);
             if (rc != CHX_OK) return rc;
             for (int r = 0; r < R; ++r) { md->rep_host[r].lo = t_enq; md->rep_host[r].flag = 0; md->rep_host[r].halt = HALT_NONE; }
