@@ -430,6 +430,11 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # chiron logs through loguru, whose default sink prints every DEBUG / INFO record (~0.1 ms each, six per
+    # replica-exchange sweep): a production run keeps warnings only
+    from loguru import logger
+    logger.remove()
+    logger.add(sys.stderr, level="WARNING")
 
     from chiron_b200 import build as _build
     if rank == 0:

@@ -185,7 +185,84 @@ __global__ void k_mark_moved(const uint32_t* __restrict__ moved, int n_moved, ui
     if (t < n_moved) is_moved[moved[t]] = 1;
 }
 
+// Generalisation the reference's API hints at (potential.py:131-137 takes one sigma /
+// epsilon): per-particle parameters with Lorentz-Berthelot mixing, sigma_ij = (sigma_i + sigma_j) / 2,
+// eps_ij = sqrt(eps_i eps_j), and an optional energy shift that makes every pair energy zero at the cutoff.
+// Same half list, same exact cutoff predicate, same pair formula (potential.py:208-212) per pair.
+template <bool PERIODIC, bool WANT_F>
+__global__ void __launch_bounds__(256)
+k_lj_nlist_mixed(const float* __restrict__ x, int n, Box box, FastCut fc, const uint32_t* __restrict__ list,
+                 const int32_t* __restrict__ nn, int M, const float* __restrict__ sigma_i,
+                 const float* __restrict__ eps_i, int shift, double* __restrict__ energy, float* __restrict__ force) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    double e_acc = 0.0;
+    if (i < n) {
+        const float xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
+        const float si = sigma_i[i], ei = eps_i[i];
+        int cnt = nn[i];
+        cnt = cnt < M ? cnt : M;
+        float fx = 0.f, fy = 0.f, fz = 0.f, e_row = 0.f;
+        for (int k = lane; k < cnt; k += 32) {
+            const uint32_t j = list[(size_t)i * M + k];
+            float r2, dx, dy, dz;
+            if (fast_within<PERIODIC>(xi, yi, zi, x[3 * j], x[3 * j + 1], x[3 * j + 2], box, fc, r2, dx, dy, dz)) {
+                const float sij = 0.5f * (si + sigma_i[j]);
+                const float eij = sqrtf(ei * eps_i[j]);
+                float e, f;
+                lj_pair_r2(r2, sij * sij, eij, e, f);
+                if (shift) {
+                    float ec, fc_unused;
+                    lj_pair_r2(fc.c * fc.c, sij * sij, eij, ec, fc_unused);
+                    e -= ec;
+                }
+                e_row += e;
+                if (WANT_F) {
+                    const float px = f * dx, py = f * dy, pz = f * dz;
+                    fx += px; fy += py; fz += pz;
+                    atomicAdd(&force[3 * j], -px);
+                    atomicAdd(&force[3 * j + 1], -py);
+                    atomicAdd(&force[3 * j + 2], -pz);
+                }
+            }
+        }
+        e_acc = (double)e_row;
+        if (WANT_F) {
+            fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+            if (lane == 0) {
+                atomicAdd(&force[3 * i], fx);
+                atomicAdd(&force[3 * i + 1], fy);
+                atomicAdd(&force[3 * i + 2], fz);
+            }
+        }
+    }
+    if (energy) block_add_double(e_acc, energy);
+}
+
 extern "C" {
+
+int chx_lj_nlist_energy_force_mixed(chx_ctx* ctx, const float* x, int n, float lx, float ly, float lz, int periodic,
+                                    const uint32_t* neighbor_list, const int32_t* n_neighbors, int M,
+                                    const float* sigma_per_particle, const float* epsilon_per_particle, float cutoff,
+                                    int shift, double* energy_dev, float* force) {
+    CHX_REQUIRE(ctx && x && neighbor_list && n_neighbors && sigma_per_particle && epsilon_per_particle, "NULL argument");
+    CHX_REQUIRE(n > 0 && M > 0, "n and M must be positive");
+    CHX_REQUIRE(energy_dev || force, "nothing to compute");
+    Box box = make_box(lx, ly, lz);
+    if (energy_dev) CHX_CUDA(cudaMemsetAsync(energy_dev, 0, sizeof(double), ctx->stream));
+    if (force) CHX_CUDA(cudaMemsetAsync(force, 0, sizeof(float) * 3 * (size_t)n, ctx->stream));
+    const FastCut fc = make_fast_cut(cutoff, lx, ly, lz, periodic != 0);
+    const int blocks = chx_div_up(n, 8);
+#define LAUNCH(P, F)                                                                                       \
+    k_lj_nlist_mixed<P, F><<<blocks, 256, 0, ctx->stream>>>(x, n, box, fc, neighbor_list, n_neighbors, M,    \
+                                                            sigma_per_particle, epsilon_per_particle, shift, \
+                                                            energy_dev, force)
+    if (periodic) { if (force) LAUNCH(true, true); else LAUNCH(true, false); }
+    else { if (force) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+    CHX_LAUNCHED(ctx);
+    return CHX_OK;
+}
 
 int chx_lj_nlist_energy_force(chx_ctx* ctx, const float* x, int n, float lx, float ly, float lz,
                               int periodic, const uint32_t* neighbor_list,

@@ -43,7 +43,17 @@ def shard_bounds(n_replicas: int, world_size: int, rank: int):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_rows(local_rows: np.ndarray, n_replicas: int, group=None) -> np.ndarray:
+def shard_ids(n_replicas: int, world_size: int, rank: int, policy: str = "contiguous") -> np.ndarray:
+    """Replica ids owned by `rank`.  "contiguous": the block of `shard_bounds`; "strided": rank, rank + world, ...
+    -- with a monotone temperature ladder every rank then holds cold and hot replicas alike, which evens out the
+    table rebuilds the hot ones cause (sizes differ by at most one either way)."""
+    if policy == "strided":
+        return np.arange(rank, n_replicas, world_size, dtype=int)
+    lo, hi = shard_bounds(n_replicas, world_size, rank)
+    return np.arange(lo, hi, dtype=int)
+
+
+def gather_rows(local_rows: np.ndarray, n_replicas: int, group=None, policy: str = "contiguous") -> np.ndarray:
     """All-gather the (n_local, K) float64 rows of every rank into the (R, K) matrix.
     Single process: returns the input.  Uses the backend of the default process group: NCCL moves
     the rows through device memory over NVLink, gloo through host memory."""
@@ -53,7 +63,8 @@ def gather_rows(local_rows: np.ndarray, n_replicas: int, group=None) -> np.ndarr
         return local_rows
     world = dist.get_world_size(group)
     K = local_rows.shape[1]
-    n_max = max(shard_bounds(n_replicas, world, r)[1] - shard_bounds(n_replicas, world, r)[0] for r in range(world))
+    ids = [shard_ids(n_replicas, world, r, policy) for r in range(world)]
+    n_max = max(len(i) for i in ids)
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
     send = torch.zeros((n_max, K), dtype=torch.float64, device=dev)
     send[:local_rows.shape[0]] = torch.from_numpy(local_rows).to(dev)
@@ -62,8 +73,7 @@ def gather_rows(local_rows: np.ndarray, n_replicas: int, group=None) -> np.ndarr
     recv = recv.cpu().numpy().reshape(world, n_max, K)
     out = np.empty((n_replicas, K), dtype=np.float64)
     for r in range(world):
-        lo, hi = shard_bounds(n_replicas, world, r)
-        out[lo:hi] = recv[r, :hi - lo]
+        out[ids[r]] = recv[r, :len(ids[r])]
     return out
 
 
@@ -74,14 +84,14 @@ class _RowGatherer:
     is one D2H copy of the gathered (R, K) matrix into pinned memory.  With gloo (CPU tests) the same calls run
     on host tensors."""
 
-    def __init__(self, n_replicas: int, K: int, group=None):
+    def __init__(self, n_replicas: int, K: int, group=None, policy: str = "contiguous"):
         import torch.distributed as dist
         self.R, self.K, self.group = n_replicas, K, group
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.world = dist.get_world_size(group) if self.dist else 1
         self.rank = dist.get_rank(group) if self.dist else 0
-        self.bounds = [shard_bounds(n_replicas, self.world, r) for r in range(self.world)]
-        self.n_max = max(hi - lo for lo, hi in self.bounds)
+        self.ids = [shard_ids(n_replicas, self.world, r, policy) for r in range(self.world)]
+        self.n_max = max(len(i) for i in self.ids)
         self.send = self.recv = self.host = None
 
     def _buffers(self, like: torch.Tensor):
@@ -110,8 +120,8 @@ class _RowGatherer:
             torch.cuda.current_stream(self.recv.device).synchronize()
         flat = self.host.numpy().reshape(self.world, self.n_max, self.K)
         out = np.empty((self.R, self.K), dtype=np.float64)
-        for r, (lo, hi) in enumerate(self.bounds):
-            out[lo:hi] = flat[r, :hi - lo]
+        for r, ids in enumerate(self.ids):
+            out[ids] = flat[r, :len(ids)]
         return out
 
 
@@ -150,7 +160,8 @@ def neighbor_swaps(u_rk: np.ndarray, replica_states: np.ndarray, iteration: int,
 # ---------------------------------------------------------------------------------------------------
 class MultiStateSampler:
     def __init__(self, mcmc_sampler: MCMCSampler, reporter: MultistateReporter, exchange: Optional[str] = None,
-                 exchange_seed: int = 0, mcmc_iterations_per_sweep: Optional[int] = None):
+                 exchange_seed: int = 0, mcmc_iterations_per_sweep: Optional[int] = None,
+                 sharding: str = "strided"):
         from .analysis import MBAREstimator
         self._thermodynamic_states = None
         self._unsampled_states = None
@@ -169,6 +180,9 @@ class MultiStateSampler:
         self._offline_estimator = MBAREstimator()
         if exchange not in (None, "neighbors"):
             raise ValueError("exchange must be None (reference behaviour) or 'neighbors'")
+        if sharding not in ("strided", "contiguous"):
+            raise ValueError("sharding must be 'strided' or 'contiguous'")
+        self.sharding = sharding          # which replicas a rank owns when the run is sharded (shard_ids)
         self.exchange = exchange
         self.exchange_seed = int(exchange_seed)
         # the reference hands the multistate n_iterations to every MCMCSampler.run as ITS n_iterations
@@ -207,18 +221,18 @@ class MultiStateSampler:
     @property
     def sampler_states(self) -> Optional[List[SamplerState]]:
         """Copies of the SamplerStates.  In a sharded run (world_size > 1) only the replicas in
-        `local_replica_range` are propagated by this rank; the positions of the others are fetched from their
+        `local_replica_ids` are propagated by this rank; the positions of the others are fetched from their
         owners here (velocities and PRNG keys of non-local replicas stay as created)."""
         if self._sampler_states is None:
             return None
         self._sync_from_engine()
         out = copy.deepcopy(self._sampler_states)
         if self._world > 1:
-            lo, hi = self.local_replica_range
+            mine = set(int(r) for r in self.local_replica_ids)
             xyz = self._report_positions()["positions"]
-            dev = self._sampler_states[lo].positions.device if hi > lo else None
+            dev = self._sampler_states[0].positions.device
             for r in range(self.number_of_replicas):
-                if not (lo <= r < hi):
+                if r not in mine:
                     out[r].positions = unit.Quantity(torch.as_tensor(xyz[r], dtype=torch.float32, device=dev),
                                                      unit.nanometer)
         return out
@@ -235,7 +249,13 @@ class MultiStateSampler:
         return self._is_completed()
 
     @property
+    def local_replica_ids(self) -> np.ndarray:
+        """Replica ids this rank propagates (all of them in a single-process run)."""
+        return shard_ids(self.number_of_replicas, self._world, self._rank, self.sharding)
+
+    @property
     def local_replica_range(self):
+        """(lo, hi) of the contiguous policy; kept for callers that shard contiguously."""
         return shard_bounds(self.number_of_replicas, self._world, self._rank)
 
     # ---- creation (`multistate.py:203-309`) ------------------------------------------------------------
@@ -256,8 +276,7 @@ class MultiStateSampler:
         assert len(self._thermodynamic_states) == len(self._nbr_lists)
         if dist.is_available() and dist.is_initialized():
             self._rank, self._world = dist.get_rank(), dist.get_world_size()
-        lo, hi = self.local_replica_range
-        for r in range(lo, hi):       # initial build of the lists of the replicas this rank owns
+        for r in self.local_replica_ids:       # initial build of the lists of the replicas this rank owns
             self._nbr_lists[r].build(self._sampler_states[r].positions, self._sampler_states[r].box_vectors)
         K = len(thermodynamic_states)
         self._replica_thermodynamic_states = np.arange(K, dtype=int)
@@ -272,6 +291,7 @@ class MultiStateSampler:
                                f"({K}) must be the same.")
         self._iteration = 0
         self._batched = None
+        self._temps_K = None
 
     # ---- minimisation (`multistate.py:311-412`; jaxopt replaced by steepest descent on the force kernel) -----
     def _minimize_replica(self, replica_id: int, tolerance=1.0 * unit.kilojoules_per_mole / unit.nanometers,
@@ -296,9 +316,8 @@ class MultiStateSampler:
     def minimize(self, tolerance=1.0 * unit.kilojoules_per_mole / unit.nanometers, max_iterations: int = 1_000) -> None:
         if self.number_of_replicas == 0:
             raise RuntimeError("Cannot minimize replicas. The simulation must be created first.")
-        lo, hi = self.local_replica_range
-        for replica_id in range(lo, hi):
-            self._minimize_replica(replica_id, tolerance, max_iterations)
+        for replica_id in self.local_replica_ids:
+            self._minimize_replica(int(replica_id), tolerance, max_iterations)
         self._batched = None
 
     # ---- propagation (`multistate.py:414-445, 497-510`) ---------------------------------------------------
@@ -316,13 +335,12 @@ class MultiStateSampler:
     def _propagate_replicas(self) -> None:
         from loguru import logger as log
         log.debug("Propagating all replicas...")
-        lo, hi = self.local_replica_range
         batched = self._batched_engine()
         if batched is not None:
             batched.propagate(self._mcmc_iterations())
             return
-        for replica_id in range(lo, hi):
-            self._propagate_replica(replica_id)
+        for replica_id in self.local_replica_ids:
+            self._propagate_replica(int(replica_id))
 
     # ---- energies (`multistate.py:178-201, 512-531`) -----------------------------------------------------
     def _compute_replica_reduced_potential(self, replica_id: int) -> np.ndarray:
@@ -333,19 +351,19 @@ class MultiStateSampler:
     def _compute_energies(self) -> None:
         from loguru import logger as log
         log.debug("Computing energy matrix for all replicas...")
-        lo, hi = self.local_replica_range
+        ids = self.local_replica_ids
         K = self.number_of_thermodynamic_states
         batched = self._batched_engine()
         if batched is not None:
             # rows stay on the device until the gathered matrix comes back (one D2H per sweep)
             if self._row_gatherer is None or (self._row_gatherer.R, self._row_gatherer.K) != (self.number_of_replicas, K):
-                self._row_gatherer = _RowGatherer(self.number_of_replicas, K)
+                self._row_gatherer = _RowGatherer(self.number_of_replicas, K, policy=self.sharding)
             self._energy_thermodynamic_states = self._row_gatherer(batched.reduced_potentials_device())
             return
-        rows = np.zeros((hi - lo, K))
-        for replica_id in range(lo, hi):
-            rows[replica_id - lo, :] = self._compute_replica_reduced_potential(replica_id)
-        self._energy_thermodynamic_states = gather_rows(rows, self.number_of_replicas)
+        rows = np.zeros((len(ids), K))
+        for k, replica_id in enumerate(ids):
+            rows[k, :] = self._compute_replica_reduced_potential(int(replica_id))
+        self._energy_thermodynamic_states = gather_rows(rows, self.number_of_replicas, policy=self.sharding)
 
     # ---- mixing (`multistate.py:447-495`) ------------------------------------------------------------------
     def _perform_swap_proposals(self):
@@ -360,14 +378,15 @@ class MultiStateSampler:
     def _apply_state_change(self, old, new):
         """Replicas keep their coordinates; a replica that moved to another temperature gets its
         velocities rescaled by sqrt(T_new / T_old)."""
-        lo, hi = self.local_replica_range
         batched = self._batched_engine()
+        if getattr(self, "_temps_K", None) is None or len(self._temps_K) != len(self._thermodynamic_states):
+            # plain floats once: unit arithmetic per replica and sweep costs more than the swap decisions
+            self._temps_K = np.array([float(ts.temperature.value_in_unit(unit.kelvin))
+                                      for ts in self._thermodynamic_states])
         scales = {}
-        for r in range(lo, hi):
+        for r in self.local_replica_ids:
             if old[r] != new[r]:
-                t_old = self._thermodynamic_states[old[r]].temperature
-                t_new = self._thermodynamic_states[new[r]].temperature
-                scales[r] = float(np.sqrt(float(t_new / t_old)))
+                scales[int(r)] = float(np.sqrt(self._temps_K[new[r]] / self._temps_K[old[r]]))
         if batched is not None:
             batched.set_states(new, scales)
         else:
@@ -433,13 +452,13 @@ class MultiStateSampler:
         """(R, N, 3) positions of ALL replicas: every rank contributes the replicas it propagates
         (one all-gather when the run is sharded)."""
         self._sync_from_engine()
-        lo, hi = self.local_replica_range
+        ids = self.local_replica_ids
         n_atoms = self._sampler_states[0].positions.shape[0]
         xyz = np.zeros((self.number_of_replicas, n_atoms, 3))
-        for replica_id in range(lo, hi):
+        for replica_id in ids:
             xyz[replica_id] = self._sampler_states[replica_id].positions.detach().cpu().numpy()
         if self._world > 1:
-            flat = gather_rows(xyz[lo:hi].reshape(hi - lo, n_atoms * 3), self.number_of_replicas)
+            flat = gather_rows(xyz[ids].reshape(len(ids), n_atoms * 3), self.number_of_replicas, policy=self.sharding)
             xyz = flat.reshape(self.number_of_replicas, n_atoms, 3)
         return {"positions": xyz}
 
@@ -503,10 +522,10 @@ class _BatchedLJReplicas:
         from .potential import LJPotential
         if not _engine.available():
             return None
-        lo, hi = ms.local_replica_range
-        if hi <= lo:
+        ids = [int(r) for r in ms.local_replica_ids]
+        if not ids:
             return None
-        ts0, nl0, st0 = ms._thermodynamic_states[0], ms._nbr_lists[lo], ms._sampler_states[lo]
+        ts0, nl0, st0 = ms._thermodynamic_states[0], ms._nbr_lists[ids[0]], ms._sampler_states[ids[0]]
         pot0 = ts0.potential
         if not isinstance(pot0, LJPotential) or not isinstance(nl0, NeighborListNsqrd) or not nl0.space.periodic:
             return None
@@ -533,31 +552,31 @@ class _BatchedLJReplicas:
                 move = par
             elif move != par:
                 return None
-        for r in range(lo, hi):
+        for r in ids:
             st, nl = ms._sampler_states[r], ms._nbr_lists[r]
             if (st.box_vectors is None or st.box_lengths_host() != box0 or st.positions.shape[0] != sig[4]
                     or not isinstance(nl, NeighborListNsqrd) or nl._skin_md() != sig[3] or nl._cutoff_md() != sig[2]):
                 return None
-        return cls(ms, lo, hi, box0, sig, move)
+        return cls(ms, ids, box0, sig, move)
 
-    def __init__(self, ms, lo, hi, box, sig, move):
+    def __init__(self, ms, ids, box, sig, move):
         from ._engine import LJLangevinEngine
         from .utils import initialize_velocities, kT_md, mass_tensor
-        self.ms, self.lo, self.hi = ms, lo, hi
+        self.ms, self.ids = ms, list(ids)      # engine replica k = replica ids[k]
         self.dt, self.gamma, self.nsteps, self.refresh = move
         self.n = sig[4]
-        st0 = ms._sampler_states[lo]
+        st0 = ms._sampler_states[self.ids[0]]
         dev = st0.positions.device
         self.kT_of_state = [kT_md(ts.temperature) for ts in ms._thermodynamic_states]
         states = ms._replica_thermodynamic_states
-        kts = [self.kT_of_state[states[r]] for r in range(lo, hi)]
+        kts = [self.kT_of_state[states[r]] for r in self.ids]
         self.engine = LJLangevinEngine(self.n, box, sig[0], sig[1], sig[2], sig[3], self.dt, self.gamma, kts[0],
-                                       n_replicas=hi - lo, device=dev)
+                                       n_replicas=len(self.ids), device=dev)
         topology = ms._thermodynamic_states[0].potential.topology
         mass = mass_tensor(topology, dev)
         xs, vs = [], []
         self._pending_v_keys = {}
-        for r in range(lo, hi):
+        for r in self.ids:
             st = ms._sampler_states[r]
             xs.append(st.positions)
             if st._velocities is None or st.velocities.shape[0] != self.n:
@@ -584,23 +603,23 @@ class _BatchedLJReplicas:
         for _ in range(int(n_mcmc_iterations)):
             # SamplerState.new_PRNG_key of every local replica in one call (states.py:150-154)
             cur = np.stack([np.asarray(ms._sampler_states[r]._current_PRNG_key, dtype=np.uint32)
-                            for r in range(self.lo, self.hi)])
+                            for r in self.ids])
             carried, keys = random.split_many(cur)
-            for r in range(self.lo, self.hi):
-                ms._sampler_states[r]._current_PRNG_key = carried[r - self.lo]
+            for k, r in enumerate(self.ids):
+                ms._sampler_states[r]._current_PRNG_key = carried[k]
             if self.refresh or any(self._missing_v):
                 x, v, _, _ = self.engine.get_state()
-                x = x.reshape(self.hi - self.lo, self.n, 3)
-                v = v.reshape(self.hi - self.lo, self.n, 3).clone()
+                x = x.reshape(len(self.ids), self.n, 3)
+                v = v.reshape(len(self.ids), self.n, 3).clone()
                 states = ms._replica_thermodynamic_states
-                for r in range(self.lo, self.hi):
-                    if self.refresh or self._missing_v[r - self.lo]:
+                for k, r in enumerate(self.ids):
+                    if self.refresh or self._missing_v[k]:
                         T = ms._thermodynamic_states[states[r]].temperature
-                        v[r - self.lo] = initialize_velocities(T, self.topology, keys[r - self.lo]) \
+                        v[k] = initialize_velocities(T, self.topology, keys[k]) \
                             .value_in_unit_system(unit.md_unit_system)
-                kts = [self.kT_of_state[states[r]] for r in range(self.lo, self.hi)]
+                kts = [self.kT_of_state[states[r]] for r in self.ids]
                 self.engine.set_state(x.contiguous(), v.contiguous(), self.mass, kts)
-                self._missing_v = [False] * (self.hi - self.lo)
+                self._missing_v = [False] * len(self.ids)
             self.engine.run(self.nsteps, keys)
             self._dirty = True
 
@@ -628,10 +647,10 @@ class _BatchedLJReplicas:
         return self.reduced_potentials_device().cpu().numpy()
 
     def set_states(self, new_states, velocity_scales: dict):
-        kts = [self.kT_of_state[new_states[r]] for r in range(self.lo, self.hi)]
+        kts = [self.kT_of_state[new_states[r]] for r in self.ids]
         self.engine.set_kT(kts)
         if velocity_scales:
-            s = [velocity_scales.get(r, 1.0) for r in range(self.lo, self.hi)]
+            s = [velocity_scales.get(r, 1.0) for r in self.ids]
             self.engine.scale_velocities(s)
             self._dirty = True
 
@@ -640,10 +659,10 @@ class _BatchedLJReplicas:
         if not self._dirty:
             return
         x, v, _, _ = self.engine.get_state()
-        x = x.reshape(self.hi - self.lo, self.n, 3)
-        v = v.reshape(self.hi - self.lo, self.n, 3)
-        for r in range(self.lo, self.hi):
+        x = x.reshape(len(self.ids), self.n, 3)
+        v = v.reshape(len(self.ids), self.n, 3)
+        for k, r in enumerate(self.ids):
             st = self.ms._sampler_states[r]
-            st.positions = unit.Quantity(x[r - self.lo].clone(), unit.nanometer)
-            st.velocities = unit.Quantity(v[r - self.lo].clone(), unit.nanometer / unit.picosecond)
+            st.positions = unit.Quantity(x[k].clone(), unit.nanometer)
+            st.velocities = unit.Quantity(v[k].clone(), unit.nanometer / unit.picosecond)
         self._dirty = False

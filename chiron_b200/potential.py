@@ -65,6 +65,72 @@ class IdealGasPotential(NeuralNetworkPotential):
         return torch.zeros_like(x)
 
 
+class LJMixturePotential(NeuralNetworkPotential):
+    """Lennard-Jones with PER-PARTICLE sigma / epsilon (Lorentz-Berthelot mixing) and an optional energy shift at
+    the cutoff -- the generalisation `LJPotential`'s signature hints at (the reference takes
+    one sigma and one epsilon, `potential.py:131-137`).  Same call surface as `LJPotential`; needs a built
+    `NeighborListNsqrd`.  It is deliberately not a subclass of `LJPotential`: the fused Langevin engine and the
+    device-resident Monte Carlo loops are single-species, so this class runs through the building blocks."""
+
+    def __init__(self, topology: Topology, sigma: unit.Quantity, epsilon: unit.Quantity,
+                 cutoff: unit.Quantity = unit.Quantity(1.0, unit.nanometer), shift: bool = False):
+        _check_topology(topology)
+        for name, q, u in (("sigma", sigma, unit.angstrom), ("epsilon", epsilon, unit.kilocalories_per_mole),
+                           ("cutoff", cutoff, unit.nanometer)):
+            if not isinstance(q, unit.Quantity):
+                raise TypeError(f"{name} must be a unit.Quantity, type({name}) = {type(q)}")
+            if not q.unit.is_compatible(u):
+                raise ValueError(f"{name} has the wrong units: {q.unit}")
+        self._sigma_host = np.atleast_1d(np.asarray(sigma.value_in_unit_system(unit.md_unit_system), dtype=np.float32))
+        self._epsilon_host = np.atleast_1d(np.asarray(epsilon.value_in_unit_system(unit.md_unit_system), dtype=np.float32))
+        if self._sigma_host.shape != self._epsilon_host.shape or self._sigma_host.ndim != 1:
+            raise ValueError("sigma and epsilon must be 1-d arrays of the same length (one entry per particle)")
+        self.cutoff = cutoff.value_in_unit_system(unit.md_unit_system)
+        self.shift = bool(shift)
+        self.topology = topology
+        self._dev = {}
+
+    def _params(self, n, dev):
+        if self._sigma_host.shape[0] != n:
+            raise ValueError(f"{self._sigma_host.shape[0]} per-particle parameters for {n} particles")
+        hit = self._dev.get(dev)
+        if hit is None:
+            hit = (torch.from_numpy(self._sigma_host).to(dev), torch.from_numpy(self._epsilon_host).to(dev))
+            self._dev[dev] = hit
+        return hit
+
+    def _evaluate(self, positions, nbr_list, want_energy, want_force):
+        from .neighbors import NeighborListNsqrd
+        x = _lib.as_device_f32(positions)
+        n, dev = x.shape[0], x.device
+        if not isinstance(nbr_list, NeighborListNsqrd):
+            raise ValueError("LJMixturePotential needs a NeighborListNsqrd")
+        if not nbr_list.is_built:
+            raise ValueError("Neighborlist must be built before use")
+        if nbr_list.cutoff.value_in_unit_system(unit.md_unit_system) != self.cutoff:
+            raise ValueError(
+                f"Neighborlist cutoff ({nbr_list.cutoff}) must be the same as the potential cutoff ({self.cutoff})")
+        sig, eps = self._params(n, dev)
+        energy = torch.zeros((), dtype=torch.float64, device=dev) if want_energy else None
+        force = torch.empty((n, 3), dtype=torch.float32, device=dev) if want_force else None
+        lx, ly, lz, periodic = nbr_list._box_args()
+        _lib.get_context(dev).call("chx_lj_nlist_energy_force_mixed", _lib.ptr(x), n, lx, ly, lz, periodic,
+                                   _lib.ptr(nbr_list.neighbor_list), _lib.ptr(nbr_list.n_neighbors),
+                                   nbr_list.neighbor_list.shape[1], _lib.ptr(sig), _lib.ptr(eps), self.cutoff,
+                                   int(self.shift), _lib.ptr(energy), _lib.ptr(force))
+        return energy, force
+
+    def compute_energy(self, positions, nbr_list=None, debug_mode=False):
+        return self._evaluate(positions, nbr_list, True, False)[0].float()
+
+    def compute_force(self, positions, nbr_list=None):
+        return self._evaluate(positions, nbr_list, False, True)[1]
+
+    def compute_energy_and_force(self, positions, nbr_list=None):
+        e, f = self._evaluate(positions, nbr_list, True, True)
+        return e.float(), f
+
+
 class LJPotential(NeuralNetworkPotential):
     """Single-species Lennard-Jones, plain truncation at the cutoff (`potential.py:130-332`)."""
 

@@ -91,3 +91,30 @@ def ho_energy(x, x0, k, U0, dtype=np.float32):
 def ho_force(x, x0, k, dtype=np.float32):
     dx = (np.asarray(x, dtype=dtype) - np.asarray(x0, dtype=dtype)).astype(dtype)
     return (-(dtype(k)) * dx).astype(dtype)
+
+
+def lj_mixture_energy_force_nlist(x, box, sigma_i, epsilon_i, cutoff, neighbor_list, neighbor_mask, shift=False,
+                                  periodic=True, dtype=np.float64):
+    """Generalisation of `lj_energy_nlist` / `lj_force_nlist` to per-particle parameters with Lorentz-Berthelot
+    mixing (sigma_ij = (sigma_i + sigma_j)/2, eps_ij = sqrt(eps_i eps_j)) and an optional energy shift at the
+    cutoff.  The reference has no such path (potential.py:131-137 takes one sigma / epsilon, SURVEY.md section 8 f4);
+    the pair formula is potential.py:208-212.  Evaluated in float64: the checker of chiron_b200.LJMixturePotential."""
+    _, nl, mask, d, r = pairs.calculate_neighborlist(x, box, cutoff, neighbor_list, neighbor_mask, periodic, dtype)
+    nl = np.asarray(nl).astype(np.int64)
+    sig = np.asarray(sigma_i, dtype=dtype)
+    eps = np.asarray(epsilon_i, dtype=dtype)
+    sij = 0.5 * (sig[:, None] + sig[nl])
+    eij = np.sqrt(eps[:, None] * eps[nl])
+    m = mask != 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q6 = (sij / d) ** 6
+        e = 4.0 * eij * (q6 * q6 - q6)
+        if shift:
+            qc6 = (sij / dtype(cutoff)) ** 6
+            e = e - 4.0 * eij * (qc6 * qc6 - qc6)
+        f = 24.0 * (eij / (d * d)) * (2.0 * q6 * q6 - q6)
+    energy = np.where(m, e, 0.0).sum(dtype=np.float64)
+    fv = np.where(m, f, 0.0)[..., None] * r
+    F = fv.sum(axis=1)
+    np.subtract.at(F, nl.reshape(-1), fv.reshape(-1, 3))
+    return float(energy), F

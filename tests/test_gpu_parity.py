@@ -956,3 +956,50 @@ def test_mc_loops_at_config3_size(cuda_device):
     assert np.array_equal(a[4], b[4])
     assert np.allclose(a[3], b[3], rtol=1e-6) and np.allclose(a[2], b[2], rtol=2e-6, atol=2e-6)
     assert abs(a[5] - b[5]) <= 2      # list of the final configuration: positions equal to fp32 rounding
+
+
+# ---------------------------------------------------------------------------------------------------
+# generalisation: per-particle sigma / epsilon, energy shift
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shift", [False, True])
+def test_lj_mixture_potential_vs_oracle(cuda_device, shift):
+    """Binary mixture with Lorentz-Berthelot mixing over a NeighborListNsqrd: energy and forces within rel 1e-5 of the
+    float64 oracle; with uniform parameters and no shift it reproduces LJPotential; a Langevin run goes through the
+    building-block path."""
+    from chiron_b200 import unit
+    from chiron_b200.integrators import LangevinIntegrator
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    from chiron_b200.potential import LJMixturePotential, LJPotential
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.utils import PRNG
+    lj_sys, x, box = _lj_system(9, 0.7, seed=17)
+    n = x.shape[0]
+    rng = np.random.default_rng(2)
+    big = rng.random(n) < 0.3
+    sig = np.where(big, 0.40, 0.34).astype(f32)
+    eps = np.where(big, 1.6, 0.238 * 4.184).astype(f32)
+    rc, skin = 1.02, 0.3
+    nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=rc * unit.nanometer, skin=skin * unit.nanometer,
+                           n_max_neighbors=200, builder="cell")
+    nl.build(x, box)
+    mix = LJMixturePotential(lj_sys.topology, sig * unit.nanometer, eps * unit.kilojoules_per_mole, rc * unit.nanometer,
+                             shift=shift)
+    e, F = mix.compute_energy_and_force(x, nl)
+    ref = pairs.build_neighborlist(x, box, rc, skin, int(nl.n_max_neighbors))
+    e_ref, F_ref = pot.lj_mixture_energy_force_nlist(x.astype(np.float64), box.astype(np.float64), sig, eps, rc,
+                                                     ref["neighbor_list"], ref["neighbor_mask"], shift=shift)
+    assert np.isclose(float(e), e_ref, rtol=1e-5)
+    assert np.allclose(_np(F), F_ref, rtol=1e-5, atol=1e-5 * np.abs(F_ref).max())
+    assert abs(_np(F).astype(np.float64).sum(axis=0)).max() < 1e-4 * np.abs(F_ref).sum() / n      # Newton's third law
+    if not shift:
+        uni = LJMixturePotential(lj_sys.topology, np.full(n, 0.34, f32) * unit.nanometer,
+                                 np.full(n, 0.238 * 4.184, f32) * unit.kilojoules_per_mole, rc * unit.nanometer)
+        one = LJPotential(lj_sys.topology, 0.34 * unit.nanometer, 0.238 * unit.kilocalories_per_mole, rc * unit.nanometer)
+        e1, F1 = uni.compute_energy_and_force(x, nl)
+        e2, F2 = one.compute_energy_and_force(x, nl)
+        assert np.isclose(float(e1), float(e2), rtol=1e-6) and np.allclose(_np(F1), _np(F2), rtol=1e-5, atol=1e-3)
+    PRNG.set_seed(1234)
+    state = SamplerState(positions=lj_sys.positions, current_PRNG_key=PRNG.get_random_key(), box_vectors=lj_sys.box_vectors)
+    integ = LangevinIntegrator(timestep=1.0 * unit.femtosecond)
+    out, _ = integ.run(state, ThermodynamicState(potential=mix, temperature=300 * unit.kelvin), number_of_steps=5, nbr_list=nl)
+    assert integ.last_run_stats["path"] == "blocks" and np.isfinite(_np(out.positions)).all()

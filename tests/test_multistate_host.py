@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from chiron_b200.multistate import gather_rows, neighbor_swaps, shard_bounds
+from chiron_b200.multistate import shard_ids, gather_rows, neighbor_swaps, shard_bounds
 
 
 def test_shard_bounds_cover_all_replicas():
@@ -62,19 +62,19 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, R, out_dir):
+def _worker(rank, world, port, R, out_dir, policy="contiguous"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(3)
     u_full = _ladder_matrix(R, rng)
-    lo, hi = shard_bounds(R, world, rank)
+    ids = shard_ids(R, world, rank, policy)
     states = np.arange(R)
     hist = []
     for it in range(1, 6):
         # every rank only knows the rows of its own replicas; U drifts deterministically per sweep
-        rows = u_full[lo:hi] * (1.0 + 0.01 * it)
-        u = gather_rows(rows, R)
+        rows = u_full[ids] * (1.0 + 0.01 * it)
+        u = gather_rows(rows, R, policy=policy)
         states = neighbor_swaps(u, states, it, seed=11)
         hist.append(states.copy())
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.array(hist))
@@ -82,9 +82,11 @@ def _worker(rank, world, port, R, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_ranks_gloo_agree_with_single_process(built_library, tmp_path):
+@pytest.mark.parametrize("policy", ["contiguous", "strided"])
+def test_two_ranks_gloo_agree_with_single_process(built_library, tmp_path, policy):
     R, world = 7, 2          # uneven shards: 4 + 3
-    mp.spawn(_worker, args=(world, _free_port(), R, str(tmp_path)), nprocs=world, join=True)
+    assert sorted(np.concatenate([shard_ids(R, world, r, policy) for r in range(world)]).tolist()) == list(range(R))
+    mp.spawn(_worker, args=(world, _free_port(), R, str(tmp_path), policy), nprocs=world, join=True)
     h0, h1 = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
     assert np.array_equal(h0, h1)                               # identical decisions without a broadcast
     assert np.array_equal(np.load(tmp_path / "u0.npy"), np.load(tmp_path / "u1.npy"))
