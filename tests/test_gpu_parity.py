@@ -528,6 +528,48 @@ def test_fused_engine_batched_replicas(cuda_device):
         e1.close()
 
 
+@pytest.mark.parametrize("mode", ["proactive", "lookahead", "persistent"])
+def test_fused_engine_batched_replicas_step_loops(cuda_device, monkeypatch, mode):
+    """The three step loops a batch of replicas can take without energy reports -- fresh tables for everybody at
+    every 50-step chunk (default), halt-driven rebuilds per replica behind the look-ahead loop (CHX_MD_PROACTIVE=0)
+    and the persistent kernel -- against independent single-replica runs: keys bit-equal, trajectories to rounding.
+    Small internal skin and a hot replica, so that replicas go stale at different steps inside a chunk."""
+    from chiron_b200._engine import LJLangevinEngine
+    sigma, eps, rc = 0.34, 0.238 * 4.184, 1.02
+    R, nsteps = 3, 61
+    xs, keys, kts = [], [], [1.5, 2.494, 6.0]
+    for r in range(R):
+        _, x, box = _lj_system(8, 0.8, seed=60 + r)
+        xs.append(x)
+        keys.append(jr.PRNGKey(100 + r))
+    n = xs[0].shape[0]
+    mass = np.full(n, 39.948, f32)
+    v0 = [dyn.maxwell_boltzmann(jr.PRNGKey(7 + r), mass, 300.0 * kts[r] / 2.494) for r in range(R)]
+    if mode == "lookahead":
+        monkeypatch.setenv("CHX_MD_PROACTIVE", "0")
+    if mode == "persistent":
+        monkeypatch.setenv("CHX_MD_PERSIST", "1")
+    eng = LJLangevinEngine(n, np.diag(box), sigma, eps, rc, 0.3, 0.002, 1.0, 2.494, n_replicas=R, internal_skin=0.04)
+    eng.set_state(np.stack(xs), np.stack(v0), mass, kts)
+    kout, _ = eng.run(nsteps, np.stack(keys))
+    xb, vb, _, _ = eng.get_state()
+    assert eng.stats()["table_rebuilds"] >= 3
+    eng.close()
+    monkeypatch.delenv("CHX_MD_PROACTIVE", raising=False)
+    monkeypatch.delenv("CHX_MD_PERSIST", raising=False)
+    L = np.diag(box)
+    for r in range(R):
+        e1 = LJLangevinEngine(n, np.diag(box), sigma, eps, rc, 0.3, 0.002, 1.0, kts[r], internal_skin=0.04)
+        e1.set_state(xs[r], v0[r], mass, [kts[r]])
+        k1, _ = e1.run(nsteps, keys[r])
+        x1, v1, _, _ = e1.get_state()
+        dx = _np(xb)[r] - _np(x1)
+        dx -= L * np.round(dx / L)
+        assert np.abs(dx).max() < 2e-5 and np.allclose(_np(vb)[r], _np(v1), rtol=0, atol=5e-4)
+        assert np.array_equal(kout[r], k1[0])
+        e1.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # Monte Carlo moves
 # ---------------------------------------------------------------------------------------------------
