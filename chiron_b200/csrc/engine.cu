@@ -1003,6 +1003,30 @@ __device__ __forceinline__ int tile_slot(const uint32_t* __restrict__ tp, uint32
     return (int)((wv >> (5 * (e - 6 * wi))) & 31u);
 }
 
+// ---- bulk asynchronous copy (TMA engine, `cp.async.bulk`) of tile words into shared memory ----
+// One lane arms an mbarrier with the byte count and issues the copy; everybody waits on the barrier's phase.
+#ifndef CHX_TILE_BULK
+#define CHX_TILE_BULK 0    // 1: the step kernel stages tile words through shared memory with cp.async.bulk (measured
+                           // against the register pipeline in profiles/r02_step_kernel_ncu.md section 4)
+#endif
+#define TILE_STAGES 3
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@!p bra WAIT_%=;\n"
+                 "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
 // x, y, z of a float4 position as an 8-byte and a 4-byte load.  A 16-byte gather would leave its .w (the
 // particle id, unused in the pair loop) dead, and ptxas recycles a dead destination register at once: the
 // next writer of that register then waits for the gather in flight (write-after-write), which exposed the
@@ -1017,11 +1041,13 @@ __device__ __forceinline__ float3 md_gather3(const float4* xs, uint32_t idx) {
 // tile (at most 12 partners per lane and tile), the common case, with the list kept in registers.
 // The loop visits tiles tp, tp + tadv, ... (nt of them): tadv = SPLIT * tstride when SPLIT warps share a
 // block, each taking every SPLIT-th tile.
-template <bool ENERGY, bool GEN, bool LW2, int SPLIT>
+template <bool ENERGY, bool GEN, bool LW2, int SPLIT, bool BULK = false>
 __device__ __forceinline__ void md_tile_loop(const float4* xs, const uint32_t* __restrict__ tp,
                                              int nt, int tstride_arg, const float4 xi0, const float4 xi,
                                              const float4 bc, const MdGeom& g, const LjConst& lj, int lane,
-                                             float& fx, float& fy, float& fz, float& e_acc, unsigned& npair) {
+                                             float& fx, float& fy, float& fz, float& e_acc, unsigned& npair,
+                                             uint32_t* tsm = nullptr, unsigned long long* tbar = nullptr) {
+    static_assert(!BULK || (LW2 && !GEN), "bulk staging exists for the two-list-word, non-generic tile loop");
     // software pipeline over the tiles: index/list words are fetched two tiles ahead and the j
     // positions one tile ahead, so the L2/HBM latency of a tile hides behind the previous one.
     // The table of a block is padded by TILE_PAD tiles, so the look-ahead never needs clamping.
@@ -1034,11 +1060,36 @@ __device__ __forceinline__ void md_tile_loop(const float4* xs, const uint32_t* _
     const uint32_t* pf = tp + lane;            // this lane's word of the tile being prefetched
     // pipeline state at the top of iteration t: (code, la, lb, xj) = tile t, (code_n, la_n, lb_n) = the words
     // of tile t + 1 -- all of them loaded at least one tile ago
-    uint32_t code = pf[0], la = pf[32], lb = pf[64];
-    float3 xj = md_gather3(xs, code & 0xffffffu);
-    pf += tadv;
-    uint32_t code_n = pf[0], la_n = pf[32], lb_n = pf[64];
-    pf += tadv;
+    uint32_t code, la, lb, code_n = 0u, la_n = 0u, lb_n = 0u;
+    float3 xj;
+    // BULK: a ring of TILE_STAGES tiles in shared memory, filled by cp.async.bulk (one 384-byte copy per tile,
+    // issued by lane 0, completion on an mbarrier per stage); stage_bits holds the phase parity of every stage
+    uint32_t s_tile = 0u, s_bar = 0u, stage = 0u, stage_bits = 0u;
+    const uint32_t* gsrc = tp;                 // global address of the next tile to stage
+    if (BULK) {
+        s_tile = (uint32_t)__cvta_generic_to_shared(tsm);
+        s_bar = (uint32_t)__cvta_generic_to_shared(tbar);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < TILE_STAGES; ++k) mbar_init(s_bar + 8 * k, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < TILE_STAGES; ++k) {
+                bulk_load(s_tile + 384 * k, gsrc, 384u, s_bar + 8 * k);
+                gsrc += tadv;
+            }
+        }
+        __syncwarp();
+        mbar_wait(s_bar, 0u);
+        code = tsm[lane]; la = tsm[32 + lane]; lb = tsm[64 + lane];
+        xj = md_gather3(xs, code & 0xffffffu);
+    } else {
+        code = pf[0]; la = pf[32]; lb = pf[64];
+        xj = md_gather3(xs, code & 0xffffffu);
+        pf += tadv;
+        code_n = pf[0]; la_n = pf[32]; lb_n = pf[64];
+        pf += tadv;
+    }
 #if CHX_TILE_PREFETCH
     const int nlines = tstride >> 5;            // 128-byte lines per tile
     if (lane < nlines) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 32 * lane));
@@ -1059,9 +1110,19 @@ __device__ __forceinline__ void md_tile_loop(const float4* xs, const uint32_t* _
         // arithmetic later.  (With the rotation at the top ptxas copied them into the loop-carried
         // registers right behind the loads and parked the dead .w of the float4 gather under a live
         // value: both waited for the load -- 12 % of all stall samples, profiles/r02_step_kernel_ncu.md.)
+        uint32_t code_g = 0u, la_g = 0u, lb_g = 0u;
+        uint32_t stage_n = 0u;
+        if (BULK) {
+            // the words of tile t + 1 have been in flight for two tiles: wait for their stage, read the index word
+            stage_n = stage + 1u == TILE_STAGES ? 0u : stage + 1u;
+            mbar_wait(s_bar + 8u * stage_n, (stage_bits >> stage_n) & 1u);
+            code_n = tsm[96u * stage_n + lane];
+        }
         float3 xg = md_gather3(xs, code_n & 0xffffffu);
-        uint32_t code_g = pf[0], la_g = pf[32], lb_g = pf[64];
-        pf += tadv;
+        if (!BULK) {
+            code_g = pf[0]; la_g = pf[32]; lb_g = pf[64];
+            pf += tadv;
+        }
 #if CHX_TILE_PREFETCH
         // the tables are streamed from HBM once per step: pull the lines of the tile after next into
         // L1 now (no register, no scoreboard), so the register loads above find them on chip
@@ -1210,13 +1271,27 @@ __device__ __forceinline__ void md_tile_loop(const float4* xs, const uint32_t* _
         // full L2 latency once per tile (9 % of all stall samples, profiles/r02_step_kernel_ncu.md).  So the
         // copy is an add of a zero that only exists once the trip loop has finished: |accumulator|, clamped
         // to 1 (also for inf / NaN), times 0.0f is +0.0f = 0x0 and cannot be evaluated, or folded, any earlier.
-        float zf;
-        asm("{ .reg .f32 t; abs.f32 t, %1; min.f32 t, t, 0f3F800000; mul.f32 %0, t, 0f00000000; }"
-            : "=f"(zf) : "f"(GEN ? fx : fx2.x));
-        const uint32_t z = __float_as_uint(zf);
-        code = code_n; la = la_n; lb = lb_n;
-        xj = xg;
-        code_n = code_g + z; la_n = la_g + z; lb_n = lb_g + z;
+        if (BULK) {
+            // tile t + 1 becomes current: its list words come out of shared memory; the stage tile t lived in
+            // (every lane has its words in registers and has used them) is refilled with tile t + 3
+            code = code_n;
+            la = tsm[96u * stage_n + 32 + lane];
+            lb = tsm[96u * stage_n + 64 + lane];
+            xj = xg;
+            __syncwarp();
+            if (lane == 0) bulk_load(s_tile + 384u * stage, gsrc, 384u, s_bar + 8u * stage);
+            gsrc += tadv;
+            stage_bits ^= 1u << stage;
+            stage = stage_n;
+        } else {
+            float zf;
+            asm("{ .reg .f32 t; abs.f32 t, %1; min.f32 t, t, 0f3F800000; mul.f32 %0, t, 0f00000000; }"
+                : "=f"(zf) : "f"(GEN ? fx : fx2.x));
+            const uint32_t z = __float_as_uint(zf);
+            code = code_n; la = la_n; lb = lb_n;
+            xj = xg;
+            code_n = code_g + z; la_n = la_g + z; lb_n = lb_g + z;
+        }
     }
     fx += fx2.x + fx2.y; fy += fy2.x + fy2.y; fz += fz2.x + fz2.y;
     if (ENERGY) e_acc += e2.x + e2.y;
@@ -1361,6 +1436,10 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
     __shared__ double red[SPLIT];
     __shared__ unsigned long long redn[SPLIT];
     __shared__ float4 part[SPLIT > 1 ? SPLIT - 1 : 1][32];
+#if CHX_TILE_BULK
+    __shared__ __align__(128) uint32_t tile_sm[SPLIT][TILE_STAGES * 96];
+    __shared__ __align__(8) unsigned long long tile_bar[SPLIT][TILE_STAGES];
+#endif
     const int r = blockIdx.y;
     const int step = step_arg + (step_base ? *step_base : 0);   // graph replays read the chunk's first step
     if (mode == FMODE_STEP) {
@@ -1407,7 +1486,12 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
             xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
             xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
             if (lw2)
+#if CHX_TILE_BULK
+                md_tile_loop<ENERGY, false, true, SPLIT, true>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy,
+                                                               fz, e_acc, npair, tile_sm[w], tile_bar[w]);
+#else
                 md_tile_loop<ENERGY, false, true, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+#endif
             else
                 md_tile_loop<ENERGY, false, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
         }
