@@ -553,6 +553,11 @@ k_md_cand(const float4* __restrict__ xs_all, const int2* __restrict__ range_all,
         const unsigned self = (unsigned)(p - b * 32);
         if (self < 32u) col &= ~(1u << self);
         if (!have) col = 0u;
+        // pairs INSIDE the block are not listed: the force kernel evaluates them densely, each pair once, with the
+        // reaction force returned by a shuffle (md_self_pairs) -- a quarter of all listed entries at rho* = 0.8
+#if CHX_SELF_N3
+        if (!gen && self < 32u) { pairs += (unsigned long long)__popc(col); col = 0u; }
+#endif
         const unsigned bal = __ballot_sync(FULL, col != 0u);
         // every lane has read its queue entry: the compacted list can overwrite the queue in place
         if (col != 0u) {
@@ -792,8 +797,8 @@ k_md_deal(const uint32_t* __restrict__ cand_col_all, const int* __restrict__ can
 __global__ void __launch_bounds__(128)
 k_md_emit(const uint32_t* __restrict__ cand_idx_all, const uint32_t* __restrict__ cand_col_all,
           const uint16_t* __restrict__ memb_all, const uint16_t* __restrict__ tmeta_all,
-          const int* __restrict__ ntiles_all, MdGeom g, int ccap, int tcap, int lw,
-          uint32_t* __restrict__ tiles_all, MdRep* __restrict__ rep) {
+          const int* __restrict__ ntiles_all, const uint8_t* __restrict__ generic_all, MdGeom g, int ccap, int tcap,
+          int lw, uint32_t* __restrict__ tiles_all, MdRep* __restrict__ rep) {
     const int r = blockIdx.y;
     if (!rep[r].flag) return;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -846,6 +851,9 @@ k_md_emit(const uint32_t* __restrict__ cand_idx_all, const uint32_t* __restrict_
         }
         slots += (unsigned long long)(32 * 2 * ((trips + 1) >> 1));
     }
+#if CHX_SELF_N3
+    if (!generic_all[rb]) slots += 32ull * 31ull;      // md_self_pairs: 31 directed pair slots per lane
+#endif
     if (lane == 0 && slots) atomicAdd(&rep[r].trip_slots, slots);
 }
 
@@ -1338,6 +1346,111 @@ __device__ __forceinline__ float normal_from_bits_fast(uint32_t bits) {
     return 1.41421356f * (p * u);
 }
 
+#ifndef CHX_SELF_N3
+#define CHX_SELF_N3 0   // 1: pairs inside a block are taken out of the tiles and evaluated by md_self_pairs.  Built, parity
+                        // green, measured NEUTRAL (profiles/r02_step_kernel_ncu.md section 5): the in-block entries were the
+                        // perfectly balanced part of every tile -- each lane has one -- so removing them lowers the mean
+                        // number of partners per lane and tile but not the maximum that sets the trip count
+#endif
+// Pairs INSIDE a block (non-generic blocks): evaluated densely and ONCE per pair -- Newton's third law where it is
+// free.  In round k lane i takes the pair (i, i + k mod 32): for k = 1..15 every unordered pair appears exactly once,
+// the force goes to lane i's accumulator and its reaction is fetched by lane i + k with one shuffle per component
+// (from lane - k); in round 16 the pairs (i, i + 16) are evaluated from both sides.  Two rounds share one packed
+// trip (.x = round k, .y = round k + 1).  Both forces stay in the warp: no scatter, no atomics, deterministic.
+// At rho* = 0.8 the 496 pairs of a block were a quarter of all listed (directed) entries: 8 packed double rounds
+// replace ~62 listed partners per lane.  Padding lanes sit at distinct far-away positions, so they fail the cutoff
+// test by themselves.  Pairs within a few ulps of the cutoff are decided by the reference's exact predicate like in
+// the tile loop (neighbors.py:69-81, :782).
+template <bool ENERGY>
+__device__ __forceinline__ void md_self_pairs(const float4 xi0, const float4 xi, const MdGeom& g, const LjConst& lj,
+                                              int lane, float& fx, float& fy, float& fz, float& e_acc, unsigned& npair) {
+    const bool valid = __float_as_int(xi0.w) >= 0;
+    const float px_ = valid ? xi.x : 1.0e18f + 1.0e12f * (float)lane;
+    const float INF = __int_as_float(0x7f800000);
+    const float2 xix = make_float2(px_, px_), xiy = make_float2(xi.y, xi.y), xiz = make_float2(xi.z, xi.z);
+    const float2 c12f = make_float2(lj.c12f, lj.c12f), c6f = make_float2(-lj.c6f, -lj.c6f);
+    const float2 neg1 = make_float2(-1.f, -1.f), negmid = make_float2(-lj.rc2_mid, -lj.rc2_mid);
+    float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax, e2 = ax;
+    float near = INF;
+#pragma unroll
+    for (int k = 1; k <= 15; k += 2) {
+        const int ja = (lane + k) & 31, jb = (lane + k + 1) & 31;
+        float2 sx, sy, sz;
+        sx.x = __shfl_sync(FULL, px_, ja); sx.y = __shfl_sync(FULL, px_, jb);
+        sy.x = __shfl_sync(FULL, xi.y, ja); sy.y = __shfl_sync(FULL, xi.y, jb);
+        sz.x = __shfl_sync(FULL, xi.z, ja); sz.y = __shfl_sync(FULL, xi.z, jb);
+        const float2 dx = __ffma2_rn(sx, neg1, xix);
+        const float2 dy = __ffma2_rn(sy, neg1, xiy);
+        const float2 dz = __ffma2_rn(sz, neg1, xiz);
+        float2 r2 = __fmul2_rn(dx, dx);
+        r2 = __ffma2_rn(dy, dy, r2);
+        r2 = __ffma2_rn(dz, dz, r2);
+        const float2 off = __fadd2_rn(r2, negmid);
+        near = fminf(fminf(near, fabsf(off.x)), fabsf(off.y));
+        const bool in0 = r2.x < lj.rc2_lo, in1 = r2.y < lj.rc2_lo;
+        float2 inv;
+        inv.x = rcp_approx(r2.x); inv.y = rcp_approx(r2.y);
+        const float2 inv3 = __fmul2_rn(__fmul2_rn(inv, inv), inv);
+        float2 msk;
+        msk.x = in0 ? 1.0f : 0.0f; msk.y = in1 ? 1.0f : 0.0f;
+        const float2 f = __fmul2_rn(__fmul2_rn(__fmul2_rn(inv, msk), inv3), __ffma2_rn(c12f, inv3, c6f));
+        const float2 qx = __fmul2_rn(f, dx), qy = __fmul2_rn(f, dy), qz = __fmul2_rn(f, dz);
+        // reaction: the lane that took ME as its partner in this round is lane - k (round k) / lane - k - 1 (round k + 1)
+        const int ga = (lane - k) & 31, gb = (lane - k - 1) & 31;
+        float2 rx, ry, rz;
+        rx.x = __shfl_sync(FULL, qx.x, ga); rx.y = __shfl_sync(FULL, qx.y, gb);
+        ry.x = __shfl_sync(FULL, qy.x, ga); ry.y = __shfl_sync(FULL, qy.y, gb);
+        rz.x = __shfl_sync(FULL, qz.x, ga); rz.y = __shfl_sync(FULL, qz.y, gb);
+        if (k == 15) { rx.y = 0.f; ry.y = 0.f; rz.y = 0.f; }     // round 16 is evaluated from both sides
+        ax = __fadd2_rn(ax, __fadd2_rn(qx, make_float2(-rx.x, -rx.y)));
+        ay = __fadd2_rn(ay, __fadd2_rn(qy, make_float2(-ry.x, -ry.y)));
+        az = __fadd2_rn(az, __fadd2_rn(qz, make_float2(-rz.x, -rz.y)));
+        if (ENERGY) {
+            // e_acc collects DIRECTED pair energies (halved by the caller): a pair taken once counts twice
+            const float2 c12e = make_float2(lj.c12e, lj.c12e), c6e = make_float2(-lj.c6e, -lj.c6e);
+            float2 ee = __fmul2_rn(inv3, __ffma2_rn(c12e, inv3, c6e));
+            const float wy = k == 15 ? 1.0f : 2.0f;
+            e2.x += in0 ? 2.0f * ee.x : 0.f;
+            e2.y += in1 ? wy * ee.y : 0.f;
+            npair += (in0 ? 2u : 0u) + (in1 ? (k == 15 ? 1u : 2u) : 0u);
+        }
+    }
+    fx += ax.x + ax.y; fy += ay.x + ay.y; fz += az.x + az.y;
+    if (ENERGY) e_acc += e2.x + e2.y;
+    if (__any_sync(FULL, near < lj.rc2_hw)) {
+        // rare: a pair of the block sits within a few ulps of the cutoff; the fast rounds left out everything with
+        // r2 >= rc2_lo, the pairs in [rc2_lo, rc2_hi) are decided here with the exact predicate on the raw positions
+        for (int k = 1; k <= 16; ++k) {
+            const int j = (lane + k) & 31;
+            const float sx = __shfl_sync(FULL, px_, j), sy = __shfl_sync(FULL, xi.y, j), sz = __shfl_sync(FULL, xi.z, j);
+            const float ox = __shfl_sync(FULL, xi0.x, j), oy = __shfl_sync(FULL, xi0.y, j), oz = __shfl_sync(FULL, xi0.z, j);
+            const int oid = __float_as_int(__shfl_sync(FULL, xi0.w, j));
+            const float dx = fmaf(sx, -1.f, px_), dy = fmaf(sy, -1.f, xi.y), dz = fmaf(sz, -1.f, xi.z);
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+            float f = 0.f, ee = 0.f;
+            if (r2 >= lj.rc2_lo && r2 < lj.rc2_hi) {
+                float rx, ry, rz, d;
+                if (__float_as_int(xi0.w) < oid)
+                    ref_displacement<true>(xi0.x, xi0.y, xi0.z, ox, oy, oz, g.box, rx, ry, rz, d);
+                else
+                    ref_displacement<true>(ox, oy, oz, xi0.x, xi0.y, xi0.z, g.box, rx, ry, rz, d);
+                if (d < lj.rc) {
+                    const float inv = 1.0f / r2;
+                    const float inv3 = inv * inv * inv;
+                    f = (inv * inv3) * fmaf(lj.c12f, inv3, -lj.c6f);
+                    ee = inv3 * fmaf(lj.c12e, inv3, -lj.c6e);
+                }
+            }
+            const float qx = f * dx, qy = f * dy, qz = f * dz;
+            const int gv = (lane - k) & 31;
+            float rx = __shfl_sync(FULL, qx, gv), ry = __shfl_sync(FULL, qy, gv), rz = __shfl_sync(FULL, qz, gv);
+            if (k == 16) { rx = 0.f; ry = 0.f; rz = 0.f; }
+            fx += qx - rx; fy += qy - ry; fz += qz - rz;
+            if (ENERGY && f != 0.f) { e_acc += (k == 16 ? 1.0f : 2.0f) * ee; npair += k == 16 ? 1u : 2u; }
+        }
+    }
+}
+
 // BAOAB update of one block's 32 particles, x_step -> x_{step+1} (written to xn_all, the OTHER position
 // buffer), with the forces (fx, fy, fz) of x_step in registers: the trailing B of step - 1, B-A-O-A of
 // step (integrators.py:174-195), wrap, the reference's rebuild condition and the engine's own.  One
@@ -1485,6 +1598,9 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
             xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
             xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
             xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
+#if CHX_SELF_N3
+            if (w == 0) md_self_pairs<ENERGY>(xi0, xi, g, lj, lane, fx, fy, fz, e_acc, npair);
+#endif
             if (lw2)
 #if CHX_TILE_BULK
                 md_tile_loop<ENERGY, false, true, SPLIT, true>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy,
@@ -1662,6 +1778,9 @@ k_md_steps(const __grid_constant__ MdStepsArgs A) {
                         xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
                         xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
                         xi.z -= g.box.lz * rintf((xi.z - bc.z) * g.inv_lz);
+#if CHX_SELF_N3
+                        if (part == 0) md_self_pairs<false>(xi0, xi, g, A.lj, lane, fx, fy, fz, e_acc, npair);
+#endif
                         if (A.tstride == 96)
                             md_tile_loop<false, false, true, 1>(xs_cur, tp, tb - ta, A.tstride, xi0, xi, bc, g, A.lj,
                                                                 lane, fx, fy, fz, e_acc, npair);
@@ -2016,7 +2135,7 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
         }
         CHX_LAUNCHED(ctx);
         k_md_emit<<<dim3(chx_div_up(g.nblk, 4), R), 128, 0, st>>>(
-            md->cand_idx, md->cand_col, md->memb, md->tmeta, md->ntiles, g, md_ccap(md), md->tcap, md->lw,
+            md->cand_idx, md->cand_col, md->memb, md->tmeta, md->ntiles, md->generic, g, md_ccap(md), md->tcap, md->lw,
             md->tiles, md->rep);
         CHX_LAUNCHED(ctx);
         int rc = md_download_rep(md);
