@@ -2213,8 +2213,10 @@ static int md_force_split(const chx_ljmd* md) {
     // measured on B200 (profiles/r01_split_tune.log, gpurun r02 tune9): splitting costs 7-15 % once every SM
     // is full (N = 262,144: 46.1 / 49.4 / 53.2 us for 1 / 2 / 4) and gains 14 % on 8 x 8,192 particles, where
     // 2 warps per block (86 % of the warp slots, one wave) beat 4 (1.73 waves): 22.1 vs 22.8 us per step
-    if (warps >= slots) return 1;
-    return 5 * 2 * warps >= 4 * slots ? 2 : 4;
+    // the largest split that still fits one wave of resident warps
+    if (4 * warps <= slots) return 4;
+    if (2 * warps <= slots) return 2;
+    return 1;
 }
 
 static MdStepConst md_step_const(const chx_ljmd* md) {
