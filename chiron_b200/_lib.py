@@ -62,7 +62,7 @@ SIGNATURES = {
     "chx_scale": [_P, _P, _L, _F, _P],
     "chx_mc_displace_run": [_P, _P, _P, _P, _P, _P, _I],
     "chx_mc_barostat_run": [_P, _P, _P, _P, _P, _P, _I],
-    "chx_lj_nlist_energy_force_mixed": [_P, _P, _I, _F, _F, _F, _I, _P, _P, _I, _P, _P, _F, _I, _P, _P],
+    "chx_lj_nlist_energy_force_mixed": [_P, _P, _I, _F, _F, _F, _I, _P, _P, _I, _P, _P, _F, _I, _F, _P, _P],
     # x64 variants
     "chx_displacement_f64": [_P, _P, _P, _L, _D, _D, _D, _I, _P, _P],
     "chx_wrap_f64": [_P, _P, _L, _D, _D, _D, _P],

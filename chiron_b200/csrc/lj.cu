@@ -193,7 +193,8 @@ template <bool PERIODIC, bool WANT_F>
 __global__ void __launch_bounds__(256)
 k_lj_nlist_mixed(const float* __restrict__ x, int n, Box box, FastCut fc, const uint32_t* __restrict__ list,
                  const int32_t* __restrict__ nn, int M, const float* __restrict__ sigma_i,
-                 const float* __restrict__ eps_i, int shift, double* __restrict__ energy, float* __restrict__ force) {
+                 const float* __restrict__ eps_i, int shift, float r_switch, double* __restrict__ energy,
+                 float* __restrict__ force) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     double e_acc = 0.0;
@@ -215,6 +216,17 @@ k_lj_nlist_mixed(const float* __restrict__ x, int n, Box box, FastCut fc, const 
                     float ec, fc_unused;
                     lj_pair_r2(fc.c * fc.c, sij * sij, eij, ec, fc_unused);
                     e -= ec;
+                }
+                if (r_switch > 0.f && r2 > r_switch * r_switch) {
+                    // switching function of OpenMM's NonbondedForce: S = 1 - 6 t^5 + 15 t^4 - 10 t^3,
+                    // t = (r - r_switch) / (r_cut - r_switch); E -> E S, (F/r) -> (F/r) S - E S' / r
+                    const float rr = sqrtf(r2);
+                    const float w = 1.0f / (fc.c - r_switch);
+                    const float t = (rr - r_switch) * w;
+                    const float S = 1.0f + t * t * t * (-10.0f + t * (15.0f - 6.0f * t));
+                    const float dS = -30.0f * t * t * (1.0f - t) * (1.0f - t) * w;
+                    f = f * S - e * dS / rr;
+                    e *= S;
                 }
                 e_row += e;
                 if (WANT_F) {
@@ -244,10 +256,11 @@ extern "C" {
 int chx_lj_nlist_energy_force_mixed(chx_ctx* ctx, const float* x, int n, float lx, float ly, float lz, int periodic,
                                     const uint32_t* neighbor_list, const int32_t* n_neighbors, int M,
                                     const float* sigma_per_particle, const float* epsilon_per_particle, float cutoff,
-                                    int shift, double* energy_dev, float* force) {
+                                    int shift, float switch_distance, double* energy_dev, float* force) {
     CHX_REQUIRE(ctx && x && neighbor_list && n_neighbors && sigma_per_particle && epsilon_per_particle, "NULL argument");
     CHX_REQUIRE(n > 0 && M > 0, "n and M must be positive");
     CHX_REQUIRE(energy_dev || force, "nothing to compute");
+    CHX_REQUIRE(switch_distance >= 0.f && switch_distance < cutoff, "switch_distance must lie in [0, cutoff)");
     Box box = make_box(lx, ly, lz);
     if (energy_dev) CHX_CUDA(cudaMemsetAsync(energy_dev, 0, sizeof(double), ctx->stream));
     if (force) CHX_CUDA(cudaMemsetAsync(force, 0, sizeof(float) * 3 * (size_t)n, ctx->stream));
@@ -256,7 +269,7 @@ int chx_lj_nlist_energy_force_mixed(chx_ctx* ctx, const float* x, int n, float l
 #define LAUNCH(P, F)                                                                                       \
     k_lj_nlist_mixed<P, F><<<blocks, 256, 0, ctx->stream>>>(x, n, box, fc, neighbor_list, n_neighbors, M,    \
                                                             sigma_per_particle, epsilon_per_particle, shift, \
-                                                            energy_dev, force)
+                                                            switch_distance, energy_dev, force)
     if (periodic) { if (force) LAUNCH(true, true); else LAUNCH(true, false); }
     else { if (force) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH

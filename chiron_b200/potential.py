@@ -66,14 +66,16 @@ class IdealGasPotential(NeuralNetworkPotential):
 
 
 class LJMixturePotential(NeuralNetworkPotential):
-    """Lennard-Jones with PER-PARTICLE sigma / epsilon (Lorentz-Berthelot mixing) and an optional energy shift at
-    the cutoff -- the generalisation `LJPotential`'s signature hints at (the reference takes
+    """Lennard-Jones with PER-PARTICLE sigma / epsilon (Lorentz-Berthelot mixing), an optional energy shift at
+    the cutoff and an optional switching function (OpenMM's quintic, from `switch_distance` to the cutoff) -- the
+    generalisation `LJPotential`'s signature hints at (the reference takes
     one sigma and one epsilon, `potential.py:131-137`).  Same call surface as `LJPotential`; needs a built
     `NeighborListNsqrd`.  It is deliberately not a subclass of `LJPotential`: the fused Langevin engine and the
     device-resident Monte Carlo loops are single-species, so this class runs through the building blocks."""
 
     def __init__(self, topology: Topology, sigma: unit.Quantity, epsilon: unit.Quantity,
-                 cutoff: unit.Quantity = unit.Quantity(1.0, unit.nanometer), shift: bool = False):
+                 cutoff: unit.Quantity = unit.Quantity(1.0, unit.nanometer), shift: bool = False,
+                 switch_distance: unit.Quantity = None):
         _check_topology(topology)
         for name, q, u in (("sigma", sigma, unit.angstrom), ("epsilon", epsilon, unit.kilocalories_per_mole),
                            ("cutoff", cutoff, unit.nanometer)):
@@ -87,6 +89,13 @@ class LJMixturePotential(NeuralNetworkPotential):
             raise ValueError("sigma and epsilon must be 1-d arrays of the same length (one entry per particle)")
         self.cutoff = cutoff.value_in_unit_system(unit.md_unit_system)
         self.shift = bool(shift)
+        self.switch_distance = 0.0
+        if switch_distance is not None:
+            if not isinstance(switch_distance, unit.Quantity) or not switch_distance.unit.is_compatible(unit.nanometer):
+                raise ValueError("switch_distance must be a unit.Quantity of length")
+            self.switch_distance = float(switch_distance.value_in_unit_system(unit.md_unit_system))
+            if not 0.0 < self.switch_distance < self.cutoff:
+                raise ValueError("switch_distance must lie between 0 and the cutoff")
         self.topology = topology
         self._dev = {}
 
@@ -117,7 +126,7 @@ class LJMixturePotential(NeuralNetworkPotential):
         _lib.get_context(dev).call("chx_lj_nlist_energy_force_mixed", _lib.ptr(x), n, lx, ly, lz, periodic,
                                    _lib.ptr(nbr_list.neighbor_list), _lib.ptr(nbr_list.n_neighbors),
                                    nbr_list.neighbor_list.shape[1], _lib.ptr(sig), _lib.ptr(eps), self.cutoff,
-                                   int(self.shift), _lib.ptr(energy), _lib.ptr(force))
+                                   int(self.shift), self.switch_distance, _lib.ptr(energy), _lib.ptr(force))
         return energy, force
 
     def compute_energy(self, positions, nbr_list=None, debug_mode=False):

@@ -328,12 +328,14 @@ int chx_ljmd_step_timing(chx_ljmd* md, double* total_ms_host, long long* steps_h
 /* ---- generalisation of LJPotential the reference's API hints at (potential.py:131-137 takes
  * one sigma / epsilon): per-particle parameters (N floats each) with Lorentz-Berthelot mixing, sigma_ij = (sigma_i +
  * sigma_j)/2, eps_ij = sqrt(eps_i eps_j), over a NeighborListNsqrd; shift != 0 subtracts every pair's energy at the
- * cutoff (continuous potential; forces unchanged).  With uniform parameters and shift = 0 it equals
- * chx_lj_nlist_energy_force. */
+ * cutoff (continuous potential; forces unchanged); switch_distance > 0 multiplies every pair energy by OpenMM's
+ * switching function S = 1 - 6t^5 + 15t^4 - 10t^3, t = (r - switch_distance)/(cutoff - switch_distance), beyond
+ * switch_distance (energy and force continuous at the cutoff).  With uniform parameters, shift = 0 and
+ * switch_distance = 0 it equals chx_lj_nlist_energy_force. */
 int chx_lj_nlist_energy_force_mixed(chx_ctx* ctx, const float* x, int n, float lx, float ly, float lz, int periodic,
                                     const uint32_t* neighbor_list, const int32_t* n_neighbors, int M,
                                     const float* sigma_per_particle, const float* epsilon_per_particle, float cutoff,
-                                    int shift, double* energy_dev, float* force);
+                                    int shift, float switch_distance, double* energy_dev, float* force);
 
 /* ---- x64 variants (the reference with jax_enable_x64: float64 positions, displacements, energies, forces) -------
  * Same semantics, argument order and padding rules as the fp32 entry points they mirror, one IEEE float64 rounding

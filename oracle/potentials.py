@@ -94,10 +94,10 @@ def ho_force(x, x0, k, dtype=np.float32):
 
 
 def lj_mixture_energy_force_nlist(x, box, sigma_i, epsilon_i, cutoff, neighbor_list, neighbor_mask, shift=False,
-                                  periodic=True, dtype=np.float64):
+                                  periodic=True, dtype=np.float64, switch_distance=0.0):
     """Generalisation of `lj_energy_nlist` / `lj_force_nlist` to per-particle parameters with Lorentz-Berthelot
-    mixing (sigma_ij = (sigma_i + sigma_j)/2, eps_ij = sqrt(eps_i eps_j)) and an optional energy shift at the
-    cutoff.  The reference has no such path (potential.py:131-137 takes one sigma / epsilon, SURVEY.md section 8 f4);
+    mixing (sigma_ij = (sigma_i + sigma_j)/2, eps_ij = sqrt(eps_i eps_j)), an optional energy shift at the
+    cutoff and an optional quintic switching function.  The reference has no such path (potential.py:131-137 takes one sigma / epsilon, SURVEY.md section 8 f4);
     the pair formula is potential.py:208-212.  Evaluated in float64: the checker of chiron_b200.LJMixturePotential."""
     _, nl, mask, d, r = pairs.calculate_neighborlist(x, box, cutoff, neighbor_list, neighbor_mask, periodic, dtype)
     nl = np.asarray(nl).astype(np.int64)
@@ -113,6 +113,14 @@ def lj_mixture_energy_force_nlist(x, box, sigma_i, epsilon_i, cutoff, neighbor_l
             qc6 = (sij / dtype(cutoff)) ** 6
             e = e - 4.0 * eij * (qc6 * qc6 - qc6)
         f = 24.0 * (eij / (d * d)) * (2.0 * q6 * q6 - q6)
+        if switch_distance > 0.0:
+            # OpenMM NonbondedForce switching function between switch_distance and the cutoff
+            w = 1.0 / (dtype(cutoff) - dtype(switch_distance))
+            t = np.clip((d - dtype(switch_distance)) * w, 0.0, 1.0)
+            S = 1.0 + t ** 3 * (-10.0 + t * (15.0 - 6.0 * t))
+            dS = -30.0 * t * t * (1.0 - t) ** 2 * w
+            f = f * S - e * dS / d
+            e = e * S
     energy = np.where(m, e, 0.0).sum(dtype=np.float64)
     fv = np.where(m, f, 0.0)[..., None] * r
     F = fv.sum(axis=1)

@@ -1003,8 +1003,8 @@ def test_mc_loops_at_config3_size(cuda_device):
 # ---------------------------------------------------------------------------------------------------
 # generalisation: per-particle sigma / epsilon, energy shift
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shift", [False, True])
-def test_lj_mixture_potential_vs_oracle(cuda_device, shift):
+@pytest.mark.parametrize("shift,switch", [(False, 0.0), (True, 0.0), (False, 0.85)])
+def test_lj_mixture_potential_vs_oracle(cuda_device, shift, switch):
     """Binary mixture with Lorentz-Berthelot mixing over a NeighborListNsqrd: energy and forces within rel 1e-5 of the
     float64 oracle; with uniform parameters and no shift it reproduces LJPotential; a Langevin run goes through the
     building-block path."""
@@ -1025,15 +1025,16 @@ def test_lj_mixture_potential_vs_oracle(cuda_device, shift):
                            n_max_neighbors=200, builder="cell")
     nl.build(x, box)
     mix = LJMixturePotential(lj_sys.topology, sig * unit.nanometer, eps * unit.kilojoules_per_mole, rc * unit.nanometer,
-                             shift=shift)
+                             shift=shift, switch_distance=(switch * unit.nanometer if switch else None))
     e, F = mix.compute_energy_and_force(x, nl)
     ref = pairs.build_neighborlist(x, box, rc, skin, int(nl.n_max_neighbors))
     e_ref, F_ref = pot.lj_mixture_energy_force_nlist(x.astype(np.float64), box.astype(np.float64), sig, eps, rc,
-                                                     ref["neighbor_list"], ref["neighbor_mask"], shift=shift)
+                                                     ref["neighbor_list"], ref["neighbor_mask"], shift=shift,
+                                                     switch_distance=switch)
     assert np.isclose(float(e), e_ref, rtol=1e-5)
     assert np.allclose(_np(F), F_ref, rtol=1e-5, atol=1e-5 * np.abs(F_ref).max())
     assert abs(_np(F).astype(np.float64).sum(axis=0)).max() < 1e-4 * np.abs(F_ref).sum() / n      # Newton's third law
-    if not shift:
+    if not shift and not switch:
         uni = LJMixturePotential(lj_sys.topology, np.full(n, 0.34, f32) * unit.nanometer,
                                  np.full(n, 0.238 * 4.184, f32) * unit.kilojoules_per_mole, rc * unit.nanometer)
         one = LJPotential(lj_sys.topology, 0.34 * unit.nanometer, 0.238 * unit.kilocalories_per_mole, rc * unit.nanometer)
