@@ -1554,6 +1554,14 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
     __shared__ __align__(8) unsigned long long tile_bar[SPLIT][TILE_STAGES];
 #endif
     const int r = blockIdx.y;
+    // Programmatic dependent launch (CHX_MD_PDL=1): inside a chunk the launch of step s + 1 is released when every
+    // CTA of step s is past its tile loop, so its CTAs are resident (and have read the static table header below)
+    // when step s drains; everything step s wrote is read after the wait.  Without the launch attribute the two
+    // griddepcontrol instructions are no-ops.
+    const int nt_all = ntiles_all[(size_t)r * g.nblk + blockIdx.x];
+    const bool gen = generic_all[(size_t)r * g.nblk + blockIdx.x] != 0;
+    const float4 bc = bcenter_all[(size_t)r * g.nblk + blockIdx.x];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int step = step_arg + (step_base ? *step_base : 0);   // graph replays read the chunk's first step
     if (mode == FMODE_STEP) {
         // tables valid for x_lo .. x_{halt-1}; a halt raised by another warp of THIS launch is step + 1
@@ -1588,10 +1596,7 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
         const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * (size_t)(tcap + TILE_PAD) * tstride +
                              (size_t)w * tstride;
         const bool lw2 = tstride == 96;
-        const int nt_all = ntiles_all[(size_t)r * g.nblk + b];
         const int nt = (nt_all - w + SPLIT - 1) / SPLIT;      // tiles w, w + SPLIT, ... < nt_all
-        const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
-        const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
         if (gen) {
             md_tile_loop<ENERGY, true, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
         } else {
@@ -1647,6 +1652,7 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
             }
         }
     }
+    asm volatile("griddepcontrol.launch_dependents;");
     if (!UPDATE || w != 0) return;
     md_block_update(r, b, lane, o, step, xi0, fx, fy, fz, took_ref, const_cast<float4*>(odd ? xs_a : xs_b), vs_all,
                     refu_all, refi_all, g, sc, rep);
@@ -2233,17 +2239,36 @@ static MdStepConst md_step_const(const chx_ljmd* md) {
 }
 
 // FMODE_STEP launches the fused step (forces + BAOAB update); the other modes evaluate forces only
+// `pdl`: the launch may start while its predecessor in the stream drains (programmatic dependent launch);
+// only for a step kernel that follows another step kernel on tables older than both.
 static int md_force(chx_ljmd* md, int mode, int step, bool energy, int report_interval, double* e_dev,
-                    const int* step_base = nullptr) {
+                    const int* step_base = nullptr, bool pdl = false) {
     const MdGeom& g = md->g;
     const dim3 gf(g.nblk, md->R);
     const int split = md_force_split(md);
     const bool upd = mode == FMODE_STEP;
+    static int use_pdl = -1;
+    if (use_pdl < 0) { const char* e = getenv("CHX_MD_PDL"); use_pdl = e ? (e[0] == '1') : 0; }   // measured 0.6 us per step SLOWER (profiles/r02_step_kernel_ncu.md section 6): opt-in
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = gf;
+    cfg.stream = md->ctx->stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && upd && use_pdl) ? 1 : 0;
+    const LjConst ljc = md_lj(md);
+    const MdStepConst stc = md_step_const(md);
+    const int tstride = md_tstride(md);
 #define MD_FORCE_LAUNCH(E, S, U)                                                                    \
-    k_md_force<E, S, U><<<gf, S * 32, 0, md->ctx->stream>>>(                                         \
-        md->xs, md->xs_b, md->fs, md->vs, md->refu, md->refi, md->tiles, md->ntiles, md->generic,   \
-        md->bcenter, g, md_lj(md), md_step_const(md), md->tcap, md_tstride(md), md->rep, mode, step, \
-        step_base, report_interval, md->R, e_dev)
+    do {                                                                                            \
+        cfg.blockDim = dim3(S * 32);                                                                \
+        CHX_CUDA(cudaLaunchKernelEx(&cfg, k_md_force<E, S, U>, (const float4*)md->xs, (const float4*)md->xs_b, md->fs, md->vs, \
+                                    md->refu, (const float4*)md->refi, (const uint32_t*)md->tiles,  \
+                                    (const int*)md->ntiles, (const uint8_t*)md->generic,            \
+                                    (const float4*)md->bcenter, g, ljc, stc, md->tcap, tstride, md->rep, mode, step, \
+                                    step_base, report_interval, md->R, e_dev));                     \
+    } while (0)
 #define MD_FORCE_SPLIT(S)                                                                           \
     do {                                                                                            \
         if (upd) { if (energy) MD_FORCE_LAUNCH(true, S, true); else MD_FORCE_LAUNCH(false, S, true); } \
@@ -2573,7 +2598,7 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     auto wants_energy = [&](int s) { return report && s >= 1 && (s - 1) % report_interval == 0; };
     auto launch_steps = [&](int s0, int s1, const int* base) -> int {
         for (int s = s0; s < s1; ++s) {
-            int rc2 = md_force(md, FMODE_STEP, s, wants_energy(s), rint, energies_dev, base);
+            int rc2 = md_force(md, FMODE_STEP, s, wants_energy(s), rint, energies_dev, base, s > s0);
             if (rc2 != CHX_OK) return rc2;
         }
         return CHX_OK;
