@@ -372,6 +372,7 @@ def bench_remd(dev, rank, world, sweeps=20, warmup=3, n_replicas=64, steps_per_s
         kms, ksteps = eng.step_timing()
         st1 = eng.stats()
         phases["step_kernels_ms"] = (kms / ksteps * steps_per_sweep) if ksteps else None
+        phases["engine_groups"] = int(getattr(eng, "G", 1))   # engines on their own streams / host threads
         phases["table_builds_per_sweep"] = (st1["table_rebuilds"] - st0["table_rebuilds"]) / max(1, sweeps)
         if phases["step_kernels_ms"] is not None:
             phases["builds_and_host_in_propagate_ms"] = phases["propagate_ms"] - phases["step_kernels_ms"]

@@ -48,8 +48,9 @@ class LJLangevinEngine:
     """Owns a chx_ljmd: R replicas x N particles, one box, one LJ parameter set."""
 
     def __init__(self, n, box, sigma, epsilon, cutoff, skin, dt, gamma, kT, n_replicas=1,
-                 internal_skin=None, device=None):
-        self.ctx = _lib.get_context(device)
+                 internal_skin=None, device=None, ctx=None):
+        # ctx: a private _lib.Context (own chx_ctx and stream) for an engine driven from its own host thread
+        self.ctx = ctx if ctx is not None else _lib.get_context(device)
         self.device = self.ctx.device
         self.n, self.R = int(n), int(n_replicas)
         if internal_skin is None:

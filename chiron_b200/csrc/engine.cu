@@ -29,6 +29,7 @@
 // the caller is what the reference would hold.  The cutoff predicate d < rc uses the reference's
 // exact fp32 operation order whenever a pair is within a few ulps of the cutoff.
 #include <stdlib.h>
+#include <mutex>
 #include <vector>
 #include "common.cuh"
 
@@ -2063,6 +2064,20 @@ static int md_download_rep(chx_ljmd* md) {
 
 static size_t md_build_smem(int nw, int qcap) { return (size_t)nw * (512 + 8 * (size_t)qcap + 160); }
 
+// cudaFuncSetAttribute is per (function, device) and engines of several host threads share the functions: raise
+// the dynamic shared-memory limit monotonically under a lock, so that no thread lowers it between another
+// thread's attribute call and its launch.
+template <typename K>
+static cudaError_t md_raise_smem_limit(K kernel, int device, size_t bytes, size_t* have_per_device) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = have_per_device[device & 63];
+    if (bytes <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
 // sort + table build for the replicas whose rep_host[r].flag is set (rep_host must already be
 // uploaded); grows the table capacity on overflow.  Leaves rep_host refreshed.
 static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
@@ -2108,7 +2123,7 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
             chx_set_error("neighbour table build needs %zu / %zu bytes of shared memory", smem, smem_d);
             return CHX_NEIGHBOR_OVERFLOW;
         }
-        CHX_CUDA(cudaFuncSetAttribute(k_md_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { static size_t have[64]; CHX_CUDA(md_raise_smem_limit(k_md_cand, ctx->device, smem, have)); }
         k_md_cand<<<dim3(chx_div_up(g.nblk, nw), R), nw * 32, smem, st>>>(
             md->xs, md->cell_range, g, R_list, md->internal_skin, md_ccap(md), md->qcap, md->cand_idx,
             md->cand_col, md->cand_n, md->generic, md->bcenter, md->rep);
@@ -2134,7 +2149,7 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
             else { if (p4) MD_DEAL2(8, 4); else MD_DEAL2(8, 6); }
 #undef MD_DEAL2
         } else {
-            CHX_CUDA(cudaFuncSetAttribute(k_md_deal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+            { static size_t have[64]; CHX_CUDA(md_raise_smem_limit(k_md_deal, ctx->device, smem_d, have)); }
             k_md_deal<<<dim3(chx_div_up(g.nblk, DEAL_BPC), R), 128, smem_d, st>>>(
                 md->cand_col, md->cand_n, g, md_ccap(md), md->tcap, md->lw, md->memb, md->tmeta, md->ntiles, md->rep,
                 md->deal_pkey);

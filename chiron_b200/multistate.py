@@ -21,6 +21,7 @@ indices move, velocities are rescaled by sqrt(T_new / T_old).  `exchange=None` (
 reproduces the reference: `_mix_replicas` changes nothing.
 """
 import copy
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -512,8 +513,131 @@ class MultiStateSampler:
             self._batched.sync_states()
 
 
+def _engine_group_count(n_local: int) -> int:
+    """Engines the rank's replicas are spread over.  With 4..16 replicas per GPU the step kernels no longer fill the
+    machine and a table rebuild is a chain of latency-bound launches: two engines on two streams, each driven by its
+    own host thread, fill each other's gaps (8 x 8,192 particles: 30.4 -> 26.1 us per step all-in, 16: 45.6 -> 43.5;
+    profiles/r02_scripts/two_engines.sh).  CHX_REMD_ENGINE_GROUPS overrides."""
+    env = os.environ.get("CHX_REMD_ENGINE_GROUPS")
+    if env:
+        return max(1, min(int(env), n_local))
+    return 2 if 4 <= n_local <= 16 else 1
+
+
+class _EngineGroups:
+    """The LJLangevinEngine surface `_BatchedLJReplicas` uses, over G engines: replica k of the set lives in engine
+    k % G (strided, so every engine holds a cross-section of the temperature ladder and goes stale at the same
+    rate).  Engine 0 runs on the caller's stream in the caller's thread; engine g > 0 has a private chx context,
+    its own stream and a worker thread for `run` (ctypes releases the GIL; `chx_ljmd_run` synchronises with its
+    stream chunk by chunk).  Everything else is issued from the caller's thread on the caller's stream: `run`
+    returns only after every side stream has drained, and the side streams wait for the caller's stream first."""
+
+    def __init__(self, n_groups, n, box, sigma, epsilon, cutoff, skin, dt, gamma, kT, n_replicas, device):
+        from . import _lib
+        from ._engine import LJLangevinEngine
+        self.R, self.n, self.device = int(n_replicas), int(n), torch.device(device)
+        self.G = int(n_groups)
+        self.members = [list(range(g, self.R, self.G)) for g in range(self.G)]
+        self.engines, self.streams = [], [None]
+        for g, mem in enumerate(self.members):
+            ctx = None
+            if g > 0:
+                s = torch.cuda.Stream(device=self.device)
+                self.streams.append(s)
+                with torch.cuda.stream(s):
+                    ctx = _lib.Context(self.device.index if self.device.index is not None else torch.cuda.current_device())
+            self.engines.append(LJLangevinEngine(n, box, sigma, epsilon, cutoff, skin, dt, gamma, kT,
+                                                 n_replicas=len(mem), device=self.device, ctx=ctx))
+        self._pool = None
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+
+    def _idx(self, g):
+        return torch.as_tensor(self.members[g], device=self.device)
+
+    def set_state(self, x, v, mass, kT_per_replica):
+        x, v = x.reshape(self.R, self.n, 3), v.reshape(self.R, self.n, 3)
+        for g, (eng, mem) in enumerate(zip(self.engines, self.members)):
+            eng.set_state(x[g::self.G].contiguous(), v[g::self.G].contiguous(), mass, [kT_per_replica[k] for k in mem])
+
+    def get_state(self):
+        x = torch.empty((self.R, self.n, 3), dtype=torch.float32, device=self.device)
+        v = torch.empty_like(x)
+        for g, eng in enumerate(self.engines):
+            xg, vg, _, _ = eng.get_state()
+            x[g::self.G] = xg.reshape(-1, self.n, 3)
+            v[g::self.G] = vg.reshape(-1, self.n, 3)
+        return x, v, None, None
+
+    def run(self, nsteps, keys):
+        keys = np.asarray(keys, dtype=np.uint32).reshape(self.R, 2)
+        out = np.empty_like(keys)
+        main = torch.cuda.current_stream(self.device)
+
+        def side(g):
+            s = self.streams[g]
+            with torch.cuda.device(self.device), torch.cuda.stream(s):
+                s.wait_stream(main)
+                k, _ = self.engines[g].run(nsteps, keys[g::self.G])
+                s.synchronize()
+            return k
+
+        if self._pool is None and self.G > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=self.G - 1, thread_name_prefix="chx-engine")
+        futures = [self._pool.submit(side, g) for g in range(1, self.G)]
+        try:
+            out[0::self.G], _ = self.engines[0].run(nsteps, keys[0::self.G])
+        finally:
+            done = [f.result() for f in futures]      # re-raises a worker's error
+        for g, k in enumerate(done, start=1):
+            out[g::self.G] = k
+        return out, None
+
+    def energy(self):
+        e = torch.empty((self.R,), dtype=torch.float64, device=self.device)
+        for g, eng in enumerate(self.engines):
+            e[g::self.G] = eng.energy()
+        return e
+
+    def set_kT(self, kT_per_replica):
+        for eng, mem in zip(self.engines, self.members):
+            eng.set_kT([kT_per_replica[k] for k in mem])
+
+    def scale_velocities(self, scale_per_replica):
+        for eng, mem in zip(self.engines, self.members):
+            sc = [scale_per_replica[k] for k in mem]
+            if any(float(c) != 1.0 for c in sc):
+                eng.scale_velocities(sc)
+
+    def step_timing(self, reset=False):
+        ms, steps = 0.0, 0
+        for eng in self.engines:
+            m, k = eng.step_timing(reset)
+            ms, steps = ms + m, steps + k
+        return ms, steps
+
+    def stats(self):
+        out = None
+        for eng in self.engines:
+            st = eng.stats()
+            if out is None:
+                out = dict(st)
+            else:
+                for key in ("table_rebuilds", "candidate_pairs", "interacting_pairs", "launches", "reference_rebuilds",
+                            "trip_slots"):
+                    out[key] += st[key]
+        return out
+
+
 class _BatchedLJReplicas:
-    """The rank's replicas in one `chx_ljmd` engine (replica = blockIdx.y)."""
+    """The rank's replicas in one `chx_ljmd` engine (replica = blockIdx.y) -- or, for a handful of replicas per GPU,
+    in two engines that run concurrently (`_EngineGroups`)."""
 
     @classmethod
     def try_create(cls, ms: "MultiStateSampler"):
@@ -570,8 +694,13 @@ class _BatchedLJReplicas:
         self.kT_of_state = [kT_md(ts.temperature) for ts in ms._thermodynamic_states]
         states = ms._replica_thermodynamic_states
         kts = [self.kT_of_state[states[r]] for r in self.ids]
-        self.engine = LJLangevinEngine(self.n, box, sig[0], sig[1], sig[2], sig[3], self.dt, self.gamma, kts[0],
-                                       n_replicas=len(self.ids), device=dev)
+        groups = _engine_group_count(len(self.ids))
+        if groups > 1:
+            self.engine = _EngineGroups(groups, self.n, box, sig[0], sig[1], sig[2], sig[3], self.dt, self.gamma,
+                                        kts[0], len(self.ids), dev)
+        else:
+            self.engine = LJLangevinEngine(self.n, box, sig[0], sig[1], sig[2], sig[3], self.dt, self.gamma, kts[0],
+                                           n_replicas=len(self.ids), device=dev)
         topology = ms._thermodynamic_states[0].potential.topology
         mass = mass_tensor(topology, dev)
         xs, vs = [], []

@@ -52,10 +52,10 @@ def main():
         best = min(best, e0.elapsed_time(e1) / steps * 1e3)
     st = eng.stats()
     kms, ksteps = eng.step_timing()
-    print("TUNE nrep=%d n=%d persist=%s chunk=%s skin=%s force_us=%.2f step_us=%.2f kernel_us_per_step=%.2f lane_util=%.3f rebuilds=%d" % (
+    print("TUNE nrep=%d n=%d persist=%s chunk=%s skin=%s force_us=%.2f step_us=%.2f kernel_us_per_step=%.2f lane_util=%.3f rebuilds=%d cand_per_particle=%.1f trips_per_block=%.1f" % (
         R, n, os.environ.get("CHX_MD_PERSIST", "1"), os.environ.get("CHX_MD_CHUNK", "-"),
         os.environ.get("CHX_MD_SKIN", "-"), t_force, best, kms / max(ksteps, 1) * 1e3, st["lane_utilisation"],
-        st["table_rebuilds"]))
+        st["table_rebuilds"], 2.0 * st["candidate_pairs"] / (R * n), st["trip_slots"] / 64.0 / (R * st["blocks"])))
 
 
 if __name__ == "__main__":

@@ -124,6 +124,36 @@ def test_batched_replicas_match_serial_path(cuda_device, tmp_path):
     assert np.allclose(a._energy_thermodynamic_states, b._energy_thermodynamic_states, rtol=1e-5)
 
 
+def test_engine_groups_on_their_own_streams_match_one_engine(cuda_device, tmp_path, monkeypatch):
+    """A handful of replicas per GPU run as two (or three) engines on separate streams and host threads
+    (`_EngineGroups`): same swap history, positions and energies as the single engine."""
+    from chiron_b200.multistate import _EngineGroups
+    runs = {}
+    for groups in ("1", "2", "3"):
+        monkeypatch.setenv("CHX_REMD_ENGINE_GROUPS", groups)
+        ms, _, _ = _lj_replicas(6, 30, tmp_path, batched=True, exchange="neighbors")
+        ms.run(4)
+        assert ms._batched
+        assert isinstance(ms._batched.engine, _EngineGroups) == (groups != "1")
+        if groups != "1":
+            assert ms._batched.engine.G == int(groups)
+            assert sorted(sum(ms._batched.engine.members, [])) == list(range(6))
+        runs[groups] = (ms._replica_thermodynamic_states.copy(), np.array(ms._energy_thermodynamic_states),
+                        [st.positions.cpu().numpy() for st in ms.sampler_states],
+                        [st.velocities.cpu().numpy() for st in ms.sampler_states],
+                        [np.asarray(st._current_PRNG_key).copy() for st in ms.sampler_states])
+    monkeypatch.delenv("CHX_REMD_ENGINE_GROUPS")
+    for groups in ("2", "3"):
+        assert np.array_equal(runs["1"][0], runs[groups][0])
+        assert np.allclose(runs["1"][1], runs[groups][1], rtol=1e-5)
+        for xa, xb in zip(runs["1"][2], runs[groups][2]):
+            assert np.allclose(xa, xb, atol=5e-5)
+        for va, vb in zip(runs["1"][3], runs[groups][3]):
+            assert np.allclose(va, vb, atol=5e-4)
+        for ka, kb in zip(runs["1"][4], runs[groups][4]):
+            assert np.array_equal(ka, kb)
+
+
 def test_replica_exchange_energy_matrix_and_swaps(cuda_device, tmp_path):
     from chiron_b200 import unit
     ms, pot, temps = _lj_replicas(6, 20, tmp_path, batched=True, exchange="neighbors")
