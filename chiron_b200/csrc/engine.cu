@@ -89,6 +89,9 @@ struct chx_ljmd {
     long long rebuilds, steps, launches0;
     bool have_state;
     bool tables_fresh;               // the tables were built and no step has run since
+    int since_build;                 // batched replicas: steps run on the tables of the last chunk-start rebuild
+    int phase_num, phase_den;        // chx_ljmd_set_chunk_phase: since_build starts at CH * num / den after set_state
+    bool phase_pending;
     int* step_base;                  // device int: first step of the chunk a graph replay runs
     cudaStream_t cap_stream;
     cudaGraphExec_t chunk_graph;     // CH fused steps captured once; re-captured when the table shape changes
@@ -2549,7 +2552,17 @@ int chx_ljmd_set_state(chx_ljmd* md, const float* x, const float* v, const float
     if (rc != CHX_OK) return rc;
     md->have_state = true;
     md->tables_fresh = true;
+    md->since_build = 0;
+    md->phase_pending = true;
     md->forces_valid = true;
+    return CHX_OK;
+}
+
+int chx_ljmd_set_chunk_phase(chx_ljmd* md, int num, int den) {
+    CHX_REQUIRE(md && den > 0 && num >= 0 && num < den, "chunk phase must be a fraction in [0, 1)");
+    md->phase_num = num;
+    md->phase_den = den;
+    md->phase_pending = true;
     return CHX_OK;
 }
 
@@ -2763,9 +2776,15 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
             t = t_enq;
         }
     }
+    // The chunk grid of batched replicas is anchored at the last set_state, not at the start of the run: the tables
+    // live CH steps across run boundaries, and chx_ljmd_set_chunk_phase shifts the grid so that two engines that
+    // share a GPU do not rebuild at the same time.
+    if (proactive && md->phase_pending) {
+        md->since_build = md->phase_den > 0 ? ((int)((long long)CH * md->phase_num / md->phase_den) & ~1) : 0;
+        md->phase_pending = false;
+    }
     while (t < nsteps) {
-        const int te = nsteps - t < CH ? nsteps : t + CH;
-        if (proactive && !(t == 0 && md->tables_fresh)) {
+        if (proactive && md->since_build >= CH) {
             for (int r = 0; r < R; ++r) { md->rep_host[r].flag = 1; clear_build_stats(md->rep_host[r]); }
             rc = md_upload_rep(md);
             if (rc != CHX_OK) return rc;
@@ -2774,7 +2793,11 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
             for (int r = 0; r < R; ++r) md->rep_host[r].flag = 0;
             rc = md_upload_rep(md);
             if (rc != CHX_OK) return rc;
+            md->since_build = 0;
         }
+        const int room = proactive ? CH - md->since_build : CH;
+        const int te = nsteps - t < room ? nsteps : t + room;
+        if (proactive) md->since_build += te - t;
         md->tables_fresh = false;
         const bool replay = use_graph && te - t == CH && !(t & 1);
         if (replay && !md->tev0) { CHX_CUDA(cudaEventCreate(&md->tev0)); CHX_CUDA(cudaEventCreate(&md->tev1)); }

@@ -297,6 +297,12 @@ int chx_ljmd_get_state(chx_ljmd* md, float* x, float* v, float* force, float* re
  * Synchronises at the end. */
 int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_interval,
                  double* energies_dev, int n_reports_capacity);
+/* Batched replicas (R > 1) rebuild their tables together every CH steps, counted from the last set_state across
+ * runs.  A phase num/den in [0, 1) makes the first interval after set_state CH * (1 - num/den) steps long, so that
+ * two engines sharing one GPU (separate contexts and streams, one host thread each) rebuild at different times
+ * and each one's latency-bound rebuild overlaps the other's step kernels.  Takes effect at the next set_state /
+ * run.  No reference counterpart (the reference propagates replicas one after the other, multistate.py:497-510). */
+int chx_ljmd_set_chunk_phase(chx_ljmd* md, int num, int den);
 /* Replica exchange support (new; the reference's _perform_swap_proposals is a stub, multistate.py:447-460):
  * change the temperature each replica is thermostatted at (kT, kJ/mol, (R) host floats) and rescale
  * its velocities (v *= scale[r], e.g. sqrt(T_new / T_old)).  Coordinates never move between replicas. */

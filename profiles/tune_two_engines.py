@@ -33,6 +33,31 @@ def main():
     v0 = initialize_velocities(bench.TEMP_K * unit.kelvin, lj.topology, crandom.PRNGKey(11))
     v0 = v0.value_in_unit_system(unit.md_unit_system).cpu().numpy()
     keys = np.asarray(crandom.split(crandom.PRNGKey(1234), R), dtype=np.uint32).reshape(R, 2)
+    if os.environ.get("LOCKSTEP", "0") == "1":
+        # the product path: _EngineGroups.run joins all engines after every 100-step run (one REMD sweep)
+        from chiron_b200.multistate import _EngineGroups
+        eg = _EngineGroups(G, n, np.diag(box), bench.SIGMA, bench.EPS, bench.RC, bench.SKIN, bench.DT_PS, bench.GAMMA,
+                           kTs[0], R, dev)
+        if os.environ.get("NO_PHASE", "0") == "1":
+            for e in eg.engines:
+                e.set_chunk_phase(0, 1)
+        xt = torch.as_tensor(np.tile(x[None], (R, 1, 1)), device=dev)
+        vt = torch.as_tensor(np.tile(v0[None], (R, 1, 1)), device=dev)
+        eg.set_state(xt, vt, torch.full((n,), bench.MASS, dtype=torch.float32, device=dev), kTs)
+        for _ in range(3):
+            keys, _e = eg.run(100, keys)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            for _ in range(sweeps):
+                keys, _e = eg.run(100, keys)
+            torch.cuda.synchronize()
+            best = min(best, (time.perf_counter() - t0) / (sweeps * 100) * 1e6)
+        xs_ = eg.get_state()[0].cpu().numpy()
+        print("TWO lockstep nrep=%d groups=%d phase=%s us_per_step_all=%.2f ms_per_100_steps=%.3f checksum=%.6f" % (
+            R, G, os.environ.get("NO_PHASE", "0") != "1", best, best / 10.0, float(np.abs(xs_).sum())))
+        return
     groups = [list(range(g, R, G)) for g in range(G)]        # strided, like the rank sharding
     engines, streams, gkeys = [], [], []
     for ids in groups:

@@ -528,7 +528,7 @@ def test_fused_engine_batched_replicas(cuda_device):
         e1.close()
 
 
-@pytest.mark.parametrize("mode", ["proactive", "lookahead", "persistent"])
+@pytest.mark.parametrize("mode", ["proactive", "lookahead", "persistent", "shifted_grid"])
 def test_fused_engine_batched_replicas_step_loops(cuda_device, monkeypatch, mode):
     """The three step loops a batch of replicas can take without energy reports -- fresh tables for everybody at
     every 50-step chunk (default), halt-driven rebuilds per replica behind the look-ahead loop (CHX_MD_PROACTIVE=0)
@@ -550,10 +550,17 @@ def test_fused_engine_batched_replicas_step_loops(cuda_device, monkeypatch, mode
     if mode == "persistent":
         monkeypatch.setenv("CHX_MD_PERSIST", "1")
     eng = LJLangevinEngine(n, np.diag(box), sigma, eps, rc, 0.3, 0.002, 1.0, 2.494, n_replicas=R, internal_skin=0.04)
+    if mode == "shifted_grid":
+        # chx_ljmd_set_chunk_phase: the first chunk after set_state is 50 * (1 - 3/5) = 20 steps long, later
+        # chunks 50; the chunk grid carries over from run to run
+        eng.set_chunk_phase(3, 5)
     eng.set_state(np.stack(xs), np.stack(v0), mass, kts)
     kout, _ = eng.run(nsteps, np.stack(keys))
     xb, vb, _, _ = eng.get_state()
     assert eng.stats()["table_rebuilds"] >= 3
+    if mode == "shifted_grid":
+        with pytest.raises(Exception):
+            eng.set_chunk_phase(5, 5)
     eng.close()
     monkeypatch.delenv("CHX_MD_PROACTIVE", raising=False)
     monkeypatch.delenv("CHX_MD_PERSIST", raising=False)
