@@ -28,6 +28,7 @@ _SIGS = {
     "chx_ljmd_table_stats": [_P, C.POINTER(C.c_longlong)],
     "chx_ljmd_force_only": [_P, _I],
     "chx_ljmd_set_chunk_phase": [_P, _I, _I],
+    "chx_ljmd_set_gpu_share": [_P, _I],
     "chx_ljmd_step_timing": [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong), _I],
     "chx_fma_peak": [_P, _I, C.POINTER(C.c_double)],
 }
@@ -122,6 +123,10 @@ class LJLangevinEngine:
     def set_chunk_phase(self, num, den):
         """Shift the chunk grid of batched replicas by num/den of a chunk (engines that share a GPU)."""
         self._call("chx_ljmd_set_chunk_phase", int(num), int(den))
+
+    def set_gpu_share(self, n_engines):
+        """This engine shares the GPU with n_engines - 1 others running at the same time."""
+        self._call("chx_ljmd_set_gpu_share", int(n_engines))
 
     def force_only(self, repeats=1):
         self._call("chx_ljmd_force_only", int(repeats))

@@ -92,6 +92,7 @@ struct chx_ljmd {
     int since_build;                 // batched replicas: steps run on the tables of the last chunk-start rebuild
     int phase_num, phase_den;        // chx_ljmd_set_chunk_phase: since_build starts at CH * num / den after set_state
     bool phase_pending;
+    int gpu_share;                   // engines running concurrently on this GPU (chx_ljmd_set_gpu_share), 0/1 = alone
     int* step_base;                  // device int: first step of the chunk a graph replay runs
     cudaStream_t cap_stream;
     cudaGraphExec_t chunk_graph;     // CH fused steps captured once; re-captured when the table shape changes
@@ -2233,7 +2234,9 @@ static int md_force_split(const chx_ljmd* md) {
     }
     if (env == 1 || env == 2 || env == 4) return env;
     const long long warps = (long long)md->g.nblk * md->R;
-    const long long slots = 32LL * md->ctx->sm_count;       // resident warps at the kernel's register count
+    // resident warps at the kernel's register count; engines that run side by side on one GPU
+    // (chx_ljmd_set_gpu_share) split it between them
+    const long long slots = 32LL * md->ctx->sm_count / (md->gpu_share > 1 ? md->gpu_share : 1);
     // measured on B200 (profiles/r01_split_tune.log, gpurun r02 tune9): splitting costs 7-15 % once every SM
     // is full (N = 262,144: 46.1 / 49.4 / 53.2 us for 1 / 2 / 4) and gains 14 % on 8 x 8,192 particles, where
     // 2 warps per block (86 % of the warp slots, one wave) beat 4 (1.73 waves): 22.1 vs 22.8 us per step
@@ -2555,6 +2558,12 @@ int chx_ljmd_set_state(chx_ljmd* md, const float* x, const float* v, const float
     md->since_build = 0;
     md->phase_pending = true;
     md->forces_valid = true;
+    return CHX_OK;
+}
+
+int chx_ljmd_set_gpu_share(chx_ljmd* md, int n_engines) {
+    CHX_REQUIRE(md && n_engines >= 1 && n_engines <= 64, "gpu share must be 1..64 engines");
+    md->gpu_share = n_engines;
     return CHX_OK;
 }
 

@@ -517,12 +517,13 @@ def _engine_group_count(n_local: int) -> int:
     """Engines the rank's replicas are spread over.  Two engines on two streams, each driven by its own host
     thread, fill each other's gaps (kernel ramp and drain, the latency-bound launches and host round trips of a
     table rebuild).  Measured on one B200 through `_EngineGroups.run`, 100-step runs of n x 8,192 particles
-    (profiles/r02_scripts/two_engines_lockstep2.sh): n = 8: 2.99 -> 2.97 ms, 16: 4.47 -> 4.52, 32: 7.88 -> 7.20,
-    64: 13.76 -> 13.49.  So two engines from 32 replicas per GPU up.  CHX_REMD_ENGINE_GROUPS overrides."""
+    (profiles/r02_scripts/two_engines_lockstep2.sh, _lockstep4.sh): n = 8: 2.99 -> 2.97 ms, 16: 4.47 -> 4.32 (with
+    the blocks of each engine on one warp, `set_gpu_share`), 32: 7.88 -> 7.20, 64: 13.76 -> 13.49.  So two engines
+    from 16 replicas per GPU up.  CHX_REMD_ENGINE_GROUPS overrides."""
     env = os.environ.get("CHX_REMD_ENGINE_GROUPS")
     if env:
         return max(1, min(int(env), n_local))
-    return 2 if n_local >= 32 else 1
+    return 2 if n_local >= 16 else 1
 
 
 class _EngineGroups:
@@ -549,6 +550,7 @@ class _EngineGroups:
                     ctx = _lib.Context(self.device.index if self.device.index is not None else torch.cuda.current_device())
             self.engines.append(LJLangevinEngine(n, box, sigma, epsilon, cutoff, skin, dt, gamma, kT,
                                                  n_replicas=len(mem), device=self.device, ctx=ctx))
+            self.engines[-1].set_gpu_share(self.G)      # split blocks over warps for 1/G of the machine
             # (staggering the engines' table rebuilds with set_chunk_phase(g, G) was measured too: no gain, the
             # shortened chunks replay no graph -- profiles/r02_scripts/two_engines_lockstep.sh)
         self._pool = None

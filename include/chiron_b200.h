@@ -303,6 +303,10 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
  * and each one's latency-bound rebuild overlaps the other's step kernels.  Takes effect at the next set_state /
  * run.  No reference counterpart (the reference propagates replicas one after the other, multistate.py:497-510). */
 int chx_ljmd_set_chunk_phase(chx_ljmd* md, int num, int den);
+/* Tell an engine that n_engines engines (separate contexts / streams / host threads) step concurrently on its GPU:
+ * the number of warps a block is split over is then chosen for 1/n_engines of the machine.  No reference
+ * counterpart. */
+int chx_ljmd_set_gpu_share(chx_ljmd* md, int n_engines);
 /* Replica exchange support (new; the reference's _perform_swap_proposals is a stub, multistate.py:447-460):
  * change the temperature each replica is thermostatted at (kT, kJ/mol, (R) host floats) and rescale
  * its velocities (v *= scale[r], e.g. sqrt(T_new / T_old)).  Coordinates never move between replicas. */
