@@ -92,6 +92,8 @@ struct chx_ljmd {
     int since_build;                 // batched replicas: steps run on the tables of the last chunk-start rebuild
     int phase_num, phase_den;        // chx_ljmd_set_chunk_phase: since_build starts at CH * num / den after set_state
     bool phase_pending;
+    uint16_t* bwork;                 // per block: work estimate of its tiles (k_md_emit)
+    uint32_t* border;                // launch order of the step kernel: (replica << 20 | block), heaviest block first
     int gpu_share;                   // engines running concurrently on this GPU (chx_ljmd_set_gpu_share), 0/1 = alone
     int* step_base;                  // device int: first step of the chunk a graph replay runs
     cudaStream_t cap_stream;
@@ -803,7 +805,7 @@ __global__ void __launch_bounds__(128)
 k_md_emit(const uint32_t* __restrict__ cand_idx_all, const uint32_t* __restrict__ cand_col_all,
           const uint16_t* __restrict__ memb_all, const uint16_t* __restrict__ tmeta_all,
           const int* __restrict__ ntiles_all, const uint8_t* __restrict__ generic_all, MdGeom g, int ccap, int tcap,
-          int lw, uint32_t* __restrict__ tiles_all, MdRep* __restrict__ rep) {
+          int lw, uint32_t* __restrict__ tiles_all, MdRep* __restrict__ rep, uint16_t* __restrict__ bwork_all) {
     const int r = blockIdx.y;
     if (!rep[r].flag) return;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -860,6 +862,52 @@ k_md_emit(const uint32_t* __restrict__ cand_idx_all, const uint32_t* __restrict_
     if (!generic_all[rb]) slots += 32ull * 31ull;      // md_self_pairs: 31 directed pair slots per lane
 #endif
     if (lane == 0 && slots) atomicAdd(&rep[r].trip_slots, slots);
+    // work of the block in the step kernel, in packed trips: 34 instructions per trip, ~70 per tile
+    if (lane == 0) bwork_all[rb] = (uint16_t)min(65535ull, slots / 64ull + 2ull * (unsigned long long)T);
+}
+
+// Launch order of the step kernel: heaviest block first (longest-processing-time-first on the hardware's CTA
+// dispatcher, which hands out CTAs in index order), so that the blocks that start last -- the ones the launch ends
+// on -- are the short ones.  One CTA, counting sort over all replicas' blocks; the order inside a bin is arbitrary
+// (the result of a block does not depend on where it runs).
+#define MD_ORDER_BINS 1024
+__global__ void __launch_bounds__(1024) k_md_order(const uint16_t* __restrict__ bwork, uint32_t* __restrict__ border,
+                                                   int nblk, int total) {
+    __shared__ unsigned hist[MD_ORDER_BINS];
+    __shared__ unsigned wsum[32];
+    const int tid = threadIdx.x;
+    hist[tid] = 0u;
+    __syncthreads();
+    for (int k = tid; k < total; k += 1024) atomicAdd(&hist[MD_ORDER_BINS - 1 - min((int)bwork[k], MD_ORDER_BINS - 1)], 1u);
+    __syncthreads();
+    // exclusive scan of the 1024 bins (bin 0 = heaviest)
+    const unsigned v = hist[tid];
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(FULL, inc, o);
+        if ((tid & 31) >= o) inc += u;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+    __syncthreads();
+    if (tid < 32) {
+        const unsigned ws = wsum[tid];
+        unsigned winc = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(FULL, winc, o);
+            if (tid >= o) winc += u;
+        }
+        wsum[tid] = winc - ws;
+    }
+    __syncthreads();
+    hist[tid] = inc - v + wsum[tid >> 5];
+    __syncthreads();
+    for (int k = tid; k < total; k += 1024) {
+        const unsigned pos = atomicAdd(&hist[MD_ORDER_BINS - 1 - min((int)bwork[k], MD_ORDER_BINS - 1)], 1u);
+        const int r = k / nblk;
+        border[pos] = (uint32_t)r << 20 | (uint32_t)(k - r * nblk);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1550,7 +1598,8 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
            const uint32_t* __restrict__ tiles_all, const int* __restrict__ ntiles_all,
            const uint8_t* __restrict__ generic_all, const float4* __restrict__ bcenter_all, MdGeom g,
            LjConst lj, MdStepConst sc, int tcap, int tstride, MdRep* __restrict__ rep, int mode, int step_arg,
-           const int* __restrict__ step_base, int report_interval, int n_rep, double* __restrict__ energy_out) {
+           const int* __restrict__ step_base, int report_interval, int n_rep, double* __restrict__ energy_out,
+           const uint32_t* __restrict__ border) {
     __shared__ double red[SPLIT];
     __shared__ unsigned long long redn[SPLIT];
     __shared__ float4 part[SPLIT > 1 ? SPLIT - 1 : 1][32];
@@ -1558,14 +1607,20 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
     __shared__ __align__(128) uint32_t tile_sm[SPLIT][TILE_STAGES * 96];
     __shared__ __align__(8) unsigned long long tile_bar[SPLIT][TILE_STAGES];
 #endif
-    const int r = blockIdx.y;
+    // CTA -> (replica, block): heaviest block first (k_md_order); without an order, the grid coordinates
+    int r = blockIdx.y, b = blockIdx.x;
+    if (border) {
+        const uint32_t packed = border[blockIdx.y * gridDim.x + blockIdx.x];
+        r = (int)(packed >> 20);
+        b = (int)(packed & 0xfffffu);
+    }
     // Programmatic dependent launch (CHX_MD_PDL=1): inside a chunk the launch of step s + 1 is released when every
     // CTA of step s is past its tile loop, so its CTAs are resident (and have read the static table header below)
     // when step s drains; everything step s wrote is read after the wait.  Without the launch attribute the two
     // griddepcontrol instructions are no-ops.
-    const int nt_all = ntiles_all[(size_t)r * g.nblk + blockIdx.x];
-    const bool gen = generic_all[(size_t)r * g.nblk + blockIdx.x] != 0;
-    const float4 bc = bcenter_all[(size_t)r * g.nblk + blockIdx.x];
+    const int nt_all = ntiles_all[(size_t)r * g.nblk + b];
+    const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
+    const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int step = step_arg + (step_base ? *step_base : 0);   // graph replays read the chunk's first step
     if (mode == FMODE_STEP) {
@@ -1575,7 +1630,6 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
     const bool odd = mode != FMODE_ALL && (step & 1);
     const float4* xs_all = odd ? xs_b : xs_a;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x;
     float e_acc = 0.f;
     unsigned npair = 0;
     const float4* xs = xs_all + (size_t)r * g.np;
@@ -1973,6 +2027,9 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->tmeta, nb * md->tcap * sizeof(uint16_t)));
     CHX_CUDA(cudaMalloc(&md->ntiles, nb * sizeof(int)));
     CHX_CUDA(cudaMalloc(&md->generic, nb));
+    CHX_CUDA(cudaMalloc(&md->bwork, nb * sizeof(uint16_t)));
+    CHX_CUDA(cudaMemset(md->bwork, 0, nb * sizeof(uint16_t)));
+    CHX_CUDA(cudaMalloc(&md->border, nb * sizeof(uint32_t)));
     CHX_CUDA(cudaMalloc(&md->bcenter, nb * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->rep, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMalloc(&md->step_base, sizeof(int)));
@@ -2161,7 +2218,9 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
         CHX_LAUNCHED(ctx);
         k_md_emit<<<dim3(chx_div_up(g.nblk, 4), R), 128, 0, st>>>(
             md->cand_idx, md->cand_col, md->memb, md->tmeta, md->ntiles, md->generic, g, md_ccap(md), md->tcap, md->lw,
-            md->tiles, md->rep);
+            md->tiles, md->rep, md->bwork);
+        CHX_LAUNCHED(ctx);
+        k_md_order<<<1, 1024, 0, st>>>(md->bwork, md->border, g.nblk, R * g.nblk);
         CHX_LAUNCHED(ctx);
         int rc = md_download_rep(md);
         if (rc != CHX_OK) return rc;
@@ -2278,6 +2337,9 @@ static int md_force(chx_ljmd* md, int mode, int step, bool energy, int report_in
     cfg.stream = md->ctx->stream;
     cfg.attrs = attr;
     cfg.numAttrs = (pdl && upd && use_pdl) ? 1 : 0;
+    static int use_lpt = -1;
+    if (use_lpt < 0) { const char* e = getenv("CHX_MD_LPT"); use_lpt = e ? (e[0] == '1') : 1; }
+    const uint32_t* order = (use_lpt && g.nblk < (1 << 20) && md->R < (1 << 12)) ? md->border : nullptr;
     const LjConst ljc = md_lj(md);
     const MdStepConst stc = md_step_const(md);
     const int tstride = md_tstride(md);
@@ -2288,7 +2350,7 @@ static int md_force(chx_ljmd* md, int mode, int step, bool energy, int report_in
                                     md->refu, (const float4*)md->refi, (const uint32_t*)md->tiles,  \
                                     (const int*)md->ntiles, (const uint8_t*)md->generic,            \
                                     (const float4*)md->bcenter, g, ljc, stc, md->tcap, tstride, md->rep, mode, step, \
-                                    step_base, report_interval, md->R, e_dev));                     \
+                                    step_base, report_interval, md->R, e_dev, (const uint32_t*)order)); \
     } while (0)
 #define MD_FORCE_SPLIT(S)                                                                           \
     do {                                                                                            \
@@ -2513,7 +2575,7 @@ int chx_ljmd_destroy(chx_ljmd* md) {
     cudaFree(md->cell_start); cudaFree(md->cell_range); cudaFree(md->lin2h); cudaFree(md->h2lin);
     cudaFree(md->cell_of); cudaFree(md->order); cudaFree(md->tiles); cudaFree(md->ntiles);
     cudaFree(md->cand_idx); cudaFree(md->cand_col); cudaFree(md->cand_n); cudaFree(md->memb); cudaFree(md->tmeta);
-    cudaFree(md->generic); cudaFree(md->bcenter); cudaFree(md->rep); cudaFree(md->step_base);
+    cudaFree(md->generic); cudaFree(md->bwork); cudaFree(md->border); cudaFree(md->bcenter); cudaFree(md->rep); cudaFree(md->step_base);
     if (md->chunk_graph) cudaGraphExecDestroy(md->chunk_graph);
     cudaFree(md->xs_b);
     cudaFree(md->pbuf); cudaFree(md->part_cnt); cudaFree(md->ctl);
