@@ -437,6 +437,46 @@ def test_lj_langevin_single_and_few_steps_vs_oracle(cuda_device, fused, tmp_path
         assert eg.shape == en.shape and np.allclose(eg, en, rtol=1e-5)
 
 
+def test_fused_engine_anisotropic_box_vs_oracle(cuda_device):
+    """The replica shape of config 5 scaled down: a 7 x 7 x 14 lattice (686 particles: the last block is padded)
+    in a box with Lx = Ly = Lz / 2, small skin so the tables and the reference list are rebuilt on the way; 40 fused
+    steps against the oracle."""
+    from chiron_b200 import unit
+    from chiron_b200.integrators import LangevinIntegrator
+    from chiron_b200.neighbors import NeighborListNsqrd, OrthogonalPeriodicSpace
+    from chiron_b200.potential import LJPotential
+    from chiron_b200.states import SamplerState, ThermodynamicState
+    from chiron_b200.testsystems import LennardJonesFluid
+    from chiron_b200.utils import PRNG
+    nsteps, skin = 40, 0.03
+    lj_sys = LennardJonesFluid(cells=(7, 7, 14), reduced_density=0.8, sigma=0.34 * unit.nanometer, seed=47)
+    x = np.asarray(lj_sys.positions.value_in_unit(unit.nanometer), dtype=f32)
+    box = np.asarray(lj_sys.box_vectors.value_in_unit(unit.nanometer), dtype=f32)
+    L = np.diag(box)
+    assert x.shape[0] == 686 and abs(L[2] / L[0] - 2.0) < 1e-6 and L[0] > 2 * (1.02 + skin)
+    potential = LJPotential(lj_sys.topology, lj_sys.sigma, lj_sys.epsilon, 1.02 * unit.nanometer)
+    PRNG.set_seed(1234)
+    state = SamplerState(positions=lj_sys.positions, current_PRNG_key=PRNG.get_random_key(),
+                         box_vectors=lj_sys.box_vectors)
+    ts = ThermodynamicState(potential=potential, temperature=300 * unit.kelvin)
+    nl = NeighborListNsqrd(OrthogonalPeriodicSpace(), cutoff=1.02 * unit.nanometer, skin=skin * unit.nanometer,
+                           n_max_neighbors=180)
+    integ = LangevinIntegrator(timestep=2.0 * unit.femtosecond)
+    out, nl_out = integ.run(state, ts, number_of_steps=nsteps, nbr_list=nl)
+    assert integ.last_run_stats["path"] == "fused"
+    sigma, eps, rc = 0.34, 0.238 * 4.184, 1.02
+    nbr = dyn.OracleNeighborList(box, rc, skin, 180)
+    st = dyn.KeyedState(next(dyn.prng_stream(1234)))
+    force = lambda xx: pot.lj_force_nlist(xx, box, sigma, eps, rc, nbr.neighbor_list, nbr.neighbor_mask)  # noqa: E731
+    xo, vo, key, _ = dyn.langevin_run(x, None, np.full(x.shape[0], 39.948), 300.0, 0.002, 1.0, st, nsteps, force, nbr=nbr)
+    assert nbr.n_builds >= 2 and nl_out.n_builds == nbr.n_builds
+    dx = _np(out.positions) - xo
+    dx -= L * np.round(dx / L)
+    assert np.abs(dx).max() < 5e-5 * float(L.max())
+    assert np.allclose(_np(out.velocities), vo, rtol=0, atol=5e-4 * float(np.abs(vo).max()))
+    assert np.array_equal(np.asarray(out.current_PRNG_key), key)
+
+
 def test_fused_engine_rebuild_events_match_oracle(cuda_device):
     """Small skin so several rebuilds happen: the engine's reference-rebuild bookkeeping (count and
     final ref_positions), the lazily materialised list, and the trajectory all follow the oracle."""
