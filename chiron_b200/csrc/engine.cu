@@ -1107,6 +1107,7 @@ __device__ __forceinline__ void md_tile_loop(const float4* xs, const uint32_t* _
                                              int nt, int tstride_arg, const float4 xi0, const float4 xi,
                                              const float4 bc, const MdGeom& g, const LjConst& lj, int lane,
                                              float& fx, float& fy, float& fz, float& e_acc, unsigned& npair,
+                                             uint32_t code0, uint32_t la0, uint32_t lb0,
                                              uint32_t* tsm = nullptr, unsigned long long* tbar = nullptr) {
     static_assert(!BULK || (LW2 && !GEN), "bulk staging exists for the two-list-word, non-generic tile loop");
     // software pipeline over the tiles: index/list words are fetched two tiles ahead and the j
@@ -1145,7 +1146,7 @@ __device__ __forceinline__ void md_tile_loop(const float4* xs, const uint32_t* _
         code = tsm[lane]; la = tsm[32 + lane]; lb = tsm[64 + lane];
         xj = md_gather3(xs, code & 0xffffffu);
     } else {
-        code = pf[0]; la = pf[32]; lb = pf[64];
+        code = code0; la = la0; lb = lb0;         // words of the first tile: loaded by the caller with its prologue batch
         xj = md_gather3(xs, code & 0xffffffu);
         pf += tadv;
         code_n = pf[0]; la_n = pf[32]; lb_n = pf[64];
@@ -1614,33 +1615,45 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
         r = (int)(packed >> 20);
         b = (int)(packed & 0xfffffu);
     }
-    // Programmatic dependent launch (CHX_MD_PDL=1): inside a chunk the launch of step s + 1 is released when every
-    // CTA of step s is past its tile loop, so its CTAs are resident (and have read the static table header below)
-    // when step s drains; everything step s wrote is read after the wait.  Without the launch attribute the two
-    // griddepcontrol instructions are no-ops.
-    const int nt_all = ntiles_all[(size_t)r * g.nblk + b];
-    const bool gen = generic_all[(size_t)r * g.nblk + b] != 0;
-    const float4 bc = bcenter_all[(size_t)r * g.nblk + b];
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int step = step_arg + (step_base ? *step_base : 0);   // graph replays read the chunk's first step
-    if (mode == FMODE_STEP) {
-        // tables valid for x_lo .. x_{halt-1}; a halt raised by another warp of THIS launch is step + 1
-        if (!(rep[r].lo <= step && step < *((volatile int*)&rep[r].halt))) return;
-    }
-    const bool odd = mode != FMODE_ALL && (step & 1);
-    const float4* xs_all = odd ? xs_b : xs_a;
+    // Everything that depends on (replica, block) only is loaded in ONE batch, ahead of the control-block reads:
+    // the launch starts on cold caches with every warp in this prologue at once, so each level of dependent loads
+    // is a full L2 round trip of the whole machine (the fixed part of the launch, profiles section 7).  The
+    // position buffer follows from step_arg alone: graph replays start on even steps (*step_base is even).
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float e_acc = 0.f;
-    unsigned npair = 0;
+    const size_t rb = (size_t)r * g.nblk + b;
+    const bool odd = mode != FMODE_ALL && (step_arg & 1);
+    const float4* xs_all = odd ? xs_b : xs_a;
     const float4* xs = xs_all + (size_t)r * g.np;
     const int i = b * 32 + lane;
     const size_t o = (size_t)r * g.np + i;
+    const uint32_t* tp = tiles_all + rb * (size_t)(tcap + TILE_PAD) * tstride + (size_t)w * tstride;
+    const int nt_all = ntiles_all[rb];
+    const bool gen = generic_all[rb] != 0;
+    const float4 bc = bcenter_all[rb];
+    const uint32_t w_code = tp[lane], w_la = tp[32 + lane], w_lb = tp[64 + lane];   // first tile of this warp
     const float4 xi0 = xs[i];
+    // the control block in the same batch: {lo, halt, flag, fs_valid} and user_step[2] (volatile: a halt raised by
+    // another warp of THIS launch may already be there -- it is step + 1 and changes nothing)
+    static_assert(offsetof(MdRep, lo) % 16 == 0 && offsetof(MdRep, halt) == offsetof(MdRep, lo) + 4 &&
+                  offsetof(MdRep, fs_valid) == offsetof(MdRep, lo) + 12 && offsetof(MdRep, user_step) % 8 == 0 &&
+                  sizeof(MdRep) % 16 == 0, "MdRep layout vs the vector loads of k_md_force");
+    int c_lo, c_halt, c_flag, c_fsv, us0, us1;
+    asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(c_lo), "=r"(c_halt), "=r"(c_flag), "=r"(c_fsv) : "l"(&rep[r].lo));
+    asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(us0), "=r"(us1) : "l"(&rep[r].user_step[0]));
+    (void)c_flag;
+    const int step = step_arg + (step_base ? *step_base : 0);   // graph replays read the chunk's first step
+    if (mode == FMODE_STEP) {
+        // tables valid for x_lo .. x_{halt-1}
+        if (!(c_lo <= step && step < c_halt)) return;
+    }
+    float e_acc = 0.f;
+    unsigned npair = 0;
     float4 xi = xi0;
     // reference rebuild (neighbors.py:903-905 -> build): the update of step - 1 found a particle
     // skin/2 away from the reference positions, so x_step becomes the new reference
     bool took_ref = false;
-    if (mode != FMODE_ALL && step >= 1 && rep[r].user_step[(step - 1) & 1] == step - 1) {
+    if (mode != FMODE_ALL && step >= 1 && (((step - 1) & 1) ? us1 : us0) == step - 1) {
         took_ref = true;
         if (w == 0) {
             refu_all[o] = xi0;
@@ -1648,16 +1661,15 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
         }
     }
     float fx = 0.f, fy = 0.f, fz = 0.f;
-    if (UPDATE && step == 0 && rep[r].fs_valid) {
+    if (UPDATE && step == 0 && c_fsv) {
         // first step of a run: set_state / the previous run left F(x_0) in fs
         if (w == 0) { const float4 f0 = fs_all[o]; fx = f0.x; fy = f0.y; fz = f0.z; }
     } else {
-        const uint32_t* tp = tiles_all + ((size_t)r * g.nblk + b) * (size_t)(tcap + TILE_PAD) * tstride +
-                             (size_t)w * tstride;
         const bool lw2 = tstride == 96;
         const int nt = (nt_all - w + SPLIT - 1) / SPLIT;      // tiles w, w + SPLIT, ... < nt_all
         if (gen) {
-            md_tile_loop<ENERGY, true, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+            md_tile_loop<ENERGY, true, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair,
+                                                     w_code, w_la, w_lb);
         } else {
             xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
             xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
@@ -1668,12 +1680,14 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
             if (lw2)
 #if CHX_TILE_BULK
                 md_tile_loop<ENERGY, false, true, SPLIT, true>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy,
-                                                               fz, e_acc, npair, tile_sm[w], tile_bar[w]);
+                                                               fz, e_acc, npair, w_code, w_la, w_lb, tile_sm[w], tile_bar[w]);
 #else
-                md_tile_loop<ENERGY, false, true, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+                md_tile_loop<ENERGY, false, true, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair,
+                                                         w_code, w_la, w_lb);
 #endif
             else
-                md_tile_loop<ENERGY, false, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair);
+                md_tile_loop<ENERGY, false, false, SPLIT>(xs_all, tp, nt, tstride, xi0, xi, bc, g, lj, lane, fx, fy, fz, e_acc, npair,
+                                                          w_code, w_la, w_lb);
         }
         if (SPLIT > 1) {
             if (w > 0) part[w - 1][lane] = make_float4(fx, fy, fz, e_acc);
@@ -1711,7 +1725,6 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
             }
         }
     }
-    asm volatile("griddepcontrol.launch_dependents;");
     if (!UPDATE || w != 0) return;
     md_block_update(r, b, lane, o, step, xi0, fx, fy, fz, took_ref, const_cast<float4*>(odd ? xs_a : xs_b), vs_all,
                     refu_all, refi_all, g, sc, rep);
@@ -1838,7 +1851,7 @@ k_md_steps(const __grid_constant__ MdStepsArgs A) {
                     float4 xi = xi0;
                     if (gen) {
                         md_tile_loop<false, true, false, 1>(xs_cur, tp, tb - ta, A.tstride, xi0, xi, bc, g, A.lj, lane,
-                                                            fx, fy, fz, e_acc, npair);
+                                                            fx, fy, fz, e_acc, npair, tp[lane], tp[32 + lane], tp[64 + lane]);
                     } else {
                         xi.x -= g.box.lx * rintf((xi.x - bc.x) * g.inv_lx);
                         xi.y -= g.box.ly * rintf((xi.y - bc.y) * g.inv_ly);
@@ -1848,10 +1861,12 @@ k_md_steps(const __grid_constant__ MdStepsArgs A) {
 #endif
                         if (A.tstride == 96)
                             md_tile_loop<false, false, true, 1>(xs_cur, tp, tb - ta, A.tstride, xi0, xi, bc, g, A.lj,
-                                                                lane, fx, fy, fz, e_acc, npair);
+                                                                lane, fx, fy, fz, e_acc, npair, tp[lane], tp[32 + lane],
+                                                                tp[64 + lane]);
                         else
                             md_tile_loop<false, false, false, 1>(xs_cur, tp, tb - ta, A.tstride, xi0, xi, bc, g, A.lj,
-                                                                 lane, fx, fy, fz, e_acc, npair);
+                                                                 lane, fx, fy, fz, e_acc, npair, tp[lane], tp[32 + lane],
+                                                                 tp[64 + lane]);
                     }
                     if (cut) {
                         // publish the partial; the last piece to arrive adds them up in piece order
@@ -2319,24 +2334,17 @@ static MdStepConst md_step_const(const chx_ljmd* md) {
 }
 
 // FMODE_STEP launches the fused step (forces + BAOAB update); the other modes evaluate forces only
-// `pdl`: the launch may start while its predecessor in the stream drains (programmatic dependent launch);
-// only for a step kernel that follows another step kernel on tables older than both.
 static int md_force(chx_ljmd* md, int mode, int step, bool energy, int report_interval, double* e_dev,
-                    const int* step_base = nullptr, bool pdl = false) {
+                    const int* step_base = nullptr) {
     const MdGeom& g = md->g;
     const dim3 gf(g.nblk, md->R);
     const int split = md_force_split(md);
     const bool upd = mode == FMODE_STEP;
-    static int use_pdl = -1;
-    if (use_pdl < 0) { const char* e = getenv("CHX_MD_PDL"); use_pdl = e ? (e[0] == '1') : 0; }   // measured 0.6 us per step SLOWER (profiles/r02_step_kernel_ncu.md section 6): opt-in
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    // (Programmatic dependent launch of the steps inside a chunk was built and measured 0.5-0.7 us per step slower,
+    // profiles/r02_step_kernel_ncu.md section 6; removed.)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = gf;
     cfg.stream = md->ctx->stream;
-    cfg.attrs = attr;
-    cfg.numAttrs = (pdl && upd && use_pdl) ? 1 : 0;
     static int use_lpt = -1;
     if (use_lpt < 0) { const char* e = getenv("CHX_MD_LPT"); use_lpt = e ? (e[0] == '1') : 1; }
     const uint32_t* order = (use_lpt && g.nblk < (1 << 20) && md->R < (1 << 12)) ? md->border : nullptr;
@@ -2697,7 +2705,7 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     auto wants_energy = [&](int s) { return report && s >= 1 && (s - 1) % report_interval == 0; };
     auto launch_steps = [&](int s0, int s1, const int* base) -> int {
         for (int s = s0; s < s1; ++s) {
-            int rc2 = md_force(md, FMODE_STEP, s, wants_energy(s), rint, energies_dev, base, s > s0);
+            int rc2 = md_force(md, FMODE_STEP, s, wants_energy(s), rint, energies_dev, base);
             if (rc2 != CHX_OK) return rc2;
         }
         return CHX_OK;
