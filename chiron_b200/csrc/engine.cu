@@ -131,6 +131,36 @@ __device__ __forceinline__ int cell_coord_clamped(float x, float inv_c, int nc) 
     return c >= nc ? nc - 1 : c;
 }
 
+// -DCHX_TRACE=1 (profiles/r02_scripts/launch_trace.sh): every warp of ONE step-kernel launch records its start and
+// end time and its SM, for the occupancy-over-time picture of a launch.  Not compiled into the product library.
+#ifndef CHX_TRACE
+#define CHX_TRACE 0
+#endif
+#if CHX_TRACE
+__device__ unsigned long long* g_md_trace = nullptr;   // [warps of the launch][3]: t0, t1 (globaltimer ns), smid
+__device__ int g_md_trace_step = -1;
+__device__ __forceinline__ unsigned long long md_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+extern "C" int chx_debug_set_trace(void* buf, int step) {
+    if (cudaMemcpyToSymbol(g_md_trace, &buf, sizeof(buf)) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(g_md_trace_step, &step, sizeof(step)) == cudaSuccess ? 0 : -1;
+}
+#define MD_TRACE_END()                                                                              \
+    do {                                                                                            \
+        if (tr_on && (threadIdx.x & 31) == 0) {                                                     \
+            unsigned sm;                                                                            \
+            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));                                          \
+            unsigned long long* q = g_md_trace + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * SPLIT + (threadIdx.x >> 5)) * 3; \
+            q[0] = tr_t0; q[1] = md_globaltimer(); q[2] = sm;                                       \
+        }                                                                                           \
+    } while (0)
+#else
+#define MD_TRACE_END() do { } while (0)
+#endif
+
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -1608,6 +1638,10 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
     __shared__ __align__(128) uint32_t tile_sm[SPLIT][TILE_STAGES * 96];
     __shared__ __align__(8) unsigned long long tile_bar[SPLIT][TILE_STAGES];
 #endif
+#if CHX_TRACE
+    const unsigned long long tr_t0 = md_globaltimer();
+    const bool tr_on = g_md_trace != nullptr && mode == FMODE_STEP && step_arg == g_md_trace_step;
+#endif
     // CTA -> (replica, block): heaviest block first (k_md_order); without an order, the grid coordinates
     int r = blockIdx.y, b = blockIdx.x;
     if (border) {
@@ -1725,9 +1759,10 @@ k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, flo
             }
         }
     }
-    if (!UPDATE || w != 0) return;
+    if (!UPDATE || w != 0) { MD_TRACE_END(); return; }
     md_block_update(r, b, lane, o, step, xi0, fx, fy, fz, took_ref, const_cast<float4*>(odd ? xs_a : xs_b), vs_all,
                     refu_all, refi_all, g, sc, rep);
+    MD_TRACE_END();
 }
 
 // ---------------------------------------------------------------------------------------------
