@@ -147,7 +147,7 @@ class ClockSampler:
                     self._smi_sample()
             except Exception:
                 self.nvml = None
-            self.stop.wait(0.01 if self.nvml is not None else 0.2)
+            self.stop.wait(float(os.environ.get("CHX_BENCH_CLOCK_S", "0.01")) if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.thread.start()
