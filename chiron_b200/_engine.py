@@ -29,6 +29,7 @@ _SIGS = {
     "chx_ljmd_force_only": [_P, _I],
     "chx_ljmd_set_chunk_phase": [_P, _I, _I],
     "chx_ljmd_set_gpu_share": [_P, _I],
+    "chx_ljmd_set_prebuild": [_P, _I],
     "chx_ljmd_step_timing": [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong), _I],
     "chx_fma_peak": [_P, _I, C.POINTER(C.c_double)],
 }
@@ -127,6 +128,10 @@ class LJLangevinEngine:
     def set_gpu_share(self, n_engines):
         """This engine shares the GPU with n_engines - 1 others running at the same time."""
         self._call("chx_ljmd_set_gpu_share", int(n_engines))
+
+    def set_prebuild(self, on=True):
+        """Overlap the table rebuild a run ends on with the caller's work between two runs (replica exchange)."""
+        self._call("chx_ljmd_set_prebuild", int(bool(on)))
 
     def force_only(self, repeats=1):
         self._call("chx_ljmd_force_only", int(repeats))

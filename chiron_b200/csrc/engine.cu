@@ -94,6 +94,14 @@ struct chx_ljmd {
     bool phase_pending;
     uint16_t* bwork;                 // per block: work estimate of its tiles (k_md_emit)
     uint32_t* border;                // launch order of the step kernel: (replica << 20 | block), heaviest block first
+    // Pre-build (chx_ljmd_set_prebuild): a run of batched replicas that ends on stale tables enqueues the next
+    // rebuild on a side stream before it returns, so that it overlaps whatever the caller does between two runs
+    // (replica exchange: energies -> all-gather -> swap decisions).  The energies of the final positions are
+    // evaluated first, on the old tables, and cached for chx_ljmd_energy.
+    bool prebuild, prebuild_pending, e_cached;
+    cudaStream_t pre_stream;
+    cudaEvent_t pre_fork, pre_join;
+    double* e_cache;                 // [R] potential energies of the current positions (valid while e_cached)
     int gpu_share;                   // engines running concurrently on this GPU (chx_ljmd_set_gpu_share), 0/1 = alone
     int* step_base;                  // device int: first step of the chunk a graph replay runs
     cudaStream_t cap_stream;
@@ -2080,6 +2088,7 @@ static int md_alloc(chx_ljmd* md) {
     CHX_CUDA(cudaMalloc(&md->bwork, nb * sizeof(uint16_t)));
     CHX_CUDA(cudaMemset(md->bwork, 0, nb * sizeof(uint16_t)));
     CHX_CUDA(cudaMalloc(&md->border, nb * sizeof(uint32_t)));
+    CHX_CUDA(cudaMalloc(&md->e_cache, (size_t)md->R * sizeof(double)));
     CHX_CUDA(cudaMalloc(&md->bcenter, nb * sizeof(float4)));
     CHX_CUDA(cudaMalloc(&md->rep, md->R * sizeof(MdRep)));
     CHX_CUDA(cudaMalloc(&md->step_base, sizeof(int)));
@@ -2191,7 +2200,7 @@ static cudaError_t md_raise_smem_limit(K kernel, int device, size_t bytes, size_
 
 // sort + table build for the replicas whose rep_host[r].flag is set (rep_host must already be
 // uploaded); grows the table capacity on overflow.  Leaves rep_host refreshed.
-static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
+static int md_rebuild_sort(chx_ljmd* md, bool odd_possible) {
     chx_ctx* ctx = md->ctx;
     const MdGeom& g = md->g;
     cudaStream_t st = ctx->stream;
@@ -2223,9 +2232,17 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
         k_md_sync_odd<<<gp, 256, 0, st>>>(g, md->rep, md->xs, md->xs_b);
         CHX_LAUNCHED(ctx);
     }
+    return CHX_OK;
+}
+
+// table kernels of one build attempt: candidates -> deal -> tile words -> launch order
+static int md_tables_launch(chx_ljmd* md) {
+    chx_ctx* ctx = md->ctx;
+    const MdGeom& g = md->g;
+    cudaStream_t st = ctx->stream;
+    const int R = md->R;
     const float R_list = md->p.cutoff + md->internal_skin;
-    bool regrown = false;
-    for (int attempt = 0; attempt < 10; ++attempt) {
+    {
         int nw = 4;
         while (nw > 1 && md_build_smem(nw, md->qcap) > 200 * 1024) nw >>= 1;
         const size_t smem = md_build_smem(nw, md->qcap);
@@ -2272,7 +2289,23 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
         CHX_LAUNCHED(ctx);
         k_md_order<<<1, 1024, 0, st>>>(md->bwork, md->border, g.nblk, R * g.nblk);
         CHX_LAUNCHED(ctx);
-        int rc = md_download_rep(md);
+    }
+    return CHX_OK;
+}
+
+// build attempts until nothing overflows (grows the capacities in between); `first_launched`: the kernels of the
+// first attempt are already in the stream (pre-build).  Leaves rep_host refreshed.
+static int md_rebuild_tables(chx_ljmd* md, bool first_launched) {
+    chx_ctx* ctx = md->ctx;
+    const MdGeom& g = md->g;
+    cudaStream_t st = ctx->stream;
+    const int R = md->R;
+    const dim3 gp(chx_div_up(g.np, 256), R);
+    bool regrown = false;
+    for (int attempt = 0; attempt < 10; ++attempt) {
+        int rc = (attempt == 0 && first_launched) ? CHX_OK : md_tables_launch(md);
+        if (rc != CHX_OK) return rc;
+        rc = md_download_rep(md);
         if (rc != CHX_OK) return rc;
         int ovf = 0;
         for (int r = 0; r < R; ++r)
@@ -2332,6 +2365,61 @@ static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
     }
     chx_set_error("neighbour table overflow: more than %d candidates per block", md_ccap(md));
     return CHX_NEIGHBOR_OVERFLOW;
+}
+
+static int md_rebuild(chx_ljmd* md, bool odd_possible = false) {
+    int rc = md_rebuild_sort(md, odd_possible);
+    if (rc != CHX_OK) return rc;
+    return md_rebuild_tables(md, false);
+}
+
+// per-replica rebuild flag and build statistics set on the device (no host buffer in flight)
+__global__ void k_md_set_flags(MdRep* __restrict__ rep, int R, int flag, int clear_stats) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    rep[r].flag = flag;
+    if (clear_stats) { rep[r].overflow = 0; rep[r].cand_pairs2 = 0ull; rep[r].trip_slots = 0ull; }
+}
+
+// later work on the caller's stream must not touch the particle arrays while the pre-build re-sorts them
+static int md_prebuild_join_device(chx_ljmd* md) {
+    if (md->prebuild_pending) CHX_CUDA(cudaStreamWaitEvent(md->ctx->stream, md->pre_join, 0));
+    return CHX_OK;
+}
+
+// finish a pending pre-build: wait for it, look at its overflow bits, grow and rebuild if it did not fit
+static int md_prebuild_resolve(chx_ljmd* md) {
+    if (!md->prebuild_pending) return CHX_OK;
+    int rc = md_prebuild_join_device(md);
+    if (rc != CHX_OK) return rc;
+    md->prebuild_pending = false;
+    rc = md_rebuild_tables(md, true);           // starts with the download + overflow check of the launched attempt
+    if (rc != CHX_OK) return rc;
+    for (int r = 0; r < md->R; ++r) md->rep_host[r].flag = 0;
+    return md_upload_rep(md);
+}
+
+// enqueue sort + first build attempt for ALL replicas on the side stream, behind everything already in the
+// caller's stream; no host synchronisation
+static int md_prebuild_enqueue(chx_ljmd* md) {
+    chx_ctx* ctx = md->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!md->pre_stream) {
+        CHX_CUDA(cudaStreamCreateWithFlags(&md->pre_stream, cudaStreamNonBlocking));
+        CHX_CUDA(cudaEventCreateWithFlags(&md->pre_fork, cudaEventDisableTiming));
+        CHX_CUDA(cudaEventCreateWithFlags(&md->pre_join, cudaEventDisableTiming));
+    }
+    CHX_CUDA(cudaEventRecord(md->pre_fork, st));
+    CHX_CUDA(cudaStreamWaitEvent(md->pre_stream, md->pre_fork, 0));
+    ctx->stream = md->pre_stream;
+    k_md_set_flags<<<chx_div_up(md->R, 128), 128, 0, md->pre_stream>>>(md->rep, md->R, 1, 1);
+    int rc = md_rebuild_sort(md, false);
+    if (rc == CHX_OK) rc = md_tables_launch(md);
+    ctx->stream = st;
+    if (rc != CHX_OK) return rc;
+    CHX_CUDA(cudaEventRecord(md->pre_join, md->pre_stream));
+    md->prebuild_pending = true;
+    return CHX_OK;
 }
 
 // warps per block in the force kernel: CHX_FORCE_SPLIT (1, 2 or 4) or by the number of blocks in flight
@@ -2613,6 +2701,13 @@ int chx_ljmd_create(chx_ctx* ctx, const chx_ljmd_params* p, chx_ljmd** out) {
 int chx_ljmd_destroy(chx_ljmd* md) {
     if (!md) return CHX_OK;
     cudaStreamSynchronize(md->ctx->stream);
+    if (md->pre_stream) {
+        cudaStreamSynchronize(md->pre_stream);
+        cudaStreamDestroy(md->pre_stream);
+        cudaEventDestroy(md->pre_fork);
+        cudaEventDestroy(md->pre_join);
+    }
+    cudaFree(md->e_cache);
     cudaFree(md->xs); cudaFree(md->vs); cudaFree(md->refu); cudaFree(md->xs_t); cudaFree(md->vs_t);
     cudaFree(md->ru_t); cudaFree(md->fs_t); cudaFree(md->fs); cudaFree(md->refi); cudaFree(md->cell_count);
     cudaFree(md->cell_start); cudaFree(md->cell_range); cudaFree(md->lin2h); cudaFree(md->h2lin);
@@ -2640,6 +2735,9 @@ int chx_ljmd_set_state(chx_ljmd* md, const float* x, const float* v, const float
     chx_ctx* ctx = md->ctx;
     const MdGeom& g = md->g;
     cudaStream_t st = ctx->stream;
+    { int rcp = md_prebuild_join_device(md); if (rcp != CHX_OK) return rcp; }   // its tables are replaced below
+    md->prebuild_pending = false;
+    md->e_cached = false;
     for (int r = 0; r < md->R; ++r) {
         md->rep_host[r] = MdRep();
         md->rep_host[r].kT = kT_per_replica_host ? kT_per_replica_host[r] : md->p.kT;
@@ -2682,6 +2780,7 @@ int chx_ljmd_set_chunk_phase(chx_ljmd* md, int num, int den) {
 
 int chx_ljmd_get_state(chx_ljmd* md, float* x, float* v, float* force, float* ref_x) {
     CHX_REQUIRE(md && md->have_state, "engine has no state");
+    { int rcp = md_prebuild_join_device(md); if (rcp != CHX_OK) return rcp; }
     const MdGeom& g = md->g;
     const dim3 gp(chx_div_up(g.np, 256), md->R);
     cudaStream_t st = md->ctx->stream;
@@ -2705,9 +2804,12 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     const int n_reports = report ? (nsteps + report_interval - 1) / report_interval : 0;
     CHX_REQUIRE(!report || n_reports <= n_reports_capacity, "energy buffer too small");
     const int rint = report ? report_interval : 0;
+    int rc = md_prebuild_resolve(md);      // tables enqueued by the previous run (chx_ljmd_set_prebuild)
+    if (rc != CHX_OK) return rc;
+    md->e_cached = false;
     // upload loop keys (parity 0), reset per-run control.  Step s of this run reads the positions
     // from buffer s & 1 (x_0 is in md->xs) and writes x_{s+1} to the other one.
-    int rc = md_download_rep(md);
+    rc = md_download_rep(md);
     if (rc != CHX_OK) return rc;
     for (int r = 0; r < R; ++r) {
         MdRep& q = md->rep_host[r];
@@ -2955,12 +3057,37 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
     }
     md->forces_valid = true;
     md->steps += nsteps;
+    if (md->prebuild && proactive && !md->persist && md->since_build >= CH) {
+        // the next run would start with a rebuild: evaluate the energies of x_n on the tables that are still valid
+        // (the caller of a replica-exchange sweep asks for them next), then enqueue the rebuild on the side stream
+        CHX_CUDA(cudaMemsetAsync(md->e_cache, 0, sizeof(double) * R, st));
+        k_md_reset_pairs<<<chx_div_up(R, 128), 128, 0, st>>>(md->rep, R);
+        CHX_LAUNCHED(ctx);
+        rc = md_force(md, FMODE_ALL, -2, true, 0, md->e_cache);
+        if (rc != CHX_OK) return rc;
+        md->e_cached = true;
+        rc = md_prebuild_enqueue(md);
+        if (rc != CHX_OK) return rc;
+        md->since_build = 0;
+    }
+    return CHX_OK;
+}
+
+int chx_ljmd_set_prebuild(chx_ljmd* md, int on) {
+    CHX_REQUIRE(md, "engine is NULL");
+    md->prebuild = on != 0;
     return CHX_OK;
 }
 
 int chx_ljmd_energy(chx_ljmd* md, double* energy_dev) {
     CHX_REQUIRE(md && md->have_state && energy_dev, "engine has no state or energy_dev is NULL");
     cudaStream_t st = md->ctx->stream;
+    if (md->e_cached) {
+        // evaluated at the end of the last run, before its pre-build started to re-sort the particles
+        CHX_CUDA(cudaMemcpyAsync(energy_dev, md->e_cache, sizeof(double) * md->R, cudaMemcpyDeviceToDevice, st));
+        return CHX_OK;
+    }
+    { int rcp = md_prebuild_resolve(md); if (rcp != CHX_OK) return rcp; }
     CHX_CUDA(cudaMemsetAsync(energy_dev, 0, sizeof(double) * md->R, st));
     k_md_reset_pairs<<<chx_div_up(md->R, 128), 128, 0, st>>>(md->rep, md->R);   // no host round trip
     CHX_LAUNCHED(md->ctx);
@@ -2969,7 +3096,9 @@ int chx_ljmd_energy(chx_ljmd* md, double* energy_dev) {
 
 int chx_ljmd_stats(chx_ljmd* md, long long* stats_host) {
     CHX_REQUIRE(md && stats_host, "NULL argument");
-    int rc = md_download_rep(md);
+    int rc = md_prebuild_resolve(md);
+    if (rc != CHX_OK) return rc;
+    rc = md_download_rep(md);
     if (rc != CHX_OK) return rc;
     long long user = 0;
     unsigned long long cand2 = 0, int2 = 0;
@@ -3003,6 +3132,7 @@ int chx_ljmd_set_kt(chx_ljmd* md, const float* kT_per_replica_host) {
 
 int chx_ljmd_scale_velocities(chx_ljmd* md, const float* scale_per_replica_host) {
     CHX_REQUIRE(md && md->have_state && scale_per_replica_host, "engine has no state or scale is NULL");
+    { int rcp = md_prebuild_join_device(md); if (rcp != CHX_OK) return rcp; }   // the pre-build moves the velocities
     const MdGeom& g = md->g;
     for (int r0 = 0; r0 < md->R; r0 += MD_ARG_CHUNK) {
         MdFloatChunk c;
@@ -3026,7 +3156,9 @@ int chx_ljmd_step_timing(chx_ljmd* md, double* total_ms_host, long long* steps_h
 
 int chx_ljmd_table_stats(chx_ljmd* md, long long* out4) {
     CHX_REQUIRE(md && out4, "NULL argument");
-    int rc = md_download_rep(md);
+    int rc = md_prebuild_resolve(md);
+    if (rc != CHX_OK) return rc;
+    rc = md_download_rep(md);
     if (rc != CHX_OK) return rc;
     unsigned long long slots = 0;
     for (int r = 0; r < md->R; ++r) slots += md->rep_host[r].trip_slots;
@@ -3077,6 +3209,7 @@ extern "C" {
 
 int chx_ljmd_force_only(chx_ljmd* md, int repeats) {
     CHX_REQUIRE(md && md->have_state, "engine has no state");
+    { int rcp = md_prebuild_resolve(md); if (rcp != CHX_OK) return rcp; }
     for (int k = 0; k < repeats; ++k) {
         int rc = md_force(md, FMODE_ALL, -2, false, 0, nullptr);
         if (rc != CHX_OK) return rc;

@@ -610,6 +610,10 @@ class _EngineGroups:
             e[g::self.G] = eng.energy()
         return e
 
+    def set_prebuild(self, on=True):
+        for eng in self.engines:
+            eng.set_prebuild(on)
+
     def set_kT(self, kT_per_replica):
         for eng, mem in zip(self.engines, self.members):
             eng.set_kT([kT_per_replica[k] for k in mem])
@@ -706,6 +710,8 @@ class _BatchedLJReplicas:
         else:
             self.engine = LJLangevinEngine(self.n, box, sig[0], sig[1], sig[2], sig[3], self.dt, self.gamma, kts[0],
                                            n_replicas=len(self.ids), device=dev)
+        # the rebuild a sweep's propagation ends on runs beside the exchange phase (CHX_REMD_PREBUILD=0: off)
+        self.engine.set_prebuild(os.environ.get("CHX_REMD_PREBUILD", "1") != "0")
         topology = ms._thermodynamic_states[0].potential.topology
         mass = mass_tensor(topology, dev)
         xs, vs = [], []

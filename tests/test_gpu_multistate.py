@@ -154,6 +154,32 @@ def test_engine_groups_on_their_own_streams_match_one_engine(cuda_device, tmp_pa
             assert np.array_equal(ka, kb)
 
 
+@pytest.mark.parametrize("groups", ["1", "2"])
+def test_prebuild_beside_the_exchange_phase_changes_nothing(cuda_device, tmp_path, monkeypatch, groups):
+    """`chx_ljmd_set_prebuild`: the table rebuild a sweep's propagation ends on is enqueued on a side stream and
+    the energies come from the cache filled before it -- same tables, so the trajectories, energies, swap history
+    and keys are bit-identical to the run that rebuilds at the start of the next propagation."""
+    monkeypatch.setenv("CHX_REMD_ENGINE_GROUPS", groups)
+    runs = {}
+    for pre in ("0", "1"):
+        monkeypatch.setenv("CHX_REMD_PREBUILD", pre)
+        ms, _, _ = _lj_replicas(6, 100, tmp_path, batched=True, exchange="neighbors")
+        ms.run(4)
+        assert ms._batched
+        runs[pre] = (ms._replica_thermodynamic_states.copy(), np.array(ms._energy_thermodynamic_states),
+                     [st.positions.cpu().numpy() for st in ms.sampler_states],
+                     [st.velocities.cpu().numpy() for st in ms.sampler_states],
+                     [np.asarray(st._current_PRNG_key).copy() for st in ms.sampler_states],
+                     ms._reporter.get_property("u_kn").copy())
+    a, b = runs["0"], runs["1"]
+    assert np.array_equal(a[0], b[0])
+    assert np.allclose(a[1], b[1], rtol=1e-12)          # energies: fp64 atomics in any order
+    for k in (2, 3, 4):
+        for u, v in zip(a[k], b[k]):
+            assert np.array_equal(u, v)
+    assert np.allclose(a[5], b[5], rtol=1e-12)
+
+
 def test_replica_exchange_energy_matrix_and_swaps(cuda_device, tmp_path):
     from chiron_b200 import unit
     ms, pot, temps = _lj_replicas(6, 20, tmp_path, batched=True, exchange="neighbors")
