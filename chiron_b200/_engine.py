@@ -30,6 +30,7 @@ _SIGS = {
     "chx_ljmd_set_chunk_phase": [_P, _I, _I],
     "chx_ljmd_set_gpu_share": [_P, _I],
     "chx_ljmd_set_prebuild": [_P, _I],
+    "chx_ljmd_prebuild_now": [_P],
     "chx_ljmd_step_timing": [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong), _I],
     "chx_fma_peak": [_P, _I, C.POINTER(C.c_double)],
 }
@@ -129,9 +130,13 @@ class LJLangevinEngine:
         """This engine shares the GPU with n_engines - 1 others running at the same time."""
         self._call("chx_ljmd_set_gpu_share", int(n_engines))
 
-    def set_prebuild(self, on=True):
-        """Overlap the table rebuild a run ends on with the caller's work between two runs (replica exchange)."""
-        self._call("chx_ljmd_set_prebuild", int(bool(on)))
+    def set_prebuild(self, mode=1):
+        """Overlap the table rebuild a run ends on with the caller's work between two runs (replica exchange):
+        1 = enqueued by the run, 2 = enqueued by `prebuild_now()`, 0 = off."""
+        self._call("chx_ljmd_set_prebuild", int(mode))
+
+    def prebuild_now(self):
+        self._call("chx_ljmd_prebuild_now")
 
     def force_only(self, repeats=1):
         self._call("chx_ljmd_force_only", int(repeats))

@@ -99,6 +99,7 @@ struct chx_ljmd {
     // (replica exchange: energies -> all-gather -> swap decisions).  The energies of the final positions are
     // evaluated first, on the old tables, and cached for chx_ljmd_energy.
     bool prebuild, prebuild_pending, e_cached;
+    bool prebuild_manual, prebuild_due;   // manual: the caller says when (chx_ljmd_prebuild_now), e.g. behind its collective
     cudaStream_t pre_stream;
     cudaEvent_t pre_fork, pre_join;
     double* e_cache;                 // [R] potential energies of the current positions (valid while e_cached)
@@ -2388,7 +2389,13 @@ static int md_prebuild_join_device(chx_ljmd* md) {
 }
 
 // finish a pending pre-build: wait for it, look at its overflow bits, grow and rebuild if it did not fit
+static int md_prebuild_enqueue(chx_ljmd* md);
 static int md_prebuild_resolve(chx_ljmd* md) {
+    if (md->prebuild_due) {                 // manual mode and nobody asked: do it now
+        md->prebuild_due = false;
+        int rcq = md_prebuild_enqueue(md);
+        if (rcq != CHX_OK) return rcq;
+    }
     if (!md->prebuild_pending) return CHX_OK;
     int rc = md_prebuild_join_device(md);
     if (rc != CHX_OK) return rc;
@@ -2737,6 +2744,7 @@ int chx_ljmd_set_state(chx_ljmd* md, const float* x, const float* v, const float
     cudaStream_t st = ctx->stream;
     { int rcp = md_prebuild_join_device(md); if (rcp != CHX_OK) return rcp; }   // its tables are replaced below
     md->prebuild_pending = false;
+    md->prebuild_due = false;
     md->e_cached = false;
     for (int r = 0; r < md->R; ++r) {
         md->rep_host[r] = MdRep();
@@ -3066,17 +3074,29 @@ int chx_ljmd_run(chx_ljmd* md, int nsteps, uint32_t* keys_host, int report_inter
         rc = md_force(md, FMODE_ALL, -2, true, 0, md->e_cache);
         if (rc != CHX_OK) return rc;
         md->e_cached = true;
-        rc = md_prebuild_enqueue(md);
-        if (rc != CHX_OK) return rc;
         md->since_build = 0;
+        if (md->prebuild_manual) {
+            md->prebuild_due = true;        // chx_ljmd_prebuild_now, or the next run / state access
+        } else {
+            rc = md_prebuild_enqueue(md);
+            if (rc != CHX_OK) return rc;
+        }
     }
     return CHX_OK;
 }
 
-int chx_ljmd_set_prebuild(chx_ljmd* md, int on) {
-    CHX_REQUIRE(md, "engine is NULL");
-    md->prebuild = on != 0;
+int chx_ljmd_set_prebuild(chx_ljmd* md, int mode) {
+    CHX_REQUIRE(md && mode >= 0 && mode <= 2, "pre-build mode must be 0 (off), 1 (at the end of a run) or 2 (on request)");
+    md->prebuild = mode != 0;
+    md->prebuild_manual = mode == 2;
     return CHX_OK;
+}
+
+int chx_ljmd_prebuild_now(chx_ljmd* md) {
+    CHX_REQUIRE(md, "engine is NULL");
+    if (!md->prebuild_due) return CHX_OK;
+    md->prebuild_due = false;
+    return md_prebuild_enqueue(md);
 }
 
 int chx_ljmd_energy(chx_ljmd* md, double* energy_dev) {

@@ -106,17 +106,23 @@ class _RowGatherer:
                                     pin_memory=torch.cuda.is_available())
         return backend_dev
 
-    def __call__(self, rows: torch.Tensor) -> np.ndarray:
+    def __call__(self, rows: torch.Tensor, after_enqueue=None) -> np.ndarray:
+        """`after_enqueue`: called once the collective and the D2H copy are in the stream, before the host waits for
+        them (the engines enqueue their table pre-build there, behind the collective instead of in front of it)."""
         dev = self._buffers(rows)
         n_local = rows.shape[0]
         if self.world == 1:
             self.host[:n_local].copy_(rows, non_blocking=True)
+            if after_enqueue is not None:
+                after_enqueue()
             if rows.is_cuda:
                 torch.cuda.current_stream(rows.device).synchronize()
             return self.host[:n_local].numpy().copy()
         self.send[:n_local].copy_(rows if rows.device == dev else rows.to(dev), non_blocking=True)
         self.dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
         self.host.copy_(self.recv, non_blocking=True)
+        if after_enqueue is not None:
+            after_enqueue()
         if self.recv.is_cuda:
             torch.cuda.current_stream(self.recv.device).synchronize()
         flat = self.host.numpy().reshape(self.world, self.n_max, self.K)
@@ -359,7 +365,8 @@ class MultiStateSampler:
             # rows stay on the device until the gathered matrix comes back (one D2H per sweep)
             if self._row_gatherer is None or (self._row_gatherer.R, self._row_gatherer.K) != (self.number_of_replicas, K):
                 self._row_gatherer = _RowGatherer(self.number_of_replicas, K, policy=self.sharding)
-            self._energy_thermodynamic_states = self._row_gatherer(batched.reduced_potentials_device())
+            self._energy_thermodynamic_states = self._row_gatherer(batched.reduced_potentials_device(),
+                                                                   after_enqueue=batched.engine.prebuild_now)
             return
         rows = np.zeros((len(ids), K))
         for k, replica_id in enumerate(ids):
@@ -610,9 +617,13 @@ class _EngineGroups:
             e[g::self.G] = eng.energy()
         return e
 
-    def set_prebuild(self, on=True):
+    def set_prebuild(self, mode=1):
         for eng in self.engines:
-            eng.set_prebuild(on)
+            eng.set_prebuild(mode)
+
+    def prebuild_now(self):
+        for eng in self.engines:
+            eng.prebuild_now()
 
     def set_kT(self, kT_per_replica):
         for eng, mem in zip(self.engines, self.members):
@@ -711,7 +722,8 @@ class _BatchedLJReplicas:
             self.engine = LJLangevinEngine(self.n, box, sig[0], sig[1], sig[2], sig[3], self.dt, self.gamma, kts[0],
                                            n_replicas=len(self.ids), device=dev)
         # the rebuild a sweep's propagation ends on runs beside the exchange phase (CHX_REMD_PREBUILD=0: off)
-        self.engine.set_prebuild(os.environ.get("CHX_REMD_PREBUILD", "1") != "0")
+        # (2: enqueued by `_compute_energies` right behind the all-gather, 1: by the run itself)
+        self.engine.set_prebuild(int(os.environ.get("CHX_REMD_PREBUILD", "2")))
         topology = ms._thermodynamic_states[0].potential.topology
         mass = mass_tensor(topology, dev)
         xs, vs = [], []

@@ -307,13 +307,17 @@ int chx_ljmd_set_chunk_phase(chx_ljmd* md, int num, int den);
  * the number of warps a block is split over is then chosen for 1/n_engines of the machine.  No reference
  * counterpart. */
 int chx_ljmd_set_gpu_share(chx_ljmd* md, int n_engines);
-/* Pre-build (off by default).  When on, a run of batched replicas (R > 1) that ends with tables due for their
+/* Pre-build (mode 0 = off, the default).  When on, a run of batched replicas (R > 1) that ends with tables due for their
  * rebuild (a) evaluates the potential energies of the final positions on the tables that are still valid and keeps
  * them for the next chx_ljmd_energy, and (b) enqueues the rebuild on a side stream before it returns, so that it
  * overlaps what the caller does between two runs (a replica-exchange sweep: energies -> all-gather -> swap
  * decisions -> chx_ljmd_set_kt).  chx_ljmd_scale_velocities / get_state / set_state wait for it on the device, the
  * next chx_ljmd_run checks its overflow bits.  Same tables, same trajectories as without.  No reference counterpart. */
-int chx_ljmd_set_prebuild(chx_ljmd* md, int on);
+int chx_ljmd_set_prebuild(chx_ljmd* md, int mode);
+/* mode 2: the run only caches the energies; the rebuild is enqueued by chx_ljmd_prebuild_now -- e.g. right behind the
+ * caller's collective, so that the collective's kernel is not queued behind the rebuild's grids -- or, if that call
+ * never comes, by the next run.  mode 1: enqueued by the run itself.  mode 0: off. */
+int chx_ljmd_prebuild_now(chx_ljmd* md);
 /* Replica exchange support (new; the reference's _perform_swap_proposals is a stub, multistate.py:447-460):
  * change the temperature each replica is thermostatted at (kT, kJ/mol, (R) host floats) and rescale
  * its velocities (v *= scale[r], e.g. sqrt(T_new / T_old)).  Coordinates never move between replicas. */

@@ -1,7 +1,7 @@
 # pre-build: the rebuild a sweep ends on runs beside the exchange phase (CHX_REMD_PREBUILD=0/1)
 python -c "import __graft_entry__ as g; g.build()"
 timeout 900 python -m pytest tests/test_gpu_multistate.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -6
-for P in 0 1 0 1; do
+for P in 0 1 2 1 2; do
   CHX_REMD_PREBUILD=$P timeout 600 python bench.py --steps 2 --warmup 1 --inner 200 --no-mc --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
 import json,sys
 d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); r=d['remd']; p=r['phases_rank0']

@@ -161,7 +161,7 @@ def test_prebuild_beside_the_exchange_phase_changes_nothing(cuda_device, tmp_pat
     and keys are bit-identical to the run that rebuilds at the start of the next propagation."""
     monkeypatch.setenv("CHX_REMD_ENGINE_GROUPS", groups)
     runs = {}
-    for pre in ("0", "1"):
+    for pre in ("0", "1", "2"):
         monkeypatch.setenv("CHX_REMD_PREBUILD", pre)
         ms, _, _ = _lj_replicas(6, 100, tmp_path, batched=True, exchange="neighbors")
         ms.run(4)
@@ -171,13 +171,14 @@ def test_prebuild_beside_the_exchange_phase_changes_nothing(cuda_device, tmp_pat
                      [st.velocities.cpu().numpy() for st in ms.sampler_states],
                      [np.asarray(st._current_PRNG_key).copy() for st in ms.sampler_states],
                      ms._reporter.get_property("u_kn").copy())
-    a, b = runs["0"], runs["1"]
-    assert np.array_equal(a[0], b[0])
-    assert np.allclose(a[1], b[1], rtol=1e-12)          # energies: fp64 atomics in any order
-    for k in (2, 3, 4):
-        for u, v in zip(a[k], b[k]):
-            assert np.array_equal(u, v)
-    assert np.allclose(a[5], b[5], rtol=1e-12)
+    for mode in ("1", "2"):                              # 1: enqueued by the run, 2: behind the all-gather
+        a, b = runs["0"], runs[mode]
+        assert np.array_equal(a[0], b[0])
+        assert np.allclose(a[1], b[1], rtol=1e-12)      # energies: fp64 atomics in any order
+        for k in (2, 3, 4):
+            for u, v in zip(a[k], b[k]):
+                assert np.array_equal(u, v)
+        assert np.allclose(a[5], b[5], rtol=1e-12)
 
 
 def test_replica_exchange_energy_matrix_and_swaps(cuda_device, tmp_path):
