@@ -98,3 +98,44 @@ def test_two_ranks_gloo_agree_with_single_process(built_library, tmp_path, polic
         states = neighbor_swaps(u_full * (1.0 + 0.01 * it), states, it, seed=11)
         assert np.array_equal(states, h0[it - 1])
     assert np.allclose(np.load(tmp_path / "u0.npy"), u_full * 1.05)
+
+
+def _gatherer_worker(rank, world, port, R, K, out_dir, policy):
+    import torch
+    from chiron_b200.multistate import _RowGatherer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    full = rng.normal(size=(R, K))
+    ids = shard_ids(R, world, rank, policy)
+    g = _RowGatherer(R, K, policy=policy)
+    calls = []
+    outs = []
+    for it in range(3):            # persistent buffers: several sweeps through the same gatherer
+        rows = torch.from_numpy(full[ids] + it)
+        outs.append(g(rows, after_enqueue=lambda: calls.append(it)))
+    assert calls == [0, 1, 2]      # once per sweep, before the host waits for the matrix
+    np.save(os.path.join(out_dir, f"g{rank}.npy"), np.array(outs))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("policy", ["contiguous", "strided"])
+def test_row_gatherer_two_ranks_gloo(built_library, tmp_path, policy):
+    """`_RowGatherer` (the device-row all-gather of the REMD exchange, here on host tensors over gloo): uneven shards,
+    both sharding policies, the `after_enqueue` hook the table pre-build hangs on."""
+    R, K, world = 7, 5, 2
+    mp.spawn(_gatherer_worker, args=(world, _free_port(), R, K, str(tmp_path), policy), nprocs=world, join=True)
+    g0, g1 = np.load(tmp_path / "g0.npy"), np.load(tmp_path / "g1.npy")
+    full = np.random.default_rng(5).normal(size=(R, K))
+    for it in range(3):
+        assert np.array_equal(g0[it], full + it) and np.array_equal(g1[it], full + it)
+
+
+def test_row_gatherer_single_process_hook():
+    import torch
+    from chiron_b200.multistate import _RowGatherer
+    rows = torch.arange(12, dtype=torch.float64).reshape(4, 3)
+    calls = []
+    out = _RowGatherer(4, 3)(rows, after_enqueue=lambda: calls.append(1))
+    assert calls == [1] and np.array_equal(out, rows.numpy())
