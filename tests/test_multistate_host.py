@@ -139,3 +139,15 @@ def test_row_gatherer_single_process_hook():
     calls = []
     out = _RowGatherer(4, 3)(rows, after_enqueue=lambda: calls.append(1))
     assert calls == [1] and np.array_equal(out, rows.numpy())
+
+
+def test_engine_group_rule(monkeypatch):
+    """Two engines per GPU from 16 local replicas up (measured, profiles/r02_step_kernel_ncu.md section 7); the
+    environment override is clamped to the number of replicas."""
+    from chiron_b200.multistate import _engine_group_count
+    monkeypatch.delenv("CHX_REMD_ENGINE_GROUPS", raising=False)
+    assert [_engine_group_count(n) for n in (1, 8, 15, 16, 32, 64)] == [1, 1, 1, 2, 2, 2]
+    monkeypatch.setenv("CHX_REMD_ENGINE_GROUPS", "4")
+    assert _engine_group_count(64) == 4 and _engine_group_count(3) == 3
+    monkeypatch.setenv("CHX_REMD_ENGINE_GROUPS", "0")
+    assert _engine_group_count(8) == 1
