@@ -1631,8 +1631,13 @@ __device__ __forceinline__ bool md_block_update(int r, int b, int lane, size_t o
 #ifndef CHX_FORCE_WARPS_PER_SM
 #define CHX_FORCE_WARPS_PER_SM 32   // resident warps per SM the step kernel is compiled for (register budget 65536 / (32 * this))
 #endif
+// Several warps per block are only used while the blocks do not fill the machine (md_force_split), so those variants
+// trade resident warps for registers: 28 warps per SM = 72 registers instead of 64 and no spills around the tile loop.
+#ifndef CHX_SPLIT_WARPS_PER_SM
+#define CHX_SPLIT_WARPS_PER_SM 28
+#endif
 template <bool ENERGY, int SPLIT, bool UPDATE>
-__global__ void __launch_bounds__(SPLIT * 32, CHX_FORCE_WARPS_PER_SM / SPLIT)
+__global__ void __launch_bounds__(SPLIT * 32, (SPLIT == 1 ? CHX_FORCE_WARPS_PER_SM : CHX_SPLIT_WARPS_PER_SM) / SPLIT)
 k_md_force(const float4* __restrict__ xs_a, const float4* __restrict__ xs_b, float4* __restrict__ fs_all,
            float4* __restrict__ vs_all, float4* __restrict__ refu_all, const float4* __restrict__ refi_all,
            const uint32_t* __restrict__ tiles_all, const int* __restrict__ ntiles_all,
@@ -2445,8 +2450,9 @@ static int md_force_split(const chx_ljmd* md) {
     // is full (N = 262,144: 46.1 / 49.4 / 53.2 us for 1 / 2 / 4) and gains 14 % on 8 x 8,192 particles, where
     // 2 warps per block (86 % of the warp slots, one wave) beat 4 (1.73 waves): 22.1 vs 22.8 us per step
     // the largest split that still fits one wave of resident warps
-    if (4 * warps <= slots) return 4;
-    if (2 * warps <= slots) return 2;
+    const long long slots_split = slots * CHX_SPLIT_WARPS_PER_SM / 32;   // the split variants hold fewer warps per SM
+    if (4 * warps <= slots_split) return 4;
+    if (2 * warps <= slots_split) return 2;
     return 1;
 }
 
